@@ -1,0 +1,138 @@
+"""Pins the oracle (oracle/*.c) against the UNMODIFIED reference build (oracle/_ref, compiled from /root/reference).
+CPU only. Skipped when oracle/_ref has not been built (it is built by __graft_entry__.build() in the dev container)."""
+import numpy as np
+import pytest
+import oracle_lib as O
+
+pytestmark = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+
+EXT, RIGHT, REVC, APPROX, GENERIC = 0x40, 0x02, 0x80, 0x08, 0x04
+
+
+def rand_pair(rng, qlen, err):
+    t = rng.integers(0, 4, qlen + rng.integers(0, 30)).astype(np.uint8)
+    q = O.mutate(t, rng, err=err)
+    if len(q) == 0:
+        q = np.array([0], dtype=np.uint8)
+    return q, t
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_extd2_matches_reference(seed):
+    rng = np.random.default_rng(100 + seed)
+    mat = O.simple_mat(2, 4, 1)
+    n = 0
+    for it in range(120):
+        qlen = int(rng.integers(1, 400))
+        q, t = rand_pair(rng, qlen, err=float(rng.choice([0.0, 0.05, 0.15, 0.4])))
+        if rng.random() < 0.2:  # sprinkle N
+            q[rng.integers(0, len(q))] = 4
+            t[rng.integers(0, len(t))] = 4
+        if rng.random() < 0.15:  # unrelated tail to trigger z-drop
+            q = np.concatenate([q, rng.integers(0, 4, 300).astype(np.uint8)])
+            t = np.concatenate([t, rng.integers(0, 4, 300).astype(np.uint8)])
+        w = int(rng.choice([-1, 5, 17, 40, 100, 751, 30001]))
+        zdrop = int(rng.choice([-1, 50, 200, 400]))
+        eb = int(rng.choice([-1, 0, 10]))
+        flag = int(rng.choice([0, APPROX, EXT, EXT | RIGHT | REVC, RIGHT, EXT | RIGHT, APPROX | RIGHT]))
+        a = O.oracle_extd2(q, t, mat, 4, 2, 24, 1, w, zdrop, eb, flag)
+        b = O.ref_extd2(q, t, mat, 4, 2, 24, 1, w, zdrop, eb, flag)
+        assert a == b, (it, len(q), len(t), w, zdrop, eb, flag)
+        n += 1
+    assert n == 120
+
+
+def test_extd2_other_scoring_and_generic():
+    rng = np.random.default_rng(7)
+    for (a_, b_, q, e, q2, e2, ts) in [(1, 4, 6, 2, 26, 1, 0), (1, 19, 39, 3, 81, 1, 0), (2, 6, 10, 2, 50, 1, 4), (1, 2, 2, 1, 32, 0, 0)]:
+        mat = O.simple_mat(a_, b_, 1, ts)
+        for it in range(40):
+            qq, tt = rand_pair(rng, int(rng.integers(1, 300)), err=0.1)
+            w = int(rng.choice([-1, 20, 200, 30001]))
+            flag = int(rng.choice([0, APPROX, EXT, EXT | RIGHT | REVC]))
+            if ts:
+                flag |= GENERIC
+            x = O.oracle_extd2(qq, tt, mat, q, e, q2, e2, w, 200, -1, flag)
+            y = O.ref_extd2(qq, tt, mat, q, e, q2, e2, w, 200, -1, flag)
+            assert x == y, (a_, b_, it, w, flag)
+
+
+def test_extd2_long_band_limited():
+    """end-extension shape: long sequences, w=751 so the band limits st0/en0 and 16-lane edge artefacts are live"""
+    rng = np.random.default_rng(11)
+    mat = O.simple_mat(2, 4, 1)
+    for it in range(6):
+        t = rng.integers(0, 4, 2500).astype(np.uint8)
+        q = O.mutate(t, rng, err=0.12)
+        for flag in (EXT, EXT | RIGHT | REVC, 0):
+            for w in (751, 100, 33):
+                x = O.oracle_extd2(q, t, mat, 4, 2, 24, 1, w, 400, -1, flag)
+                y = O.ref_extd2(q, t, mat, 4, 2, 24, 1, w, 400, -1, flag)
+                assert x == y, (it, flag, w)
+
+
+def test_ll_i16():
+    rng = np.random.default_rng(3)
+    mat = O.simple_mat(2, 4, 1)
+    for it in range(300):
+        qq, tt = rand_pair(rng, int(rng.integers(1, 200)), err=float(rng.choice([0.0, 0.1, 0.3])))
+        if rng.random() < 0.3:
+            tt = np.concatenate([rng.integers(0, 4, int(rng.integers(0, 50))).astype(np.uint8), tt])
+        assert O.oracle_ll_i16(qq, tt, mat, 4, 2) == O.ref_ll_i16(qq, tt, mat, 4, 2), it
+
+
+@pytest.mark.parametrize("w,k,hpc", [(10, 15, 0), (5, 15, 0), (19, 19, 0), (10, 14, 0), (11, 21, 0), (10, 19, 1), (3, 4, 0), (50, 28, 0)])
+def test_sketch(w, k, hpc):
+    rng = np.random.default_rng(w * 100 + k)
+    for it in range(60):
+        n = int(rng.integers(1, 3000))
+        alphabet = rng.choice([b"ACGT", b"ACGTN", b"AT", b"ACGTacgtNn", b"AC"])
+        s = bytes(rng.choice(list(alphabet), n).astype(np.uint8))
+        if rng.random() < 0.3:  # low complexity stretch
+            s = s[: n // 2] + b"AT" * 40 + b"A" * 30 + s[n // 2:]
+        a = O.oracle_sketch(s, w, k, rid=it, is_hpc=hpc)
+        b = O.ref_sketch(s, w, k, rid=it, is_hpc=hpc)
+        assert a.shape == b.shape and (a == b).all(), (it, n)
+
+
+def test_radix_sort_tie_order():
+    rng = np.random.default_rng(5)
+    for it in range(200):
+        n = int(rng.integers(0, 3000))
+        bits = int(rng.choice([2, 6, 12, 20, 40, 64]))
+        x = rng.integers(0, 2 ** min(bits, 63), n, dtype=np.uint64)
+        if bits == 64:
+            x = x * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+        a = np.stack([x, np.arange(n, dtype=np.uint64)], axis=1)
+        assert (O.oracle_sort128(a) == O.ref_sort128(a)).all(), it
+
+
+def make_anchors(rng, n_chain=3, n_noise=200, qlen=10000, span=15):
+    """anchors: x = rev<<63|rid<<32|rpos, y = span<<32|qpos; sorted by x with the reference's own sort"""
+    rows = []
+    for c in range(n_chain):
+        rid = int(rng.integers(0, 3)); rev = int(rng.integers(0, 2))
+        r0 = int(rng.integers(1000, 100000)); q = int(rng.integers(20, 200)); r = r0
+        while q < qlen - 50:
+            rows.append(((rev << 63) | (rid << 32) | r, (span << 32) | q))
+            if rng.random() < 0.1:  # duplicate ref position (tie in x)
+                rows.append(((rev << 63) | (rid << 32) | r, (span << 32) | (q + int(rng.integers(1, 30)))))
+            step = int(rng.integers(1, 120))
+            q += step; r += step + int(rng.integers(-6, 7)) * int(rng.random() < 0.3)
+    for _ in range(n_noise):
+        rows.append(((int(rng.integers(0, 2)) << 63) | (int(rng.integers(0, 3)) << 32) | int(rng.integers(0, 200000)),
+                     (span << 32) | int(rng.integers(span, qlen))))
+    a = np.array(rows, dtype=np.uint64).reshape(-1, 2)
+    return O.ref_sort128(a)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lchain_dp(seed):
+    rng = np.random.default_rng(40 + seed)
+    for it in range(25):
+        a = make_anchors(rng, n_chain=int(rng.integers(1, 5)), n_noise=int(rng.integers(0, 400)))
+        for (mdx, mdy, bw, skip, iters, mincnt, minsc, is_cdna) in [(5000, 5000, 500, 25, 5000, 3, 40, 0), (2000, 2000, 2000, 25, 50, 3, 100, 0), (200000, 2000, 200000, 25, 5000, 3, 40, 1)]:
+            pg = np.float32(np.float32(0.8) * 0.01 * 15)
+            x = O.oracle_lchain_dp(a, mdx, mdy, bw, skip, iters, mincnt, minsc, float(pg), 0.0, is_cdna)
+            y = O.ref_lchain_dp(a, mdx, mdy, bw, skip, iters, mincnt, minsc, float(pg), 0.0, is_cdna)
+            assert (x[0] == y[0]).all() and x[1].shape == y[1].shape and (x[1] == y[1]).all(), (it, mdx)

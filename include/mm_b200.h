@@ -1,0 +1,121 @@
+/* include/mm_b200.h -- the C-ABI boundary between host C (the minimap.h API, include/minimap.h) and the
+ * hand-written sm_100a CUDA kernels of the seed-chain-extend hot path.
+ *
+ * Plain C: pointers, sizes, PODs. No C++/torch types cross this line. Every entry point names the reference
+ * interface it replaces (file:line under lh3/minimap2 v2.30). The library is libminimap2_b200.so
+ * (minimap2_b200/csrc). A CUDA failure prints to stderr (when mm_verbose>=1) and abort()s, matching the
+ * reference's no-error-code convention on the map path (misc.c:123-151, kalloc.c:32-36). If no CUDA device is
+ * present every entry point below fails loudly (returns <0 from mmb_init / aborts elsewhere); there is NO CPU fallback.
+ */
+#ifndef MM_B200_H
+#define MM_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device / context
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct mmb_ctx_s mmb_ctx_t; /* one per GPU (one process per GPU); owns streams and arenas */
+
+/* returns 0 on success, <0 when no usable CUDA device (fails loudly; nothing else may be called) */
+int  mmb_device_count(void);
+mmb_ctx_t *mmb_ctx_create(int device);          /* NULL + message on failure */
+void mmb_ctx_destroy(mmb_ctx_t *ctx);
+void *mmb_ctx_stream(mmb_ctx_t *ctx);           /* cudaStream_t the kernels are launched on (for CUDA-event timing) */
+/* counters: kernels launched by this library since creation / last reset (bench.py "gpu_launches") */
+uint64_t mmb_launch_count(mmb_ctx_t *ctx, int reset);
+/* accumulated device time (ms, CUDA events on the launch stream) per kernel family since last reset;
+ * which: 0 sketch, 1 seed, 2 sort, 3 chain, 4 ksw(extd2), 5 other. Only valid when profiling was enabled. */
+void  mmb_profile_enable(mmb_ctx_t *ctx, int on);
+double mmb_profile_ms(mmb_ctx_t *ctx, int which, int reset);
+uint64_t mmb_profile_units(mmb_ctx_t *ctx, int which, int reset); /* algorithmic units: bases, anchors, DP cells.. */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K3: ksw2 extension kernels   (replaces ksw_extd2_sse ksw2_extd2_sse.c:27-401, ksw_ll_i16 ksw2_ll_sse.c:85-152,
+ *                                dispatched like mm_align_pair align.c:336-368)
+ * --------------------------------------------------------------------------------------------------------- */
+#define MMB_KSW_SCORE_ONLY   0x01   /* = KSW_EZ_* (ksw2.h:8-20) */
+#define MMB_KSW_RIGHT        0x02
+#define MMB_KSW_GENERIC_SC   0x04
+#define MMB_KSW_APPROX_MAX   0x08
+#define MMB_KSW_APPROX_DROP  0x10
+#define MMB_KSW_EXTZ_ONLY    0x40
+#define MMB_KSW_REV_CIGAR    0x80
+/* job-level addressing flags (how the kernel walks the resident sequences) */
+#define MMB_JOB_Q_COMP       0x10000 /* complement query bases (3-c, N stays 4): reverse strand (align.c:1056-1061) */
+#define MMB_JOB_LL           0x20000 /* run ksw_ll_i16 (local score) instead of extd2 */
+
+typedef struct {
+	int64_t q_start;   /* index of the first query base of this job in the query byte array (nt4 codes, 1 B/base) */
+	int64_t t_start;   /* index of the first target base (bases; 4-bit packed S or byte array, see t_packed) */
+	int32_t q_step;    /* +1 or -1: direction the query is walked (mm_seq_rev for left extension, align.c:787) */
+	int32_t t_step;    /* +1 or -1 */
+	int32_t qlen, tlen;
+	int32_t w, zdrop, end_bonus;
+	int32_t flag;      /* MMB_KSW_* | MMB_JOB_* */
+} mmb_ksw_job_t;
+
+typedef struct {      /* ksw_extz_t (ksw2.h:34-43) without the pointer */
+	int32_t max, zdropped;
+	int32_t max_q, max_t;
+	int32_t mqe, mqe_t;
+	int32_t mte, mte_q;
+	int32_t score;
+	int32_t n_cigar, reach_end;
+	uint32_t cigar_off; /* offset (in uint32 ops) of this job's CIGAR in the batch cigar buffer */
+} mmb_ksw_res_t;
+
+typedef struct {      /* scoring: what align.c:655 ksw_gen_ts_mat + mm_mapopt_t a,b,q,e,q2,e2 give */
+	int8_t mat[25];
+	int8_t q, e, q2, e2;
+} mmb_ksw_score_t;
+
+/* Kernel-level entry with HOST buffers (used by the parity tests and for single calls):
+ * query/target are byte arrays of nt4 codes (0..4). res[n_jobs]; cigar ops are appended to cigar_buf (capacity
+ * cigar_cap uint32s); returns the number of cigar ops written, or <0 if cigar_cap was too small (-needed). */
+int64_t mmb_ksw_batch_host(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *jobs,
+						   const uint8_t *query, int64_t query_len, const uint8_t *target, int64_t target_len,
+						   mmb_ksw_res_t *res, uint32_t *cigar_buf, int64_t cigar_cap);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K1: minimizer sketch   (replaces mm_sketch, sketch.c:77-143)
+ * --------------------------------------------------------------------------------------------------------- */
+/* Kernel-level entry with HOST buffers. seqs: concatenated ASCII (or nt4) sequences; off[n_seq+1] offsets.
+ * out must hold the total number of minimizers; call with out==NULL to get the count. rid of sequence i is rid0+i.
+ * Returns total minimizers; n_out[i] (optional) receives the per-sequence counts. */
+int64_t mmb_sketch_batch_host(mmb_ctx_t *ctx, int n_seq, const char *seqs, const int64_t *off, int w, int k, int is_hpc,
+							  uint32_t rid0, uint64_t *out_xy /* mm128_t pairs */, int64_t out_cap, int64_t *n_out);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * K2c: chaining   (replaces mg_lchain_dp lchain.c:148-217 incl. mg_chain_backtrack/compact_a, and mg_lchain_rmq :250-368)
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+	int32_t max_dist_x, max_dist_y, bw, max_skip, max_iter, min_cnt, min_sc;
+	float chn_pen_gap, chn_pen_skip;
+	int32_t is_cdna, n_seg;
+	/* rmq variant */
+	int32_t use_rmq, max_dist_inner, rmq_size_cap;
+} mmb_chain_par_t;
+
+/* Kernel-level entry with HOST buffers. anchors: concatenated mm128_t (x,y) per read, a_off[n_reads+1].
+ * Output: for read i, n_u[i] chains; u values appended at u_off[i]; compacted anchors overwrite a_out at a_off[i]
+ * (n_v[i] of them). u_out capacity must be >= total anchors/ min_cnt... (pass total anchors to be safe). */
+int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
+						 int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Index on device + whole-path batch mapping are driven through the minimap.h API (include/minimap.h):
+ * mm_idx_* builds/loads the host index and mirrors it into HBM (side table keyed by mm_idx_t*), mm_map_file /
+ * mmb_map_batch run the GPU batch scheduler that replaces worker_pipeline/kt_for (map.c:403-691).
+ * --------------------------------------------------------------------------------------------------------- */
+struct mm_idx_s_fwd; /* see minimap.h */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,504 @@
+// minimap2_b200/csrc/ksw_extd2.cu
+//
+// K3: banded dual-affine-gap extension / global alignment with traceback on sm_100a.
+// Replaces ksw_extd2_sse (reference ksw2_extd2_sse.c:27-401), ksw_backtrack / ksw_apply_zdrop (ksw2.h:130-187).
+//
+// "Universal" kernel: one worker (a warp, or a whole CTA for long jobs) per alignment, anti-diagonal order, the
+// same difference recurrence on int8 with wrap-around arithmetic, the same flat per-target-position state arrays
+// and the same 16-lane chunk rounding of every anti-diagonal, so results (score, z-drop, max/mqe/mte end points,
+// CIGAR) are bit-identical to the reference even when the band clips the matrix and stale lanes are consumed
+// (SURVEY 7.2 items 4-6). Four DP cells are packed per 32-bit word (SIMD-in-register byte ops), 128 cells per
+// warp step; state lives in shared memory, the 1 B/cell traceback matrix in HBM (L2-resident while hot).
+//
+// Design notes
+//  * v/x/x2 are double-buffered by row parity so every lane reads row r-1 values without ordering constraints
+//    (the SSE code gets the same effect by carrying lane 15 in a register). u/y/y2/s are read and written at the
+//    same target position only. Because st/en are non-decreasing in r, a lane is active for one contiguous run of
+//    rows, which makes the parity double-buffer exact (both buffers start with the same fill).
+//  * off[]/off_end[] of the reference (ksw2_extd2_sse.c:230) are pure functions of r and are recomputed in the
+//    traceback instead of being stored.
+//  * Jobs are pulled from a queue (atomic counter) by persistent workers: grid = SMs x resident CTAs.
+#include "mmb_internal.h"
+#include <algorithm>
+#include <numeric>
+
+#define KSW_NEG_INF (-0x40000000)
+
+namespace {
+
+struct KswArgs {
+	const mmb_ksw_job_t *jobs;
+	const int *order;      // job indices of this tier, largest first
+	int n;                 // jobs in this tier
+	const uint8_t *query;
+	const void *target;
+	int t_packed;
+	mmb_ksw_res_t *res;
+	uint32_t *cigar;
+	long long cigar_cap;
+	unsigned long long *cigar_used;
+	uint8_t *pws;          // traceback workspace, pws_stride bytes per worker
+	size_t pws_stride;
+	uint32_t *cigws;       // cigar scratch, cigws_stride uint32 per worker
+	size_t cigws_stride;
+	int *counter;          // job queue head
+	int L, LQ;             // state array length (multiple of 16) / reversed-query length (multiple of 16)
+	int8_t mat[25];
+	int8_t q, e, q2, e2;   // already ordered so that q+e <= q2+e2
+	int8_t skip;           // -min(mat) > 2(q+e): the reference returns immediately (:100)
+	int long_thres, long_diff;
+};
+
+__device__ __forceinline__ uint32_t blend4(uint32_t a, uint32_t b, uint32_t m) { return (a & ~m) | (b & m); } // m ? b : a
+__device__ __forceinline__ uint32_t rep4(int8_t v) { return 0x01010101u * (uint8_t)v; }
+
+template<int G> __device__ __forceinline__ void gsync()
+{
+	if (G == 32) __syncwarp(); else __syncthreads();
+}
+
+// group-wide argmax of (h, lower rank wins). scratch: 2*(G/32) ints of shared memory (G>32 only)
+template<int G> __device__ __forceinline__ void greduce_max(int &h, int &rank, int *scratch, int g)
+{
+	const unsigned full = 0xffffffffu;
+	int m = __reduce_max_sync(full, h);
+	int rk = h == m? rank : 0x7fffffff;
+	rk = __reduce_min_sync(full, rk);
+	h = m, rank = rk;
+	if (G > 32) {
+		const int nw = G / 32;
+		__syncthreads();
+		if ((g & 31) == 0) scratch[(g >> 5) * 2] = h, scratch[(g >> 5) * 2 + 1] = rank;
+		__syncthreads();
+		int bh = scratch[0], br = scratch[1];
+		for (int i = 1; i < nw; ++i) {
+			int hh = scratch[i * 2], rr = scratch[i * 2 + 1];
+			if (hh > bh || (hh == bh && rr < br)) bh = hh, br = rr;
+		}
+		h = bh, rank = br;
+		__syncthreads();
+	}
+}
+
+__device__ __forceinline__ uint8_t fetch_target(const void *target, int packed, long long idx)
+{
+	if (packed) {
+		const uint32_t *S = (const uint32_t*)target;
+		return (uint8_t)(S[idx >> 3] >> ((idx & 7) << 2) & 0xf);
+	}
+	return ((const uint8_t*)target)[idx];
+}
+
+// bounds of anti-diagonal r (ksw2_extd2_sse.c:132-147)
+__device__ __forceinline__ bool diag_bounds(int r, int qlen, int tlen, int w, int &st0, int &en0)
+{
+	int st = 0, en = tlen - 1;
+	if (st < r - qlen + 1) st = r - qlen + 1;
+	if (en > r) en = r;
+	if (st < (r - w + 1) >> 1) st = (r - w + 1) >> 1;
+	if (en > (r + w) >> 1) en = (r + w) >> 1;
+	st0 = st, en0 = en;
+	return st <= en;
+}
+
+struct EzState {
+	int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end;
+};
+
+__device__ __forceinline__ void push_cigar(uint32_t *cig, int &n, uint32_t op, int len) // ksw2.h:114-124
+{
+	if (n == 0 || op != (cig[n - 1] & 0xf)) cig[n++] = (uint32_t)len << 4 | op;
+	else cig[n - 1] += (uint32_t)len << 4;
+}
+
+// ksw2.h:130-162 (rotated layout), off/off_end recomputed
+__device__ int backtrack(const uint8_t *p, int n_col, int qlen, int tlen, int w, int i0, int j0, uint32_t *cig)
+{
+	int n = 0, i = i0, j = j0, state = 0;
+	while (i >= 0 && j >= 0) {
+		int r = i + j, st0, en0, force = -1;
+		diag_bounds(r, qlen, tlen, w, st0, en0);
+		int off = st0 / 16 * 16, off_end = (en0 + 16) / 16 * 16 - 1;
+		if (i < off) force = 2;
+		if (i > off_end) force = 1;
+		uint32_t tmp = force < 0? p[(size_t)r * n_col + i - off] : 0;
+		if (state == 0) state = tmp & 7;
+		else if (!(tmp >> (state + 2) & 1)) state = 0;
+		if (state == 0) state = tmp & 7;
+		if (force >= 0) state = force;
+		if (state == 0) push_cigar(cig, n, 0, 1), --i, --j;
+		else if (state == 1 || state == 3) push_cigar(cig, n, 2, 1), --i;
+		else push_cigar(cig, n, 1, 1), --j;
+	}
+	if (i >= 0) push_cigar(cig, n, 2, i + 1);
+	if (j >= 0) push_cigar(cig, n, 1, j + 1);
+	return n;
+}
+
+template<int G>
+__global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
+{
+	extern __shared__ __align__(16) uint8_t smem_raw[];
+	__shared__ int s_job[8];
+	__shared__ int s_red[16];
+	const int NW = blockDim.x / G;               // workers per CTA
+	const int wk = threadIdx.x / G, g = threadIdx.x % G;
+	const int worker = blockIdx.x * NW + wk;
+	const int L = A.L, LQ = A.LQ;
+	const size_t wbytes = (size_t)15 * L + LQ + 64;
+	uint8_t *base = smem_raw + wbytes * wk;
+	// state arrays (all offsets multiples of 16)
+	uint8_t *u = base, *y = u + L, *y2 = y + L, *s = y2 + L, *sf = s + L;
+	uint8_t *vb[2] = { sf + L, sf + 2 * L }, *xb[2] = { sf + 3 * L, sf + 4 * L }, *x2b[2] = { sf + 5 * L, sf + 6 * L };
+	uint8_t *qr = sf + 7 * L + 16;               // 16 zero bytes in front, >=32 behind
+	int32_t *H = (int32_t*)(sf + 7 * L + LQ + 64);
+	uint8_t *p = A.pws + A.pws_stride * worker;
+	uint32_t *cig = A.cigws + A.cigws_stride * worker;
+	const int8_t q = A.q, e = A.e, q2 = A.q2, e2 = A.e2;
+	const int8_t qe = (int8_t)(q + e), qe2 = (int8_t)(q2 + e2);
+	const uint32_t Q4 = rep4(q), Q24 = rep4(q2), QE4 = rep4(qe), QE24 = rep4(qe2);
+	const uint32_t NQE4 = rep4((int8_t)(-q - e)), NQE24 = rep4((int8_t)(-q2 - e2));
+	const uint32_t MCH4 = rep4(A.mat[0]), MIS4 = rep4(A.mat[1]);
+	const uint32_t SCN4 = rep4(A.mat[24] == 0? (int8_t)(-e2) : A.mat[24]);
+
+	for (;;) {
+		if (g == 0) s_job[wk] = atomicAdd(A.counter, 1);
+		gsync<G>();
+		const int slot = s_job[wk];
+		gsync<G>();
+		if (slot >= A.n) break;
+		const int jid = A.order[slot];
+		const mmb_ksw_job_t jb = A.jobs[jid];
+		const int qlen = jb.qlen, tlen = jb.tlen, flag = jb.flag;
+		int w = jb.w;
+		EzState ez;
+		ez.max_q = ez.max_t = ez.mqe_t = ez.mte_q = -1;
+		ez.max = 0, ez.score = ez.mqe = ez.mte = KSW_NEG_INF;
+		ez.n_cigar = 0, ez.zdropped = 0, ez.reach_end = 0;
+		if (qlen <= 0 || tlen <= 0 || A.skip) {
+			if (g == 0) {
+				mmb_ksw_res_t o;
+				o.max = ez.max, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1;
+				o.mqe = o.mte = o.score = KSW_NEG_INF, o.n_cigar = 0, o.reach_end = 0, o.cigar_off = 0;
+				A.res[jid] = o;
+			}
+			continue;
+		}
+		const bool with_cigar = !(flag & MMB_KSW_SCORE_ONLY), approx_max = (flag & MMB_KSW_APPROX_MAX) != 0;
+		const bool right = (flag & MMB_KSW_RIGHT) != 0, generic = (flag & MMB_KSW_GENERIC_SC) != 0;
+		if (w < 0) w = tlen > qlen? tlen : qlen;
+		const int tlen16 = (tlen + 15) / 16 * 16;
+		int n_col = qlen < tlen? qlen : tlen;
+		n_col = (((n_col < w + 1? n_col : w + 1) + 15) / 16 + 1) * 16;
+
+		// ---- stage sequences and initialise state (ksw2_extd2_sse.c:107-129) ----
+		for (int i = g * 4; i < tlen16; i += G * 4) {
+			*(uint32_t*)(u + i) = NQE4, *(uint32_t*)(y + i) = NQE4, *(uint32_t*)(y2 + i) = NQE24, *(uint32_t*)(s + i) = 0;
+			*(uint32_t*)(vb[0] + i) = NQE4, *(uint32_t*)(vb[1] + i) = NQE4;
+			*(uint32_t*)(xb[0] + i) = NQE4, *(uint32_t*)(xb[1] + i) = NQE4;
+			*(uint32_t*)(x2b[0] + i) = NQE24, *(uint32_t*)(x2b[1] + i) = NQE24;
+			if (!approx_max) { H[i] = H[i + 1] = H[i + 2] = H[i + 3] = KSW_NEG_INF; }
+		}
+		for (int i = g; i < tlen16; i += G)
+			sf[i] = i < tlen? fetch_target(A.target, A.t_packed, jb.t_start + (long long)i * jb.t_step) : 0;
+		for (int i = g; i < LQ + 48; i += G) { // qr[-16 .. LQ+32)
+			int k = i - 16; // position in qr
+			uint8_t c = 0;
+			if (k >= 0 && k < qlen) {
+				c = A.query[jb.q_start + (long long)(qlen - 1 - k) * jb.q_step];
+				if ((flag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
+			}
+			qr[k] = c;
+		}
+		gsync<G>();
+
+		int last_st = -1, last_en = -1;
+		int H0 = 0, last_H0_t = 0;      // approximate-max tracker (thread 0)
+		const int n_rows = qlen + tlen - 1;
+		int r;
+		for (r = 0; r < n_rows; ++r) {
+			int st0, en0;
+			if (!diag_bounds(r, qlen, tlen, w, st0, en0)) { ez.zdropped = 1; break; }
+			const int st = st0 / 16 * 16, en = (en0 + 16) / 16 * 16 - 1;
+			const int nb = r & 1, ob = nb ^ 1;
+			uint8_t *vn = vb[nb], *xn = xb[nb], *x2n = x2b[nb];
+			const uint8_t *vo = vb[ob], *xo = xb[ob], *x2o = x2b[ob];
+			int8_t x1, x21, v1;
+			const int8_t vbound = r == 0? (int8_t)(-q - e) : r < A.long_thres? (int8_t)(-e) : r == A.long_thres? (int8_t)A.long_diff : (int8_t)(-e2);
+			if (st > 0) { // :149-158
+				if (st - 1 >= last_st && st - 1 <= last_en) x1 = (int8_t)xo[st - 1], x21 = (int8_t)x2o[st - 1], v1 = (int8_t)vo[st - 1];
+				else x1 = (int8_t)(-q - e), x21 = (int8_t)(-q2 - e2), v1 = (int8_t)(-q - e);
+			} else x1 = (int8_t)(-q - e), x21 = (int8_t)(-q2 - e2), v1 = vbound;
+			const bool set_top = en >= r; // :159-162 (applied in registers: only lane r reads y[r], y2[r], u[r] this row)
+			// fresh score range [st0, s_end) in 16-byte chunks from st0 (:165-180); generic: [st0, en0]
+			const int s_end = generic? en0 + 1 : min(st0 + ((en0 - st0) / 16 + 1) * 16, tlen16);
+			const int t_hi = max(en, s_end - 1);
+			const int qoff = qlen - 1 - r;
+			uint8_t *prow = p + (size_t)r * n_col;
+
+			for (int t0 = st + 4 * g; t0 <= t_hi; t0 += 4 * G) {
+				uint32_t S = *(const uint32_t*)(s + t0);
+				if (t0 + 3 >= st0 && t0 < s_end) { // some byte of this word gets a fresh score
+					uint32_t fresh;
+					if (!generic) {
+						uint32_t sq = *(const uint32_t*)(sf + t0);
+						int qi = qoff + t0; // >= -16 thanks to the front pad
+						const uint32_t *qw = (const uint32_t*)(qr + (qi & ~3));
+						uint32_t sr = __funnelshift_r(qw[0], qw[1], (qi & 3) * 8);
+						uint32_t nmask = __vcmpeq4(sq, 0x04040404u) | __vcmpeq4(sr, 0x04040404u);
+						fresh = blend4(MIS4, MCH4, __vcmpeq4(sq, sr));
+						fresh = blend4(fresh, SCN4, nmask);
+					} else {
+						fresh = 0;
+						for (int b = 0; b < 4; ++b) {
+							int t = t0 + b;
+							if (t >= st0 && t < s_end) fresh |= (uint32_t)(uint8_t)A.mat[sf[t] * 5 + qr[qoff + t]] << (8 * b);
+						}
+					}
+					uint32_t m = 0;
+					#pragma unroll
+					for (int b = 0; b < 4; ++b) if (t0 + b >= st0 && t0 + b < s_end) m |= 0xffu << (8 * b);
+					S = blend4(S, fresh, m);
+					*(uint32_t*)(s + t0) = S;
+				}
+				if (t0 > en) continue; // score-only overshoot lanes
+				uint32_t U = *(const uint32_t*)(u + t0), Y = *(const uint32_t*)(y + t0), Y2 = *(const uint32_t*)(y2 + t0);
+				uint32_t Vo = *(const uint32_t*)(vo + t0), Xo = *(const uint32_t*)(xo + t0), X2o = *(const uint32_t*)(x2o + t0);
+				uint32_t vp, xp, x2p;
+				if (t0 == st) vp = (uint8_t)v1, xp = (uint8_t)x1, x2p = (uint8_t)x21;
+				else vp = vo[t0 - 1], xp = xo[t0 - 1], x2p = x2o[t0 - 1];
+				if (set_top && r >= t0 && r < t0 + 4) {
+					uint32_t sh = (r - t0) * 8, m = 0xffu << sh;
+					Y = (Y & ~m) | ((NQE4 & 0xff) << sh);
+					Y2 = (Y2 & ~m) | ((NQE24 & 0xff) << sh);
+					U = (U & ~m) | ((uint32_t)(uint8_t)vbound << sh);
+				}
+				const uint32_t VT1 = Vo << 8 | vp, XT1 = Xo << 8 | xp, X2T1 = X2o << 8 | x2p;
+				uint32_t Aa = __vadd4(XT1, VT1), Bb = __vadd4(Y, U), A2 = __vadd4(X2T1, VT1), B2 = __vadd4(Y2, U);
+				uint32_t Z = S, D = 0, m;
+				if (!right) { // :232-243
+					m = __vcmpgts4(Aa, Z); D = m & 0x01010101u;            Z = blend4(Z, Aa, m);
+					m = __vcmpgts4(Bb, Z); D = blend4(D, 0x02020202u, m);  Z = blend4(Z, Bb, m);
+					m = __vcmpgts4(A2, Z); D = blend4(D, 0x03030303u, m);  Z = blend4(Z, A2, m);
+					m = __vcmpgts4(B2, Z); D = blend4(D, 0x04040404u, m);  Z = blend4(Z, B2, m);
+				} else {      // :279-290
+					m = __vcmpgts4(Z, Aa); D = ~m & 0x01010101u;           Z = blend4(Aa, Z, m);
+					m = __vcmpgts4(Z, Bb); D = blend4(0x02020202u, D, m);  Z = blend4(Bb, Z, m);
+					m = __vcmpgts4(Z, A2); D = blend4(0x03030303u, D, m);  Z = blend4(A2, Z, m);
+					m = __vcmpgts4(Z, B2); D = blend4(0x04040404u, D, m);  Z = blend4(B2, Z, m);
+				}
+				Z = __vmins4(Z, MCH4);
+				*(uint32_t*)(u + t0) = __vsub4(Z, VT1);
+				*(uint32_t*)(vn + t0) = __vsub4(Z, U);
+				uint32_t T = __vsub4(Z, Q4);
+				Aa = __vsub4(Aa, T), Bb = __vsub4(Bb, T);
+				T = __vsub4(Z, Q24);
+				A2 = __vsub4(A2, T), B2 = __vsub4(B2, T);
+				if (!right) { // keep if > 0 (:261-273)
+					m = __vcmpgts4(Aa, 0); *(uint32_t*)(xn + t0)  = __vsub4(Aa & m, QE4);  D |= m & 0x08080808u;
+					m = __vcmpgts4(Bb, 0); *(uint32_t*)(y + t0)   = __vsub4(Bb & m, QE4);  D |= m & 0x10101010u;
+					m = __vcmpgts4(A2, 0); *(uint32_t*)(x2n + t0) = __vsub4(A2 & m, QE24); D |= m & 0x20202020u;
+					m = __vcmpgts4(B2, 0); *(uint32_t*)(y2 + t0)  = __vsub4(B2 & m, QE24); D |= m & 0x40404040u;
+				} else {      // keep if >= 0 (:308-320)
+					m = ~__vcmpgts4(0, Aa); *(uint32_t*)(xn + t0)  = __vsub4(Aa & m, QE4);  D |= m & 0x08080808u;
+					m = ~__vcmpgts4(0, Bb); *(uint32_t*)(y + t0)   = __vsub4(Bb & m, QE4);  D |= m & 0x10101010u;
+					m = ~__vcmpgts4(0, A2); *(uint32_t*)(x2n + t0) = __vsub4(A2 & m, QE24); D |= m & 0x20202020u;
+					m = ~__vcmpgts4(0, B2); *(uint32_t*)(y2 + t0)  = __vsub4(B2 & m, QE24); D |= m & 0x40404040u;
+				}
+				if (with_cigar) *(uint32_t*)(prow + (t0 - st)) = D;
+			}
+			gsync<G>();
+
+			int stop = 0;
+			if (!approx_max) { // exact max with the reference's tie rules (:323-366)
+				int max_H, max_t;
+				if (r > 0) {
+					int Hen0 = 0;
+					if (g == 0) Hen0 = en0 > 0? H[en0 - 1] + (int8_t)u[en0] : H[en0] + (int8_t)vn[en0];
+					gsync<G>();
+					const int nblk = (en0 - st0) / 4, en1 = st0 + nblk * 4;
+					int bh = KSW_NEG_INF, brank = 0x7fffffff;
+					for (int t = st0 + g; t < en0; t += G) {
+						int hv = H[t] + (int8_t)vn[t];
+						H[t] = hv;
+						int idx = t - st0;
+						int rank = t < en1? 1 + (idx & 3) * nblk + (idx >> 2) : 1 + 4 * nblk + (t - en1);
+						if (hv > bh || (hv == bh && rank < brank)) bh = hv, brank = rank;
+					}
+					if (g == 0) {
+						H[en0] = Hen0;
+						if (Hen0 > bh || Hen0 == bh) bh = Hen0, brank = 0; // the seed candidate wins ties (strict > to displace it)
+					}
+					greduce_max<G>(bh, brank, s_red, g);
+					max_H = bh;
+					if (brank == 0) max_t = en0;
+					else if (brank <= 4 * nblk) { int k = brank - 1; max_t = st0 + (k % nblk) * 4 + k / nblk; }
+					else max_t = en1 + (brank - 1 - 4 * nblk);
+				} else {
+					if (g == 0) H[0] = (int8_t)vn[0] - qe;
+					gsync<G>();
+					max_H = H[0], max_t = 0;
+				}
+				gsync<G>();
+				// every thread keeps ez in registers and applies the same updates (values are group-uniform)
+				if (en0 == tlen - 1 && H[en0] > ez.mte) ez.mte = H[en0], ez.mte_q = r - en0;
+				if (r - st0 == qlen - 1 && H[st0] > ez.mqe) ez.mqe = H[st0], ez.mqe_t = st0;
+				// ksw_apply_zdrop (ksw2.h:171-187)
+				if (max_H > ez.max) ez.max = max_H, ez.max_t = max_t, ez.max_q = r - max_t;
+				else if (max_t >= ez.max_t && r - max_t >= ez.max_q) {
+					int tl = max_t - ez.max_t, ql = (r - max_t) - ez.max_q, l = tl > ql? tl - ql : ql - tl;
+					if (jb.zdrop >= 0 && ez.max - max_H > jb.zdrop + l * e2) ez.zdropped = 1, stop = 1;
+				}
+				if (!stop && r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H[tlen - 1];
+				gsync<G>(); // H is rewritten next row
+			} else { // approximate max: follow one path (:367-383); thread 0 tracks it, result broadcast at the end
+				if (g == 0) {
+					if (r > 0) {
+						if (last_H0_t >= st0 && last_H0_t <= en0 && last_H0_t + 1 >= st0 && last_H0_t + 1 <= en0) {
+							int d0 = (int8_t)vn[last_H0_t], d1 = (int8_t)u[last_H0_t + 1];
+							if (d0 > d1) H0 += d0; else H0 += d1, ++last_H0_t;
+						} else if (last_H0_t >= st0 && last_H0_t <= en0) H0 += (int8_t)vn[last_H0_t];
+						else ++last_H0_t, H0 += (int8_t)u[last_H0_t];
+					} else H0 = (int8_t)vn[0] - qe, last_H0_t = 0;
+				}
+				if (flag & MMB_KSW_APPROX_DROP) { // not used by align.c; supported for API completeness
+					int hh = __shfl_sync(0xffffffffu, H0, 0), tt = __shfl_sync(0xffffffffu, last_H0_t, 0);
+					if (G > 32) { if (g == 0) s_red[0] = H0, s_red[1] = last_H0_t; __syncthreads(); hh = s_red[0], tt = s_red[1]; __syncthreads(); }
+					if (hh > ez.max) ez.max = hh, ez.max_t = tt, ez.max_q = r - tt;
+					else if (tt >= ez.max_t && r - tt >= ez.max_q) {
+						int tl = tt - ez.max_t, ql = (r - tt) - ez.max_q, l = tl > ql? tl - ql : ql - tl;
+						if (jb.zdrop >= 0 && ez.max - hh > jb.zdrop + l * e2) ez.zdropped = 1, stop = 1;
+					}
+				}
+				if (!stop && r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0; // only thread 0's copy is meaningful
+			}
+			if (stop) break;
+			last_st = st, last_en = en;
+		}
+
+		// ---- traceback (ksw2_extd2_sse.c:388-400) and result write-out ----
+		int n_cig = 0;
+		bool rev_cigar = (flag & MMB_KSW_REV_CIGAR) != 0;
+		if (with_cigar) {
+			int bi = -1, bj = -1;
+			if (!ez.zdropped && !(flag & MMB_KSW_EXTZ_ONLY)) bi = tlen - 1, bj = qlen - 1;
+			else if (!ez.zdropped && (flag & MMB_KSW_EXTZ_ONLY) && ez.mqe + jb.end_bonus > ez.max) ez.reach_end = 1, bi = ez.mqe_t, bj = qlen - 1;
+			else if (ez.max_t >= 0 && ez.max_q >= 0) bi = ez.max_t, bj = ez.max_q;
+			__threadfence_block();
+			gsync<G>();
+			if (g == 0 && bi >= 0) n_cig = backtrack(p, n_col, qlen, tlen, w, bi, bj, cig);
+			if (G == 32) n_cig = __shfl_sync(0xffffffffu, n_cig, 0);
+			else { if (g == 0) s_red[0] = n_cig; __syncthreads(); n_cig = s_red[0]; __syncthreads(); }
+		}
+		unsigned long long coff = 0;
+		if (n_cig > 0) {
+			if (g == 0) coff = atomicAdd(A.cigar_used, (unsigned long long)n_cig);
+			if (G == 32) coff = __shfl_sync(0xffffffffu, coff, 0);
+			else { if (g == 0) *(unsigned long long*)s_red = coff; __syncthreads(); coff = *(unsigned long long*)s_red; __syncthreads(); }
+			if ((long long)(coff + n_cig) <= A.cigar_cap)
+				for (int i = g; i < n_cig; i += G)
+					A.cigar[coff + i] = rev_cigar? cig[i] : cig[n_cig - 1 - i];
+		}
+		if (g == 0) {
+			mmb_ksw_res_t o;
+			o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t;
+			o.mqe = ez.mqe, o.mqe_t = ez.mqe_t, o.mte = ez.mte, o.mte_q = ez.mte_q;
+			o.score = ez.score, o.n_cigar = n_cig, o.reach_end = ez.reach_end, o.cigar_off = (uint32_t)coff;
+			A.res[jid] = o;
+		}
+		gsync<G>();
+	}
+}
+
+} // namespace
+
+// Host-side tiering + launch. Tiers by max(qlen,tlen): warp-per-job for <=1024, CTA-per-job above.
+void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
+					const uint8_t *d_query, const void *d_target, int t_packed,
+					mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap, unsigned long long *d_cigar_used)
+{
+	if (n_jobs <= 0) return;
+	KswArgs A;
+	A.jobs = d_jobs, A.query = d_query, A.target = d_target, A.t_packed = t_packed, A.res = d_res;
+	A.cigar = d_cigar, A.cigar_cap = cigar_cap, A.cigar_used = d_cigar_used;
+	for (int i = 0; i < 25; ++i) A.mat[i] = sc->mat[i];
+	int8_t q = sc->q, e = sc->e, q2 = sc->q2, e2 = sc->e2;
+	if (q2 + e2 < q + e) std::swap(q, q2), std::swap(e, e2); // ksw2_extd2_sse.c:78
+	A.q = q, A.e = e, A.q2 = q2, A.e2 = e2;
+	int min_sc = sc->mat[1];
+	for (int i = 1; i < 25; ++i) min_sc = std::min<int>(min_sc, sc->mat[i]);
+	A.skip = -min_sc > 2 * (q + e);
+	int lt = e != e2? (q2 - q) / (e - e2) - 1 : 0; // :102-105
+	if (q2 + e2 + lt * e2 > q + e + lt * e) ++lt;
+	A.long_thres = lt, A.long_diff = lt * (e - e2) - (q2 - q) - e2;
+
+	// tiers: {max len16, group size, workers per CTA}
+	struct Tier { int maxlen, G, nw; };
+	const Tier tiers[] = { {256, 32, 8}, {512, 32, 8}, {1024, 32, 4}, {13000, 256, 1} };
+	const int n_tiers = 4;
+	std::vector<std::vector<int>> tj(n_tiers + 1);
+	uint64_t cells = 0;
+	for (int i = 0; i < n_jobs; ++i) {
+		int m = std::max(h_jobs[i].qlen, h_jobs[i].tlen), k = 0;
+		cells += (uint64_t)std::max(h_jobs[i].qlen, 0) * std::max(h_jobs[i].tlen, 0);
+		while (k < n_tiers && m > tiers[k].maxlen) ++k;
+		tj[k].push_back(i);
+	}
+	if (!tj[n_tiers].empty()) {
+		fprintf(stderr, "[ERROR] ksw job longer than %d not supported by this build\n", tiers[n_tiers - 1].maxlen);
+		abort();
+	}
+	ProfScope prof(ctx, MMB_PROF_KSW, cells);
+	for (int k = 0; k < n_tiers; ++k) {
+		std::vector<int> &v = tj[k];
+		if (v.empty()) continue;
+		std::sort(v.begin(), v.end(), [&](int a, int b) {
+			int64_t ca = (int64_t)h_jobs[a].qlen * h_jobs[a].tlen, cb = (int64_t)h_jobs[b].qlen * h_jobs[b].tlen;
+			return ca != cb? ca > cb : a < b; });
+		int maxq = 0, maxt = 0; size_t maxp = 0; int maxsum = 0;
+		for (int i : v) {
+			const mmb_ksw_job_t &j = h_jobs[i];
+			maxq = std::max(maxq, j.qlen), maxt = std::max(maxt, j.tlen), maxsum = std::max(maxsum, j.qlen + j.tlen);
+			int w = j.w < 0? std::max(j.qlen, j.tlen) : j.w;
+			int n_col = std::min(j.qlen, j.tlen);
+			n_col = ((std::min(n_col, w + 1) + 15) / 16 + 1) * 16;
+			maxp = std::max(maxp, (size_t)(j.qlen + j.tlen - 1) * n_col + 16);
+		}
+		A.L = (maxt + 15) / 16 * 16, A.LQ = (maxq + 15) / 16 * 16;
+		const int G = tiers[k].G, nw = tiers[k].nw, threads = G * nw;
+		size_t smem = ((size_t)15 * A.L + A.LQ + 64) * nw;
+		int cta_per_sm = 1;
+		if (G == 32) {
+			MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smem, ctx->smem_optin)));
+			MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<32>, threads, smem));
+		} else {
+			MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smem, ctx->smem_optin)));
+			MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<256>, threads, smem));
+		}
+		if (smem > ctx->smem_optin || cta_per_sm < 1) {
+			fprintf(stderr, "[ERROR] ksw tier %d needs %zu B shared memory per CTA\n", k, smem);
+			abort();
+		}
+		int grid = ctx->n_sm * cta_per_sm;
+		int need = ((int)v.size() + nw - 1) / nw;
+		grid = std::max(1, std::min(grid, need));
+		const int workers = grid * nw;
+		maxp = (maxp + 255) & ~(size_t)255;
+		// bound the traceback workspace (8 GB): fewer resident workers for very large matrices
+		while ((size_t)workers * maxp > ((size_t)8 << 30) && grid > 1) grid = (grid + 1) / 2;
+		A.pws_stride = maxp, A.cigws_stride = (size_t)maxsum + 8;
+		A.pws = (uint8_t*)ctx->d_e.reserve(A.pws_stride * (size_t)grid * nw);
+		A.cigws = (uint32_t*)ctx->d_f.reserve(A.cigws_stride * 4 * (size_t)grid * nw);
+		int *d_order = (int*)ctx->d_g.reserve((v.size() + 1) * sizeof(int));
+		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
+		A.counter = d_order, A.order = d_order + 1, A.n = (int)v.size();
+		if (G == 32) ksw_extd2_kernel<32><<<grid, threads, smem, ctx->stream>>>(A);
+		else ksw_extd2_kernel<256><<<grid, threads, smem, ctx->stream>>>(A);
+		MMB_CUDA_CHECK(cudaGetLastError());
+		++ctx->n_launch;
+		// the order buffer / workspaces are reused by the next tier: serialise on the stream (same stream => ordered),
+		// but the host vector must stay alive until the copy is done
+		MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	}
+}

@@ -1,0 +1,99 @@
+// minimap2_b200/csrc/mmb_ctx.cu -- device context + kernel-level C-ABI entry points with host buffers (mm_b200.h).
+#include "mmb_internal.h"
+#include <cstring>
+
+int mm_verbose_dummy_anchor = 0;
+
+extern "C" int mmb_device_count(void)
+{
+	int n = 0;
+	cudaError_t err = cudaGetDeviceCount(&n);
+	if (err != cudaSuccess) {
+		fprintf(stderr, "[ERROR] minimap2_b200: no usable CUDA device (%s); there is no CPU fallback\n", cudaGetErrorString(err));
+		return -1;
+	}
+	return n;
+}
+
+extern "C" mmb_ctx_t *mmb_ctx_create(int device)
+{
+	int n = mmb_device_count();
+	if (n <= 0 || device < 0 || device >= n) {
+		fprintf(stderr, "[ERROR] minimap2_b200: cannot create a context on device %d (%d visible)\n", device, n);
+		return nullptr;
+	}
+	mmb_ctx_t *c = new mmb_ctx_t();
+	c->device = device;
+	MMB_CUDA_CHECK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	MMB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+	c->n_sm = prop.multiProcessorCount;
+	c->smem_optin = prop.sharedMemPerBlockOptin;
+	MMB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	MMB_CUDA_CHECK(cudaEventCreate(&c->ev0));
+	MMB_CUDA_CHECK(cudaEventCreate(&c->ev1));
+	return c;
+}
+
+extern "C" void mmb_ctx_destroy(mmb_ctx_t *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	c->d_a.release(); c->d_b.release(); c->d_c.release(); c->d_d.release();
+	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release();
+	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+	cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+extern "C" void *mmb_ctx_stream(mmb_ctx_t *c) { return (void*)c->stream; }
+
+extern "C" uint64_t mmb_launch_count(mmb_ctx_t *c, int reset)
+{
+	uint64_t n = c->n_launch;
+	if (reset) c->n_launch = 0;
+	return n;
+}
+
+extern "C" void mmb_profile_enable(mmb_ctx_t *c, int on) { c->profiling = on; }
+extern "C" double mmb_profile_ms(mmb_ctx_t *c, int which, int reset)
+{
+	if (which < 0 || which >= MMB_PROF_N) return 0.0;
+	double v = c->prof_ms[which];
+	if (reset) c->prof_ms[which] = 0;
+	return v;
+}
+extern "C" uint64_t mmb_profile_units(mmb_ctx_t *c, int which, int reset)
+{
+	if (which < 0 || which >= MMB_PROF_N) return 0;
+	uint64_t v = c->prof_units[which];
+	if (reset) c->prof_units[which] = 0;
+	return v;
+}
+
+extern "C" int64_t mmb_ksw_batch_host(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *jobs,
+									  const uint8_t *query, int64_t query_len, const uint8_t *target, int64_t target_len,
+									  mmb_ksw_res_t *res, uint32_t *cigar_buf, int64_t cigar_cap)
+{
+	if (n_jobs <= 0) return 0;
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	uint8_t *d_q = ctx->d_a.as<uint8_t>(query_len + 16), *d_t = ctx->d_b.as<uint8_t>(target_len + 16);
+	mmb_ksw_job_t *d_jobs = ctx->d_c.as<mmb_ksw_job_t>(n_jobs);
+	mmb_ksw_res_t *d_res = ctx->d_d.as<mmb_ksw_res_t>(n_jobs);
+	uint32_t *d_cig = (uint32_t*)ctx->d_h.reserve((size_t)(cigar_cap + 2) * 4 + 16);
+	unsigned long long *d_used = (unsigned long long*)(d_cig); // first 8 bytes: counter; ops start at +2
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_q, query, query_len, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_t, target, target_len, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs, sizeof(mmb_ksw_job_t) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, 8, ctx->stream));
+	mmb_ksw_launch(ctx, sc, n_jobs, jobs, d_jobs, d_q, d_t, 0, d_res, d_cig + 2, cigar_cap, d_used);
+	unsigned long long used = 0;
+	MMB_CUDA_CHECK(cudaMemcpyAsync(res, d_res, sizeof(mmb_ksw_res_t) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	if ((int64_t)used > cigar_cap) return -(int64_t)used;
+	MMB_CUDA_CHECK(cudaMemcpyAsync(cigar_buf, d_cig + 2, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	return (int64_t)used;
+}

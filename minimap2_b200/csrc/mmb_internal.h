@@ -1,0 +1,91 @@
+// minimap2_b200/csrc/mmb_internal.h -- internal declarations shared by the CUDA translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "mm_b200.h"
+
+extern "C" int mm_verbose;
+
+#define MMB_CUDA_CHECK(expr) do { \
+	cudaError_t err__ = (expr); \
+	if (err__ != cudaSuccess) { \
+		fprintf(stderr, "[ERROR] CUDA failure '%s' at %s:%d: %s\n", #expr, __FILE__, __LINE__, cudaGetErrorString(err__)); \
+		abort(); \
+	} } while (0)
+
+enum { MMB_PROF_SKETCH = 0, MMB_PROF_SEED = 1, MMB_PROF_SORT = 2, MMB_PROF_CHAIN = 3, MMB_PROF_KSW = 4, MMB_PROF_OTHER = 5, MMB_PROF_N = 6 };
+
+// A grow-only device buffer (arena slice): avoids cudaMalloc on the per-batch path.
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	void *reserve(size_t bytes) {
+		if (bytes > cap) {
+			if (p) MMB_CUDA_CHECK(cudaFree(p));
+			size_t ncap = bytes + (bytes >> 2) + 256;
+			MMB_CUDA_CHECK(cudaMalloc(&p, ncap));
+			cap = ncap;
+		}
+		return p;
+	}
+	template<class T> T *as(size_t n) { return (T*)reserve(n * sizeof(T)); }
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PinBuf { // pinned host staging buffer
+	void *p = nullptr;
+	size_t cap = 0;
+	void *reserve(size_t bytes) {
+		if (bytes > cap) {
+			if (p) MMB_CUDA_CHECK(cudaFreeHost(p));
+			size_t ncap = bytes + (bytes >> 2) + 256;
+			MMB_CUDA_CHECK(cudaMallocHost(&p, ncap));
+			cap = ncap;
+		}
+		return p;
+	}
+	template<class T> T *as(size_t n) { return (T*)reserve(n * sizeof(T)); }
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct mmb_ctx_s {
+	int device = 0;
+	int n_sm = 0;
+	size_t smem_optin = 0;
+	cudaStream_t stream = nullptr;
+	uint64_t n_launch = 0;
+	int profiling = 0;
+	double prof_ms[MMB_PROF_N] = {0};
+	uint64_t prof_units[MMB_PROF_N] = {0};
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	// scratch used by the kernel-level host entry points
+	DevBuf d_a, d_b, d_c, d_d, d_e, d_f, d_g, d_h;
+};
+
+// RAII-ish timing of one kernel family on the ctx stream (only when profiling is enabled; synchronous then)
+struct ProfScope {
+	mmb_ctx_t *c; int which;
+	ProfScope(mmb_ctx_t *ctx, int w, uint64_t units) : c(ctx), which(w) {
+		if (c->profiling) { MMB_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream)); c->prof_units[w] += units; }
+	}
+	~ProfScope() {
+		if (c->profiling) {
+			float ms = 0;
+			MMB_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
+			MMB_CUDA_CHECK(cudaEventSynchronize(c->ev1));
+			MMB_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+			c->prof_ms[which] += ms;
+		}
+	}
+};
+
+// ---- device-side launchers (all asynchronous on ctx->stream) ----
+
+// ksw_extd2.cu: d_jobs/d_res are device arrays; query is a device byte array (nt4), target either bytes or 4-bit packed words.
+// h_jobs is the host copy (used for tiering). cigar ops go to d_cigar (capacity cigar_cap), *d_cigar_used counts them.
+void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
+					const uint8_t *d_query, const void *d_target, int t_packed,
+					mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap, unsigned long long *d_cigar_used);

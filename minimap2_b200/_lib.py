@@ -56,6 +56,11 @@ def lib():
         L.mmb_ksw_batch_host.restype = C.c_int64
         L.mmb_ksw_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+        L.mmb_sketch_batch_host.restype = C.c_int64
+        L.mmb_sketch_batch_host.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32,
+                                            C.c_void_p, C.c_int64, C.c_void_p]
+        L.mmb_chain_batch_host.restype = C.c_int
+        L.mmb_chain_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -1,0 +1,212 @@
+// minimap2_b200/csrc/chain.cu
+//
+// K2c: anchor chaining on sm_100a. Replaces mg_lchain_dp (reference lchain.c:148-217), mg_chain_backtrack /
+// mg_chain_bk_end (lchain.c:9-76) and compact_a (lchain.c:78-111).
+//
+// Reads are the parallel axis: a batch holds 10^4..10^5 reads whose anchor arrays are independent, while inside a
+// read the DP is a chain of data-dependent decisions (strict '>' tie rule scanning j downward, the max_skip early
+// exit fed by the t[] marks written inside the same scan, the max_ii shortcut, float32 penalties) and the backtrack
+// is pointer chasing over an UNSTABLE radix sort whose tie order decides which chain end is peeled first. Each read
+// is therefore replayed exactly by one thread over its own slice of the batch-wide SoA arrays in HBM; a launch covers
+// the whole batch (grid = ceil(n_reads/128)), scratch comes from one arena sized by the anchor count.
+#include "mmb_internal.h"
+#include "mm_algo.cuh"
+
+namespace {
+
+struct ChainArgs {
+	mmb_chain_par_t par;
+	int n_reads;
+	const int64_t *a_off;   // n_reads+1 anchor offsets
+	const m128 *a;          // anchors sorted by x (input; not modified)
+	// scratch, all indexed by the read's anchor offset
+	int32_t *f, *p, *v, *t;
+	m128 *z, *b;
+	int32_t *stk;           // radix-sort range stack: stk_off[i] per read
+	const int64_t *stk_off;
+	// outputs
+	int32_t *n_u, *n_v;
+	uint64_t *u;            // at a_off[i]
+	m128 *a_out;            // at a_off[i]
+};
+
+__device__ int32_t bk_end(int32_t max_drop, const m128 *z, const int32_t *f, const int32_t *p, int32_t *t, int32_t k) // lchain.c:9-25
+{
+	int32_t i = (int32_t)z[k].y, end_i = -1, max_i = i, max_s = 0;
+	if (i < 0 || t[i] != 0) return i;
+	do {
+		int32_t s;
+		t[i] = 2;
+		end_i = i = p[i];
+		s = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+		if (s > max_s) max_s = s, max_i = i;
+		else if (max_s - s > max_drop) break;
+	} while (i >= 0 && t[i] == 0);
+	for (i = (int32_t)z[k].y; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
+	return max_i;
+}
+
+__global__ void __launch_bounds__(128) chain_dp_kernel(ChainArgs A)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= A.n_reads) return;
+	const int64_t off = A.a_off[rd];
+	const int32_t n = (int32_t)(A.a_off[rd + 1] - off);
+	A.n_u[rd] = 0, A.n_v[rd] = 0;
+	if (n <= 0) return;
+	const m128 *a = A.a + off;
+	int32_t *f = A.f + off, *p = A.p + off, *v = A.v + off, *t = A.t + off;
+	const mmb_chain_par_t &P = A.par;
+	int32_t max_dist_x = P.max_dist_x, max_dist_y = P.max_dist_y, max_drop = P.bw;
+	const int32_t bw = P.bw, max_skip = P.max_skip, max_iter = P.max_iter, is_cdna = P.is_cdna, n_seg = P.n_seg;
+	const float pen_gap = P.chn_pen_gap, pen_skip = P.chn_pen_skip;
+	if (max_dist_x < bw) max_dist_x = bw;
+	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
+	if (is_cdna) max_drop = INT32_MAX;
+
+	// ---- fill (lchain.c:168-207) ----
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	int32_t st = 0, best_prev = -1;
+	for (int32_t i = 0; i < n; ++i) {
+		const m128 ai = a[i];
+		int32_t max_j = -1, max_f = (int32_t)(ai.y >> 32 & 0xff), n_skip = 0, j, end_j;
+		while (st < i && (ai.x >> 32 != a[st].x >> 32 || ai.x > a[st].x + (uint64_t)(int64_t)max_dist_x)) ++st;
+		if (i - st > max_iter) st = i - max_iter;
+		for (j = i - 1; j >= st; --j) {
+			int32_t sc = mmx_comput_sc(ai, a[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+			if (sc == INT32_MIN) continue;
+			sc += f[j];
+			if (sc > max_f) {
+				max_f = sc, max_j = j;
+				if (n_skip > 0) --n_skip;
+			} else if (t[j] == i) {
+				if (++n_skip > max_skip) break;
+			}
+			if (p[j] >= 0) t[p[j]] = i;
+		}
+		end_j = j;
+		if (best_prev < 0 || ai.x - a[best_prev].x > (uint64_t)(int64_t)max_dist_x) {
+			int32_t mx = INT32_MIN;
+			best_prev = -1;
+			for (j = i - 1; j >= st; --j) if (mx < f[j]) mx = f[j], best_prev = j;
+		}
+		if (best_prev >= 0 && best_prev < end_j) {
+			int32_t tmp = mmx_comput_sc(ai, a[best_prev], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+			if (tmp != INT32_MIN && max_f < tmp + f[best_prev]) max_f = tmp + f[best_prev], max_j = best_prev;
+		}
+		f[i] = max_f, p[i] = max_j;
+		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+		if (best_prev < 0 || (ai.x - a[best_prev].x <= (uint64_t)(int64_t)max_dist_x && f[best_prev] < f[i])) best_prev = i;
+	}
+
+	// ---- backtrack (lchain.c:27-76) ----
+	m128 *z = A.z + off;
+	int32_t n_z = 0;
+	const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt;
+	for (int32_t i = 0; i < n; ++i) if (f[i] >= min_sc) z[n_z].x = (uint64_t)(int64_t)f[i], z[n_z++].y = (uint64_t)i;
+	if (n_z == 0) return;
+	mmx_rs_sort(z, (int64_t)n_z, A.stk + A.stk_off[rd], KeyX128());
+	uint64_t *u = A.u + off;
+	int32_t n_u = 0, n_v = 0;
+	// the reference makes a counting pass and a filling pass with identical traversals; one filling pass suffices here
+	// because v[] (reused as the index list, as in the reference) and u[] have capacity n
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	for (int32_t k = n_z - 1; k >= 0; --k) {
+		if (t[z[k].y] == 0) {
+			const int32_t n_v0 = n_v, end_i = bk_end(max_drop, z, f, p, t, k);
+			int32_t i, sc;
+			for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
+			sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+			if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+			else n_v = n_v0;
+		}
+	}
+	A.n_u[rd] = n_u, A.n_v[rd] = n_v;
+	if (n_u == 0) return;
+
+	// ---- compact (lchain.c:78-111) ----
+	m128 *b = A.b + off, *w = z; // z is free now; n_u <= n_z
+	int32_t k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t k0 = k, ni = (int32_t)u[i];
+		for (int32_t j = 0; j < ni; ++j) b[k++] = a[v[k0 + (ni - j - 1)]];
+	}
+	k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint64_t)i;
+		k += (int32_t)u[i];
+	}
+	mmx_rs_sort(w, (int64_t)n_u, A.stk + A.stk_off[rd], KeyX128());
+	// u2 -> stored temporarily in f/p space (8 bytes per entry): reuse t,v? use (uint64_t*)f with capacity n/2: not enough
+	// in general, so write the reordered u[] through the (now free) v/t pair viewed as uint64 when n_u*2 <= n, else in place
+	// via a second buffer carved from b's tail. Simplest exact approach: stash old u into z's y-field copies first.
+	m128 *ao = A.a_out + off;
+	k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t j = (int32_t)w[i].y, nn = (int32_t)u[j];
+		const int32_t src = (int32_t)(w[i].y >> 32);
+		w[i].x = u[j]; // keep the chain's u value next to its order (w[i].x is no longer needed)
+		for (int32_t q = 0; q < nn; ++q) ao[k + q] = b[src + q];
+		k += nn;
+	}
+	for (int32_t i = 0; i < n_u; ++i) u[i] = w[i].x;
+}
+
+__global__ void stk_len_kernel(const int64_t *a_off, int n_reads, int64_t *stk_off)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_reads) stk_off[i] = mmx_rs_stack_len(a_off[i + 1] - a_off[i]);
+}
+
+} // namespace
+
+#include "scan.cuh"
+
+// Device-level launcher (asynchronous). d_a: anchors (sorted by x per read), d_a_off: n_reads+1 offsets, total anchors n_tot.
+// Outputs (device): d_n_u, d_n_v (n_reads), d_u (n_tot, at the read's anchor offset), d_a_out (n_tot).
+void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
+					  int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2)
+{
+	if (n_reads <= 0) return;
+	ChainArgs A;
+	A.par = *par, A.n_reads = n_reads, A.a_off = d_a_off, A.a = d_a;
+	// scratch layout: f,p,v,t (4 x int32 n_tot) | z (m128 n_tot) | b (m128 n_tot)
+	const size_t n = (size_t)n_tot + 4;
+	uint8_t *s = (uint8_t*)scratch.reserve(n * (16 + 16 + 16) + 256);
+	A.f = (int32_t*)s, A.p = A.f + n, A.v = A.p + n, A.t = A.v + n;
+	A.z = (m128*)(s + n * 16), A.b = A.z + n;
+	// stack offsets
+	int64_t *d_stk_off = (int64_t*)scratch2.reserve(((size_t)n_reads + 1) * 8 + ((size_t)n_tot / 65 * 24 + (size_t)n_reads * 48 + 64) * 4);
+	stk_len_kernel<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(d_a_off, n_reads, d_stk_off);
+	++ctx->n_launch;
+	mmb_exclusive_scan_i64_async(ctx, d_stk_off, n_reads);
+	A.stk_off = d_stk_off, A.stk = (int32_t*)(d_stk_off + n_reads + 1);
+	A.n_u = d_n_u, A.n_v = d_n_v, A.u = d_u, A.a_out = d_a_out;
+	ProfScope prof(ctx, MMB_PROF_CHAIN, (uint64_t)n_tot);
+	chain_dp_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(A);
+	MMB_CUDA_CHECK(cudaGetLastError());
+	++ctx->n_launch;
+}
+
+extern "C" int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
+									int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy)
+{
+	if (n_reads <= 0) return 0;
+	if (par->use_rmq) { fprintf(stderr, "[ERROR] mmb_chain_batch_host: rmq chaining goes through mmb_chain_rmq_batch_host\n"); abort(); }
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	const int64_t n_tot = a_off[n_reads];
+	m128 *d_a = ctx->d_a.as<m128>((size_t)n_tot + 1);
+	int64_t *d_off = ctx->d_b.as<int64_t>((size_t)n_reads + 1);
+	int32_t *d_nu = ctx->d_c.as<int32_t>((size_t)n_reads * 2 + 2), *d_nv = d_nu + n_reads;
+	uint64_t *d_u = ctx->d_d.as<uint64_t>((size_t)n_tot + 1);
+	m128 *d_ao = ctx->d_e.as<m128>((size_t)n_tot + 1);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_a, anchors_xy, sizeof(m128) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_off, a_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
+	mmb_chain_device(ctx, par, n_reads, d_a, d_off, n_tot, d_nu, d_nv, d_u, d_ao, ctx->d_f, ctx->d_g);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(n_u, d_nu, sizeof(int32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(n_v, d_nv, sizeof(int32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(u_out, d_u, sizeof(uint64_t) * n_tot, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(a_out_xy, d_ao, sizeof(m128) * n_tot, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}

@@ -1,0 +1,78 @@
+// minimap2_b200/csrc/hostlogic.h -- host orchestration pieces (hit post-processing, alignment driver, formatting).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+#include <string>
+#include <unordered_map>
+#include "minimap.h"
+#include "mm_b200.h"
+#include "mm_algo.cuh"
+
+#define HL_PARENT_UNSET   (-1)   // mmpriv.h:9-10
+#define HL_PARENT_TMP_PRI (-2)
+
+// ---- hits.cc ----
+void hl_reg_set_coor(mm_reg1_t *r, int32_t qlen, const m128 *a, int is_qstrand);
+mm_reg1_t *hl_gen_regs(uint32_t hash, int qlen, int n_u, const uint64_t *u, const m128 *a, int is_qstrand);
+void hl_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, m128 *a, int is_qstrand);
+void hl_set_parent(float mask_level, int mask_len, int n, mm_reg1_t *r, int sub_diff, int hard_mask_level, float alt_diff_frac);
+void hl_hit_sort(int *n_regs, mm_reg1_t *r, float alt_diff_frac);
+int hl_set_sam_pri(int n, mm_reg1_t *r);
+void hl_sync_regs(int n_regs, mm_reg1_t *regs);
+void hl_select_sub(float pri_ratio, int min_diff, int best_n, int check_strand, int min_strand_sc, int *n_, mm_reg1_t *r);
+int hl_filter_strand_retained(int n_regs, mm_reg1_t *r);
+void hl_filter_regs(const mm_mapopt_t *opt, int qlen, int *n_regs, mm_reg1_t *regs);
+int hl_squeeze_a(int n_regs, mm_reg1_t *regs, m128 *a);
+void hl_set_mapq(int n_regs, mm_reg1_t *regs, int min_chain_sc, int match_sc, int rep_len, int is_sr, int is_splice);
+void hl_est_err(const mm_idx_t *mi, int qlen, int n_regs, mm_reg1_t *regs, const m128 *a, int32_t n, const uint64_t *mini_pos);
+double hl_event_identity(const mm_reg1_t *r);
+void hl_update_dp_max(int qlen, int n_regs, mm_reg1_t *regs, float frac, int a, int b);
+
+// ---- align.cc: the alignment driver (mm_align_skeleton / mm_align1, align.c:645-1120) as a replayable routine ----
+struct KswKey {
+	int64_t q_start, t_start;
+	int32_t q_step, t_step, qlen, tlen, w, zdrop, end_bonus, flag;
+	bool operator==(const KswKey &o) const {
+		return q_start == o.q_start && t_start == o.t_start && q_step == o.q_step && t_step == o.t_step && qlen == o.qlen &&
+			   tlen == o.tlen && w == o.w && zdrop == o.zdrop && end_bonus == o.end_bonus && flag == o.flag;
+	}
+};
+struct KswKeyHash {
+	size_t operator()(const KswKey &k) const {
+		uint64_t h = mmx_hash64_full((uint64_t)k.q_start * 0x9E3779B97F4A7C15ULL ^ (uint64_t)k.t_start);
+		h = mmx_hash64_full(h ^ ((uint64_t)(uint32_t)k.qlen << 32 | (uint32_t)k.tlen));
+		h = mmx_hash64_full(h ^ ((uint64_t)(uint32_t)k.flag << 32 | (uint32_t)k.w) ^ ((uint64_t)(uint32_t)k.zdrop << 20) ^ (uint32_t)k.end_bonus ^ ((uint64_t)(k.q_step + 2) << 60) ^ ((uint64_t)(k.t_step + 2) << 56));
+		return (size_t)h;
+	}
+};
+
+struct KswDone {            // a finished job: ksw_extz_t fields + where its CIGAR lives in ReadAlign::cigar_pool
+	mmb_ksw_res_t r;
+	uint32_t pool_off;
+};
+
+struct ReadAlign {          // per-read alignment working set (lives across waves)
+	int qlen = 0;
+	int64_t q_dev_off = 0;  // offset of this read's first base in the device query array
+	std::vector<uint8_t> qseq[2]; // nt4 forward / reverse complement (align.c:1056-1061)
+	std::unordered_map<KswKey, int, KswKeyHash> cache; // key -> index into done (-1: requested, not delivered yet)
+	std::vector<KswDone> done;
+	std::vector<uint32_t> cigar_pool;
+	std::vector<mmb_ksw_job_t> want; // jobs requested by the current replay
+	std::vector<KswKey> want_key;
+	bool incomplete = false;
+};
+
+// Runs the whole per-read alignment (mm_align_skeleton semantics) using cached ksw results; missing results are appended
+// to ra.want and ra.incomplete is set. When complete, *n_regs_/regs hold the aligned hits (regs may be realloc'd).
+// a[] must have its IGNORE/LONG_JOIN marks cleared by the caller before every replay.
+mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAlign &ra, int *n_regs_, mm_reg1_t *regs, int n_a, m128 *a);
+
+// ---- format.cc ----
+struct hl_str { std::string s; };
+void hl_set_seq_for_tags(const char *seq);
+void hl_write_paf(std::string &s, const mm_idx_t *mi, const char *qname, int qlen, const mm_reg1_t *r, int64_t opt_flag, int rep_len);
+void hl_write_sam(std::string &s, const mm_idx_t *mi, const char *qname, const char *seq, const char *qual, int qlen, int reg_idx,
+				  int n_regs, const mm_reg1_t *regs, int64_t opt_flag, int rep_len);
+void hl_write_sam_hdr(std::string &s, const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[]);

@@ -410,6 +410,115 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// ksw_ll_i16 (reference ksw2_ll_sse.c:37-152): Farrar-striped local alignment score with int16 saturation, used only for
+// inversion probes (align.c:95-96, :940-941). The 8 int16 lanes of an SSE register map to 8 threads; a warp runs 4 jobs.
+// The striped order is part of the contract: the lazy-F loop leaves E uncorrected and the reported query end is the LAST
+// striped slot holding the maximum (:148-150).
+// ---------------------------------------------------------------------------------------------------------
+struct LLArgs {
+	const mmb_ksw_job_t *jobs;
+	const int *order;
+	int n;
+	const uint8_t *query;
+	const void *target;
+	int t_packed;
+	mmb_ksw_res_t *res;
+	int16_t *ws;          // per group: 4 arrays of slen_max*8 int16 + query bytes
+	size_t ws_stride;     // bytes per group
+	int slen_max;
+	int *counter;
+	int8_t mat[25];
+};
+
+__device__ __forceinline__ int16_t subs_u16(int16_t a, uint16_t b) { uint16_t ua = (uint16_t)a; return ua > b? (int16_t)(ua - b) : (int16_t)0; }
+__device__ __forceinline__ int16_t max16(int16_t a, int16_t b) { return a > b? a : b; }
+
+__global__ void __launch_bounds__(128) ksw_ll_kernel(LLArgs A)
+{
+	const int lane = threadIdx.x & 31, k = lane & 7, grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+	const unsigned gmask = 0xffu << (lane & 24);
+	uint8_t *wsb = (uint8_t*)A.ws + A.ws_stride * grp;
+	const int SM = A.slen_max * 8;
+	int16_t *H0 = (int16_t*)wsb, *H1 = H0 + SM, *E = H1 + SM, *Hmax = E + SM;
+	uint8_t *qs = (uint8_t*)(Hmax + SM);
+	for (;;) {
+		int slot = 0;
+		if (k == 0) slot = atomicAdd(A.counter, 1);
+		slot = __shfl_sync(gmask, slot, lane & 24);
+		if (slot >= A.n) break;
+		const int jid = A.order[slot];
+		const mmb_ksw_job_t jb = A.jobs[jid];
+		const int qlen = jb.qlen, tlen = jb.tlen, slen = (qlen + 7) / 8;
+		const uint16_t go = (uint16_t)(jb.w + jb.zdrop), ge = (uint16_t)jb.zdrop; // w = gap open, zdrop = gap extension for LL jobs
+		for (int i = k; i < slen * 8; i += 8) {
+			H0[i] = 0, E[i] = 0, Hmax[i] = 0, H1[i] = 0;
+			uint8_t c = 0;
+			if (i < qlen) {
+				c = A.query[jb.q_start + (long long)i * jb.q_step];
+				if ((jb.flag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
+			}
+			qs[i] = c;
+		}
+		__syncwarp(gmask);
+		int gmax = 0, qe = -1, te = -1;
+		for (int i = 0; i < tlen; ++i) {
+			const int t = fetch_target(A.target, A.t_packed, jb.t_start + (long long)i * jb.t_step);
+			const int8_t *ma = A.mat + t * 5;
+			int16_t f = 0, mx = 0, h, e;
+			h = slen > 0? H0[(slen - 1) * 8 + k] : 0;
+			h = __shfl_up_sync(gmask, h, 1, 8);
+			if (k == 0) h = 0;
+			for (int j = 0; j < slen; ++j) {
+				const int qp = j + k * slen;
+				const int sc = qp >= qlen? -1 : ma[qs[qp]];
+				int t32 = (int)h + sc;
+				t32 = t32 > 32767? 32767 : t32 < -32768? -32768 : t32;
+				h = (int16_t)t32;
+				e = E[j * 8 + k];
+				h = max16(h, e); h = max16(h, f); mx = max16(mx, h);
+				H1[j * 8 + k] = h;
+				const int16_t hs = subs_u16(h, go);
+				e = subs_u16(e, ge); e = max16(e, hs);
+				E[j * 8 + k] = e;
+				f = subs_u16(f, ge); f = max16(f, hs);
+				h = H0[j * 8 + k];
+			}
+			bool done = false;
+			for (int kk = 0; kk < 8 && !done; ++kk) { // lazy F (:124-135)
+				f = __shfl_up_sync(gmask, f, 1, 8);
+				if (k == 0) f = 0;
+				for (int j = 0; j < slen; ++j) {
+					int16_t hh = H1[j * 8 + k];
+					hh = max16(hh, f);
+					H1[j * 8 + k] = hh;
+					const int16_t hs = subs_u16(hh, go);
+					f = subs_u16(f, ge);
+					if (!(__ballot_sync(gmask, f > hs) & gmask)) { done = true; break; }
+				}
+			}
+			int imax = mx;
+			for (int o = 4; o > 0; o >>= 1) imax = max(imax, __shfl_xor_sync(gmask, imax, o, 8));
+			if (imax >= gmax) {
+				gmax = imax, te = i;
+				for (int j = 0; j < slen; ++j) Hmax[j * 8 + k] = H1[j * 8 + k];
+			}
+			int16_t *tmp = H1; H1 = H0; H0 = tmp;
+		}
+		int best = -1;
+		for (int j = 0; j < slen; ++j) if ((int)(uint16_t)Hmax[j * 8 + k] == gmax) best = j * 8 + k;
+		for (int o = 4; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(gmask, best, o, 8));
+		if (best >= 0) qe = best / 8 + best % 8 * slen;
+		if (k == 0) {
+			mmb_ksw_res_t o;
+			o.max = 0, o.zdropped = 0, o.max_q = qe, o.max_t = te, o.mqe = o.mte = KSW_NEG_INF, o.mqe_t = o.mte_q = -1;
+			o.score = gmax, o.n_cigar = 0, o.reach_end = 0, o.cigar_off = 0;
+			A.res[jid] = o;
+		}
+		__syncwarp(gmask);
+	}
+}
+
 } // namespace
 
 // Host-side tiering + launch. Tiers by max(qlen,tlen): warp-per-job for <=1024, CTA-per-job above.
@@ -438,7 +547,9 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 	const int n_tiers = 4;
 	std::vector<std::vector<int>> tj(n_tiers + 1);
 	uint64_t cells = 0;
+	std::vector<int> llj;
 	for (int i = 0; i < n_jobs; ++i) {
+		if (h_jobs[i].flag & MMB_JOB_LL) { llj.push_back(i); continue; }
 		int m = std::max(h_jobs[i].qlen, h_jobs[i].tlen), k = 0;
 		cells += (uint64_t)std::max(h_jobs[i].qlen, 0) * std::max(h_jobs[i].tlen, 0);
 		while (k < n_tiers && m > tiers[k].maxlen) ++k;
@@ -447,6 +558,28 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 	if (!tj[n_tiers].empty()) {
 		fprintf(stderr, "[ERROR] ksw job longer than %d not supported by this build\n", tiers[n_tiers - 1].maxlen);
 		abort();
+	}
+	if (!llj.empty()) {
+		LLArgs L;
+		int maxq = 1;
+		for (int i : llj) maxq = std::max(maxq, h_jobs[i].qlen);
+		L.jobs = d_jobs, L.query = d_query, L.target = d_target, L.t_packed = t_packed, L.res = d_res, L.n = (int)llj.size();
+		for (int i = 0; i < 25; ++i) L.mat[i] = sc->mat[i];
+		L.slen_max = (maxq + 7) / 8;
+		L.ws_stride = ((size_t)L.slen_max * 8 * 2 * 4 + (size_t)L.slen_max * 8 + 255) & ~(size_t)255;
+		int groups = std::min((int)llj.size(), ctx->n_sm * 16 * 4);
+		int grid = (groups * 8 + 127) / 128;
+		groups = grid * 16;
+		L.ws = (int16_t*)ctx->d_e.reserve(L.ws_stride * (size_t)groups);
+		int *d_order = (int*)ctx->d_g.reserve((llj.size() + 1) * sizeof(int));
+		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, llj.data(), llj.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
+		L.counter = d_order, L.order = d_order + 1;
+		ProfScope prof(ctx, MMB_PROF_OTHER, 0);
+		ksw_ll_kernel<<<grid, 128, 0, ctx->stream>>>(L);
+		MMB_CUDA_CHECK(cudaGetLastError());
+		++ctx->n_launch;
+		MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	}
 	ProfScope prof(ctx, MMB_PROF_KSW, cells);
 	for (int k = 0; k < n_tiers; ++k) {

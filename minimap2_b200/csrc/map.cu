@@ -1,0 +1,502 @@
+// minimap2_b200/csrc/map.cu -- the GPU batch scheduler behind mm_map / mm_map_frag / mm_map_file (minimap.h).
+//
+// Replaces the reference's thread pipeline (map.c:403-691: worker_pipeline / kt_for(worker_for)) and the per-read
+// orchestration mm_map_frag_core (map.c:227-378). A batch of reads goes through
+//   stage 1 (device, whole batch per launch): encode -> K1 sketch -> K2a lookup/select -> K2b expand+sort -> K2c chain
+//   stage 2 (host threads): chains -> hits (hits.cc), primary/secondary selection, divergence estimate
+//   stage 3 (waves): host threads replay the alignment driver (align.cc) per read, the ksw2 jobs they request are run as
+//            one K3 launch set per wave, results are scattered back into per-read caches; typically 2-3 waves
+//   stage 4 (host threads): final hit selection and MAPQ
+// Results are returned in input order with the reference's ownership rules (libc malloc, caller frees).
+#include "pipeline.h"
+#include "hostlogic.h"
+#include "scan.cuh"
+#include "fastx.h"
+#include <thread>
+#include <atomic>
+#include <functional>
+#include <cstring>
+#include <algorithm>
+
+extern "C" double realtime(void);
+extern "C" double cputime(void);
+
+void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
+					const uint8_t *d_query, const void *d_target, int t_packed,
+					mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap, unsigned long long *d_cigar_used);
+
+namespace {
+
+void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t, int)> &fn)
+{
+	if (n <= 0) return;
+	if (n_threads < 1) n_threads = 1;
+	if (n_threads > n) n_threads = (int)n;
+	if (n_threads == 1) { for (int64_t i = 0; i < n; ++i) fn(i, 0); return; }
+	std::atomic<int64_t> next(0);
+	std::vector<std::thread> th;
+	const int64_t grain = std::max<int64_t>(1, n / (n_threads * 16));
+	for (int t = 0; t < n_threads; ++t)
+		th.emplace_back([&, t]() {
+			for (;;) {
+				int64_t b = next.fetch_add(grain);
+				if (b >= n) break;
+				int64_t e = std::min(n, b + grain);
+				for (int64_t i = b; i < e; ++i) fn(i, t);
+			}
+		});
+	for (auto &x : th) x.join();
+}
+
+__global__ void encode_kernel(uint8_t *s, int64_t n)
+{
+	int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i + 3 < n) {
+		uchar4 v = *reinterpret_cast<uchar4*>(s + i);
+		v.x = mmx_nt4(v.x), v.y = mmx_nt4(v.y), v.z = mmx_nt4(v.z), v.w = mmx_nt4(v.w);
+		*reinterpret_cast<uchar4*>(s + i) = v;
+	} else for (; i < n; ++i) s[i] = mmx_nt4(s[i]);
+}
+
+__global__ void init_nmz_kernel(const int64_t *mz_off, int n, int32_t *n_mz)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) n_mz[i] = (int32_t)(mz_off[i + 1] - mz_off[i]);
+}
+
+__global__ void to_i64_kernel(const int32_t *a, int n, int64_t *b)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) b[i] = a[i];
+}
+
+__global__ void copy_i64_kernel(const int64_t *a, int n, int64_t *b)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) b[i] = a[i];
+}
+
+// gather per-read slices (src at src_off[r], cnt[r] items) into a dense array at dst_off[r]; one warp per read
+template<class T>
+__global__ void gather_kernel(const T *src, const int64_t *src_off, const int32_t *cnt, const int64_t *dst_off, int n_reads, T *dst)
+{
+	const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (w >= n_reads) return;
+	const T *s = src + src_off[w];
+	T *d = dst + dst_off[w];
+	for (int i = lane; i < cnt[w]; i += 32) d[i] = s[i];
+}
+
+inline uint32_t x31_hash_string(const char *s) // khash.h:383-388
+{
+	uint32_t h = (uint32_t)*s;
+	if (h) for (++s; *s; ++s) h = (h << 5) - h + (uint32_t)*s;
+	return h;
+}
+inline uint32_t wang_hash(uint32_t key) // khash.h:400-409
+{
+	key += ~(key << 15); key ^= (key >> 10); key += (key << 3); key ^= (key >> 6); key += ~(key << 11); key ^= (key >> 16);
+	return key;
+}
+
+struct BatchBufs { // device arenas reused across batches (per context)
+	DevBuf seq, off, mz, mz_off, n_mz, qlen, s_n, s_off, k_idx, k_aoff, flt, mini_pos, n_keep, rep_len, n_a, a_off, a, stk;
+	DevBuf n_u, n_v, u, a_out, ch1, ch2, t1, t2, doff, dense_u, dense_a, dense_mp;
+	DevBuf jobs, res, cig;
+	PinBuf h_seq, h_misc;
+};
+BatchBufs *g_bufs = nullptr;
+
+struct ReadState {
+	int qlen = 0;
+	const char *seq = nullptr, *name = nullptr;
+	uint32_t hash = 0;
+	int rep_len = 0, n_mini_pos = 0, n_u = 0, n_a = 0;
+	const uint64_t *mini_pos = nullptr, *u = nullptr;
+	const m128 *a_src = nullptr;
+	int n_regs0 = 0;
+	mm_reg1_t *regs0 = nullptr;            // after chain_post/est_err (pristine, no ->p)
+	std::vector<m128> a;                   // working copy of the anchors for the alignment replay
+	ReadAlign *ra = nullptr;
+	int n_regs = 0;
+	mm_reg1_t *regs = nullptr;             // final
+	bool done = false;
+};
+
+void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
+{
+	const char *what = nullptr;
+	if (opt->flag & MM_F_SPLICE) what = "spliced alignment (-x splice: ksw_exts2)";
+	else if (opt->flag & MM_F_SR) what = "short-read mode (-x sr)";
+	else if (opt->flag & MM_F_RMQ) what = "RMQ chaining as the primary chainer (--rmq / asm presets)";
+	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
+	else if (opt->q == opt->q2 && opt->e == opt->e2) what = "single-affine gap cost (ksw_extz2)";
+	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
+	else if (mi->n_alt) what = "ALT contigs";
+	if (what) {
+		fprintf(stderr, "[ERROR] minimap2_b200: %s is not implemented in this build; refusing to run (no CPU fallback)\n", what);
+		abort();
+	}
+}
+
+} // namespace
+
+extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
+							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
+{
+	if (n_reads <= 0) return 0;
+	unsupported_check(mi, opt);
+	mm_idx_bucket_s *B = mi->B;
+	mmb_ctx_t *ctx = B->ctx;
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	if (!g_bufs) g_bufs = new BatchBufs();
+	BatchBufs &bb = *g_bufs;
+	if (n_threads < 1) n_threads = 1;
+	std::vector<ReadState> rs(n_reads);
+	std::vector<int64_t> off(n_reads + 1, 0);
+	std::vector<int> live; // reads that go through the pipeline (non-empty, within max_qlen)
+	for (int i = 0; i < n_reads; ++i) {
+		rs[i].qlen = qlens[i], rs[i].seq = seqs[i], rs[i].name = names? names[i] : nullptr;
+		n_regs_out[i] = 0, regs_out[i] = nullptr;
+		if (rep_len_out) rep_len_out[i] = 0;
+		bool ok = qlens[i] > 0 && !(opt->max_qlen > 0 && qlens[i] > opt->max_qlen); // map.c:243-244
+		if (ok) live.push_back(i);
+	}
+	const int n = (int)live.size();
+	if (n == 0) return 0;
+	for (int j = 0; j < n; ++j) off[j + 1] = off[j] + rs[live[j]].qlen;
+	const int64_t total_bases = off[n];
+
+	// ---------------- stage 1: device ----------------
+	uint8_t *h_seq = bb.h_seq.as<uint8_t>((size_t)total_bases + 16);
+	parallel_for(n, n_threads, [&](int64_t j, int) { memcpy(h_seq + off[j], rs[live[j]].seq, rs[live[j]].qlen); });
+	uint8_t *d_seq = bb.seq.as<uint8_t>((size_t)total_bases + 16);
+	int64_t *d_off = bb.off.as<int64_t>((size_t)n + 1);
+	int32_t *d_qlen = bb.qlen.as<int32_t>((size_t)n);
+	std::vector<int32_t> h_qlen(n);
+	for (int j = 0; j < n; ++j) h_qlen[j] = rs[live[j]].qlen;
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_seq, h_seq, total_bases, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_qlen, h_qlen.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	encode_kernel<<<(unsigned)((total_bases / 4 + 256) / 256), 256, 0, ctx->stream>>>(d_seq, total_bases);
+	++ctx->n_launch;
+	int64_t *d_mz_off = bb.mz_off.as<int64_t>((size_t)n + 1);
+	const int64_t total_mz = mmb_sketch_device(ctx, d_seq, nullptr, d_off, n, nullptr, 0, mi->w, mi->k, mi->flag & MM_I_HPC, total_bases,
+											   bb.mz, d_mz_off, bb.t1, bb.t2, 1 /* rid = segment index 0 for every read (map.c:65) */);
+	SeedArgs S;
+	S.ix = B->view(mi), S.n_reads = n, S.mz = (m128*)bb.mz.p, S.mz_off = d_mz_off, S.qlen = d_qlen;
+	S.n_mz = bb.n_mz.as<int32_t>((size_t)n);
+	S.q_occ_max = opt->mid_occ, S.q_occ_frac = opt->q_occ_frac;
+	S.max_occ = opt->mid_occ, S.max_max_occ = opt->max_max_occ, S.occ_dist = opt->occ_dist, S.flag = opt->flag;
+	const size_t nm = (size_t)total_mz + 4;
+	S.s_n = bb.s_n.as<uint32_t>(nm), S.s_off = bb.s_off.as<uint64_t>(nm), S.k_idx = bb.k_idx.as<uint32_t>(nm), S.k_aoff = bb.k_aoff.as<uint32_t>(nm);
+	S.flt = bb.flt.as<uint8_t>(nm), S.mini_pos = bb.mini_pos.as<uint64_t>(nm);
+	S.n_keep = bb.n_keep.as<int32_t>((size_t)n), S.rep_len = bb.rep_len.as<int32_t>((size_t)n), S.n_a = bb.n_a.as<int64_t>((size_t)n + 1);
+	init_nmz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_mz_off, n, S.n_mz);
+	++ctx->n_launch;
+	mmb_seed_select_device(ctx, S, total_mz);
+	int64_t *d_a_off = bb.a_off.as<int64_t>((size_t)n + 1);
+	copy_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(S.n_a, n, d_a_off);
+	++ctx->n_launch;
+	const int64_t total_a = mmb_exclusive_scan_i64(ctx, d_a_off, n, true);
+	S.a = bb.a.as<m128>((size_t)total_a + 4), S.a_off = d_a_off;
+	mmb_seed_expand_sort_device(ctx, S, total_mz, total_a, bb.stk);
+	// chaining parameters (map.c:262-281)
+	mmb_chain_par_t cp;
+	memset(&cp, 0, sizeof(cp));
+	int max_chain_gap_qry = opt->max_gap, max_chain_gap_ref;
+	if (opt->max_gap_ref > 0) max_chain_gap_ref = opt->max_gap_ref;
+	else if (opt->max_frag_len > 0) { // qlen-dependent (map.c:266-268); only meaningful for paired short reads
+		fprintf(stderr, "[ERROR] minimap2_b200: max_frag_len > 0 (short-read pairing) is not implemented\n");
+		abort();
+	} else max_chain_gap_ref = opt->max_gap;
+	cp.max_dist_x = max_chain_gap_ref, cp.max_dist_y = max_chain_gap_qry, cp.bw = opt->bw, cp.max_skip = opt->max_chain_skip;
+	cp.max_iter = opt->max_chain_iter, cp.min_cnt = opt->min_cnt, cp.min_sc = opt->min_chain_score;
+	cp.chn_pen_gap = (float)(opt->chain_gap_scale * 0.01 * mi->k), cp.chn_pen_skip = (float)(opt->chain_skip_scale * 0.01 * mi->k);
+	cp.is_cdna = 0, cp.n_seg = 1;
+	int32_t *d_n_u = bb.n_u.as<int32_t>((size_t)n), *d_n_v = bb.n_v.as<int32_t>((size_t)n);
+	uint64_t *d_u = bb.u.as<uint64_t>((size_t)total_a + 4);
+	m128 *d_a_out = bb.a_out.as<m128>((size_t)total_a + 4);
+	mmb_chain_device(ctx, &cp, n, S.a, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2);
+	// TODO(long-join rescue, map.c:283-292): re-chain with mg_lchain_rmq on the device when n_regs0>1
+
+	// dense copies for the host: offsets for u, a and mini_pos
+	int64_t *d_doff = bb.doff.as<int64_t>((size_t)(n + 1) * 3);
+	int64_t *d_uo = d_doff, *d_vo = d_doff + (n + 1), *d_mo = d_doff + 2 * (n + 1);
+	to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_n_u, n, d_uo);
+	to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_n_v, n, d_vo);
+	to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(S.n_keep, n, d_mo);
+	ctx->n_launch += 3;
+	const int64_t tot_u = mmb_exclusive_scan_i64(ctx, d_uo, n, true);
+	const int64_t tot_v = mmb_exclusive_scan_i64(ctx, d_vo, n, true);
+	const int64_t tot_m = mmb_exclusive_scan_i64(ctx, d_mo, n, true);
+	uint64_t *d_du = bb.dense_u.as<uint64_t>((size_t)tot_u + 1);
+	m128 *d_da = bb.dense_a.as<m128>((size_t)tot_v + 1);
+	uint64_t *d_dm = bb.dense_mp.as<uint64_t>((size_t)tot_m + 1);
+	const unsigned gw = (unsigned)(((int64_t)n * 32 + 255) / 256);
+	gather_kernel<uint64_t><<<gw, 256, 0, ctx->stream>>>(d_u, d_a_off, d_n_u, d_uo, n, d_du);
+	gather_kernel<m128><<<gw, 256, 0, ctx->stream>>>(d_a_out, d_a_off, d_n_v, d_vo, n, d_da);
+	gather_kernel<uint64_t><<<gw, 256, 0, ctx->stream>>>(S.mini_pos, d_mz_off, S.n_keep, d_mo, n, d_dm);
+	ctx->n_launch += 3;
+	// host copies
+	const size_t misc_bytes = sizeof(int64_t) * (size_t)(n + 1) * 3 + sizeof(int32_t) * (size_t)n + sizeof(uint64_t) * (size_t)(tot_u + tot_m) + sizeof(m128) * (size_t)tot_v + 64;
+	uint8_t *hm = bb.h_misc.as<uint8_t>(misc_bytes);
+	int64_t *h_uo = (int64_t*)hm, *h_vo = h_uo + (n + 1), *h_mo = h_vo + (n + 1);
+	m128 *h_da = (m128*)(h_mo + (n + 1));
+	uint64_t *h_du = (uint64_t*)(h_da + tot_v), *h_dm = h_du + tot_u;
+	int32_t *h_rep = (int32_t*)(h_dm + tot_m);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(h_uo, d_doff, sizeof(int64_t) * (size_t)(n + 1) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(h_da, d_da, sizeof(m128) * (size_t)tot_v, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(h_du, d_du, sizeof(uint64_t) * (size_t)tot_u, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(h_dm, d_dm, sizeof(uint64_t) * (size_t)tot_m, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(h_rep, S.rep_len, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+
+	// ---------------- stage 2: chains -> hits (map.c:317-336) ----------------
+	const bool with_cigar = (opt->flag & MM_F_CIGAR) != 0;
+	parallel_for(n, n_threads, [&](int64_t j, int) {
+		ReadState &r = rs[live[j]];
+		r.rep_len = h_rep[j];
+		r.n_u = (int)(h_uo[j + 1] - h_uo[j]), r.u = h_du + h_uo[j];
+		r.n_a = (int)(h_vo[j + 1] - h_vo[j]), r.a_src = h_da + h_vo[j];
+		r.n_mini_pos = (int)(h_mo[j + 1] - h_mo[j]), r.mini_pos = h_dm + h_mo[j];
+		uint32_t hash = r.name && !(opt->flag & MM_F_NO_HASH_NAME)? x31_hash_string(r.name) : 0; // map.c:246-248
+		hash ^= wang_hash((uint32_t)r.qlen) + wang_hash((uint32_t)opt->seed);
+		r.hash = wang_hash(hash);
+		r.a.assign(r.a_src, r.a_src + r.n_a);
+		int n_regs0 = r.n_u;
+		mm_reg1_t *regs0 = hl_gen_regs(r.hash, r.qlen, r.n_u, r.u, r.a.data(), 0);
+		if (!(opt->flag & MM_F_ALL_CHAINS)) { // chain_post (map.c:206-213)
+			hl_set_parent(opt->mask_level, opt->mask_len, n_regs0, regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
+			hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 1, (int)(opt->max_gap * 0.8), &n_regs0, regs0);
+		}
+		hl_est_err(mi, r.qlen, n_regs0, regs0, r.a.data(), r.n_mini_pos, r.mini_pos);
+		n_regs0 = hl_filter_strand_retained(n_regs0, regs0);
+		r.n_regs0 = n_regs0, r.regs0 = regs0;
+		if (with_cigar && n_regs0 > 0) {
+			ReadAlign *ra = new ReadAlign();
+			ra->qlen = r.qlen, ra->q_dev_off = off[j];
+			ra->qseq[0].resize(r.qlen), ra->qseq[1].resize(r.qlen);
+			for (int i = 0; i < r.qlen; ++i) { // align.c:1056-1061
+				uint8_t c = mmx_nt4((uint8_t)r.seq[i]);
+				ra->qseq[0][i] = c, ra->qseq[1][r.qlen - 1 - i] = c < 4? 3 - c : 4;
+			}
+			r.ra = ra;
+		} else r.done = true, r.n_regs = n_regs0, r.regs = regs0, r.regs0 = nullptr;
+	});
+
+	// ---------------- stage 3: alignment waves ----------------
+	if (with_cigar) {
+		mmb_ksw_score_t sc;
+		{ // align.c:11-38 via a throw-away driver-compatible matrix
+			const int m = 5;
+			int8_t aa = (int8_t)(opt->a < 0? -opt->a : opt->a), bb2 = (int8_t)(opt->b > 0? -opt->b : opt->b);
+			int8_t sa = (int8_t)(opt->sc_ambi > 0? -opt->sc_ambi : opt->sc_ambi);
+			for (int i = 0; i < m - 1; ++i) { for (int k = 0; k < m - 1; ++k) sc.mat[i * m + k] = i == k? aa : bb2; sc.mat[i * m + m - 1] = sa; }
+			for (int k = 0; k < m; ++k) sc.mat[(m - 1) * m + k] = sa;
+			if (!(opt->transition == 0 || opt->transition == opt->b)) {
+				int8_t t = (int8_t)(opt->transition > 0? -opt->transition : opt->transition);
+				sc.mat[0 * m + 2] = t, sc.mat[1 * m + 3] = t, sc.mat[2 * m + 0] = t, sc.mat[3 * m + 1] = t;
+			}
+			sc.q = (int8_t)opt->q, sc.e = (int8_t)opt->e, sc.q2 = (int8_t)opt->q2, sc.e2 = (int8_t)opt->e2;
+		}
+		std::vector<int> active;
+		for (int j = 0; j < n; ++j) if (!rs[live[j]].done) active.push_back(live[j]);
+		int wave = 0;
+		while (!active.empty()) {
+			// replay every active read; collect the jobs they miss
+			parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
+				ReadState &r = rs[active[t]];
+				ReadAlign &ra = *r.ra;
+				ra.want.clear(); ra.want_key.clear();
+				r.a.assign(r.a_src, r.a_src + r.n_a); // pristine anchors (IGNORE/LONG_JOIN marks cleared)
+				int n_regs = r.n_regs0;
+				mm_reg1_t *regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
+				memcpy(regs, r.regs0, sizeof(mm_reg1_t) * n_regs);
+				regs = hl_align_skeleton(opt, mi, ra, &n_regs, regs, r.n_a, r.a.data());
+				if (ra.incomplete) {
+					for (int i = 0; i < n_regs; ++i) free(regs[i].p);
+					free(regs);
+				} else {
+					if (!(opt->flag & MM_F_ALL_CHAINS)) { // align_regs (map.c:215-225)
+						hl_set_parent(opt->mask_level, opt->mask_len, n_regs, regs, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
+						hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 0, (int)(opt->max_gap * 0.8), &n_regs, regs);
+						hl_set_sam_pri(n_regs, regs);
+					}
+					r.n_regs = n_regs, r.regs = regs, r.done = true;
+				}
+			});
+			// gather jobs
+			std::vector<int> still;
+			std::vector<int64_t> joff(active.size() + 1, 0);
+			for (size_t t = 0; t < active.size(); ++t) {
+				ReadState &r = rs[active[t]];
+				joff[t + 1] = joff[t] + (r.done? 0 : (int64_t)r.ra->want.size());
+			}
+			const int64_t n_jobs = joff[active.size()];
+			if (n_jobs > 0) {
+				std::vector<mmb_ksw_job_t> jobs((size_t)n_jobs);
+				parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
+					ReadState &r = rs[active[t]];
+					if (!r.done && !r.ra->want.empty()) memcpy(&jobs[joff[t]], r.ra->want.data(), sizeof(mmb_ksw_job_t) * r.ra->want.size());
+				});
+				// run in chunks to bound the result buffers
+				const int64_t CH = 1 << 20;
+				std::vector<mmb_ksw_res_t> res((size_t)n_jobs);
+				std::vector<std::vector<uint32_t>> cig_chunks;
+				std::vector<int64_t> chunk_of_job_base;
+				for (int64_t b = 0; b < n_jobs; b += CH) {
+					const int64_t m = std::min(CH, n_jobs - b);
+					int64_t cap = 0;
+					for (int64_t i = 0; i < m; ++i) if (!(jobs[b + i].flag & MMB_JOB_LL)) cap += (jobs[b + i].qlen + jobs[b + i].tlen) / 2 + 8;
+					for (;;) {
+						mmb_ksw_job_t *d_jobs = bb.jobs.as<mmb_ksw_job_t>((size_t)m);
+						mmb_ksw_res_t *d_res = bb.res.as<mmb_ksw_res_t>((size_t)m);
+						uint32_t *d_cig = bb.cig.as<uint32_t>((size_t)cap + 4);
+						unsigned long long *d_used = (unsigned long long*)d_cig;
+						MMB_CUDA_CHECK(cudaMemcpyAsync(d_jobs, &jobs[b], sizeof(mmb_ksw_job_t) * m, cudaMemcpyHostToDevice, ctx->stream));
+						MMB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, 8, ctx->stream));
+						mmb_ksw_launch(ctx, &sc, (int)m, &jobs[b], d_jobs, d_seq, B->d_S, 1, d_res, d_cig + 2, cap, d_used);
+						unsigned long long used = 0;
+						MMB_CUDA_CHECK(cudaMemcpyAsync(&res[b], d_res, sizeof(mmb_ksw_res_t) * m, cudaMemcpyDeviceToHost, ctx->stream));
+						MMB_CUDA_CHECK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, ctx->stream));
+						MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+						if ((int64_t)used > cap) { cap = (int64_t)used + 16; continue; } // rare: rerun the chunk with a larger CIGAR arena
+						cig_chunks.emplace_back((size_t)used + 1);
+						if (used) MMB_CUDA_CHECK(cudaMemcpyAsync(cig_chunks.back().data(), d_cig + 2, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+						MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+						break;
+					}
+				}
+				// scatter results into the per-read caches
+				parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
+					ReadState &r = rs[active[t]];
+					if (r.done) return;
+					ReadAlign &ra = *r.ra;
+					for (size_t i = 0; i < ra.want.size(); ++i) {
+						const int64_t jid = joff[t] + (int64_t)i;
+						const mmb_ksw_res_t &rr = res[jid];
+						KswDone d; d.r = rr, d.pool_off = (uint32_t)ra.cigar_pool.size();
+						const std::vector<uint32_t> &cc = cig_chunks[jid / CH];
+						ra.cigar_pool.insert(ra.cigar_pool.end(), cc.begin() + rr.cigar_off, cc.begin() + rr.cigar_off + rr.n_cigar);
+						ra.cache[ra.want_key[i]] = (int)ra.done.size();
+						ra.done.push_back(d);
+					}
+				});
+			}
+			for (size_t t = 0; t < active.size(); ++t) if (!rs[active[t]].done) still.push_back(active[t]);
+			if (!still.empty() && n_jobs == 0) { fprintf(stderr, "[ERROR] minimap2_b200: alignment scheduler made no progress\n"); abort(); }
+			active.swap(still);
+			if (++wave > 64) { fprintf(stderr, "[ERROR] minimap2_b200: too many alignment waves\n"); abort(); }
+		}
+	}
+
+	// ---------------- stage 4: finalize (map.c:338-343) ----------------
+	parallel_for(n, n_threads, [&](int64_t j, int) {
+		ReadState &r = rs[live[j]];
+		if (r.regs0) free(r.regs0);
+		delete r.ra;
+		r.regs = (mm_reg1_t*)realloc(r.regs, sizeof(mm_reg1_t) * (r.n_regs > 0? r.n_regs : 1));
+		hl_set_mapq(r.n_regs, r.regs, opt->min_chain_score, opt->a, r.rep_len, 0, 0);
+		if (r.n_regs == 0) { free(r.regs); r.regs = nullptr; }
+		n_regs_out[live[j]] = r.n_regs, regs_out[live[j]] = r.regs;
+		if (rep_len_out) rep_len_out[live[j]] = r.rep_len;
+	});
+	return 0;
+}
+
+// ---- the classic single-read API (map.c:13-31, 380-397): a batch of one ----
+extern "C" mm_tbuf_t *mm_tbuf_init(void) { return (mm_tbuf_t*)calloc(1, sizeof(mm_tbuf_t)); }
+extern "C" void mm_tbuf_destroy(mm_tbuf_t *b) { free(b); }
+extern "C" void *mm_tbuf_get_km(mm_tbuf_t *b) { return b? b->km : 0; }
+
+static std::mutex g_map_mu; // the batch arenas are shared: serialise concurrent single-read callers
+
+extern "C" void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **seqs, int *n_regs, mm_reg1_t **regs, mm_tbuf_t *b, const mm_mapopt_t *opt, const char *qname)
+{
+	if (n_segs != 1) {
+		fprintf(stderr, "[ERROR] minimap2_b200: multi-segment (paired-end) mapping is not implemented\n");
+		abort();
+	}
+	std::lock_guard<std::mutex> lk(g_map_mu);
+	int rep_len = 0;
+	const char *names[1] = { qname };
+	mm_map_batch(mi, 1, qlens, seqs, qname? names : nullptr, n_regs, regs, &rep_len, opt, 1);
+	if (b) {
+		b->rep_len = rep_len;
+		b->frag_gap = opt->max_gap_ref > 0? opt->max_gap_ref : opt->max_gap; // map.c:263-271,317
+	}
+}
+
+extern "C" mm_reg1_t *mm_map(const mm_idx_t *mi, int qlen, const char *seq, int *n_regs, mm_tbuf_t *b, const mm_mapopt_t *opt, const char *qname)
+{
+	mm_reg1_t *regs = nullptr;
+	mm_map_frag(mi, 1, &qlen, &seq, n_regs, &regs, b, opt, qname);
+	return regs;
+}
+
+// ---- mm_map_file (map.c:663-691): read mini-batches, map them on the GPU, print in input order ----
+extern "C" int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads)
+{
+	if (n_segs != 1) { fprintf(stderr, "[ERROR] minimap2_b200: multi-file (paired) input is not implemented\n"); return -1; }
+	FastxReader rd(fn[0]);
+	if (!rd.ok()) {
+		if (mm_verbose >= 1) fprintf(stderr, "ERROR: failed to open file '%s'\n", fn[0]);
+		return -1;
+	}
+	const bool with_qual = (opt->flag & MM_F_OUT_SAM) && !(opt->flag & MM_F_NO_QUAL);
+	const bool with_comment = (opt->flag & MM_F_COPY_COMMENT) != 0;
+	std::string out;
+	int64_t n_processed = 0;
+	for (;;) {
+		std::vector<FastxRecord> recs;
+		int64_t size = 0;
+		FastxRecord r;
+		int ret;
+		while ((ret = rd.next(r, with_qual, with_comment)) > 0) { // mm_bseq_read3 (bseq.c:80-119)
+			size += (int64_t)r.seq.size();
+			recs.push_back(std::move(r));
+			if (size >= opt->mini_batch_size) break;
+		}
+		if (recs.empty()) break;
+		const int n = (int)recs.size();
+		std::vector<int> qlens(n), n_regs(n), rep_len(n);
+		std::vector<const char*> seqs(n), names(n);
+		std::vector<mm_reg1_t*> regs(n);
+		for (int i = 0; i < n; ++i) qlens[i] = (int)recs[i].seq.size(), seqs[i] = recs[i].seq.c_str(), names[i] = recs[i].name.c_str();
+		mm_map_batch(idx, n, qlens.data(), seqs.data(), names.data(), n_regs.data(), regs.data(), rep_len.data(), opt, n_threads);
+		for (int i = 0; i < n; ++i) { // output step (map.c:578-641)
+			const char *qual = recs[i].qual.empty()? nullptr : recs[i].qual.c_str();
+			if (n_regs[i] > 0) {
+				for (int j = 0; j < n_regs[i]; ++j) {
+					const mm_reg1_t *rg = &regs[i][j];
+					if ((opt->flag & MM_F_NO_PRINT_2ND) && rg->id != rg->parent) continue;
+					out.clear();
+					if (opt->flag & MM_F_OUT_SAM) hl_write_sam(out, idx, names[i], seqs[i], qual, qlens[i], j, n_regs[i], regs[i], opt->flag, rep_len[i]);
+					else { hl_set_seq_for_tags(seqs[i]); hl_write_paf(out, idx, names[i], qlens[i], rg, opt->flag, rep_len[i]); }
+					if (with_comment && !recs[i].comment.empty()) out += "\t" + recs[i].comment;
+					puts(out.c_str());
+				}
+			} else if ((opt->flag & MM_F_PAF_NO_HIT) || ((opt->flag & MM_F_OUT_SAM) && !(opt->flag & MM_F_SAM_HIT_ONLY))) {
+				out.clear();
+				if (opt->flag & MM_F_OUT_SAM) hl_write_sam(out, idx, names[i], seqs[i], qual, qlens[i], -1, 0, nullptr, opt->flag, rep_len[i]);
+				else hl_write_paf(out, idx, names[i], qlens[i], nullptr, opt->flag, rep_len[i]);
+				if (with_comment && !recs[i].comment.empty()) out += "\t" + recs[i].comment;
+				puts(out.c_str());
+			}
+			for (int j = 0; j < n_regs[i]; ++j) free(regs[i][j].p);
+			free(regs[i]);
+		}
+		n_processed += n;
+		if (mm_verbose >= 3)
+			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), n);
+		if (ret <= 0) break;
+	}
+	fflush(stdout);
+	return 0;
+}
+
+extern "C" int mm_map_file(const mm_idx_t *idx, const char *fn, const mm_mapopt_t *opt, int n_threads)
+{
+	return mm_map_file_frag(idx, 1, &fn, opt, n_threads);
+}

@@ -1,0 +1,29 @@
+// minimap2_b200/csrc/pipeline.h -- device-side stage interfaces of the batch mapper (K1 -> K2a/b -> K2c -> K3).
+#pragma once
+#include "index.h"
+#include "mm_algo.cuh"
+
+struct SeedArgs {
+	DevIndexView ix;
+	int n_reads;
+	m128 *mz;                 // minimizers of all reads (sketch output), per-read slices at mz_off
+	const int64_t *mz_off;    // n_reads+1
+	int32_t *n_mz;            // live count per read (shrinks after the query-side filter)
+	const int32_t *qlen;
+	int q_occ_max; float q_occ_frac;
+	int max_occ, max_max_occ, occ_dist;
+	int64_t flag;
+	// per minimizer (same offsets as mz)
+	uint32_t *s_n; uint64_t *s_off;
+	uint32_t *k_idx, *k_aoff; uint8_t *flt; uint64_t *mini_pos;
+	// per read
+	int32_t *n_keep, *rep_len; int64_t *n_a;
+	// anchors
+	m128 *a; const int64_t *a_off;
+};
+
+void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz);
+void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, int64_t total_a, DevBuf &stkbuf);
+
+void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
+					  int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2);

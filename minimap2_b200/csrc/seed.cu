@@ -1,0 +1,269 @@
+// minimap2_b200/csrc/seed.cu
+//
+// K2a/K2b: seeds -> anchors on sm_100a. Replaces mm_seed_mz_flt (reference seed.c:5-28), mm_collect_matches /
+// mm_seed_collect_all / mm_seed_select (seed.c:30-132), mm_idx_get on the device index (index.c:93-110),
+// collect_seed_hits (map.c:168-204) and its radix_sort_128x (ksort.h:98-151, exact tie order).
+//
+// Stage kernels over a whole read batch (SoA arrays in HBM, per-read slices given by offset arrays):
+//   mzflt_kernel   1 thread / read      query-side high-multiplicity minimizer filter
+//   lookup_kernel  1 thread / minimizer hash-table probe: one 16 B slot load per probe (random HBM sector access)
+//   select_kernel  1 thread / read      tandem flags, high-occurrence streak selection (<=128-entry heap), rep_len,
+//                                       mini_pos, per-seed anchor offsets
+//   expand_kernel  1 thread / seed      occurrence list -> anchors (strand-normalised coordinates)
+//   sort_kernel    1 thread / read      exact emulation of the reference's unstable in-place MSD radix sort
+#include "index.h"
+#include "mm_algo.cuh"
+#include "scan.cuh"
+#include "pipeline.h"
+
+namespace {
+
+__device__ __forceinline__ int find_read(const int64_t *off, int n, int64_t t)
+{
+	int lo = 0, hi = n;
+	while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (off[mid] <= t) lo = mid; else hi = mid; }
+	return lo;
+}
+
+// heap-sort a uint64 array ascending (per-thread, in global scratch)
+__device__ void heapsort_u64(uint64_t *a, int n)
+{
+	for (int start = (n >> 1) - 1; start >= 0; --start) {
+		int i = start; uint64_t tmp = a[i];
+		for (int k; (k = 2 * i + 1) < n; i = k) { if (k + 1 < n && a[k] < a[k + 1]) ++k; if (a[k] <= tmp) break; a[i] = a[k]; }
+		a[i] = tmp;
+	}
+	for (int end = n - 1; end > 0; --end) {
+		uint64_t tmp = a[end]; a[end] = a[0];
+		int i = 0;
+		for (int k; (k = 2 * i + 1) < end; i = k) { if (k + 1 < end && a[k] < a[k + 1]) ++k; if (a[k] <= tmp) break; a[i] = a[k]; }
+		a[i] = tmp;
+	}
+}
+
+__global__ void __launch_bounds__(128) mzflt_kernel(SeedArgs A) // seed.c:5-28
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= A.n_reads) return;
+	const int64_t base = A.mz_off[rd];
+	const int n = A.n_mz[rd];
+	if (n <= A.q_occ_max || A.q_occ_frac <= 0.0f || A.q_occ_max <= 0) return;
+	m128 *mz = A.mz + base;
+	uint64_t *tmp = A.mini_pos + base; // free at this point
+	for (int i = 0; i < n; ++i) tmp[i] = mz[i].x;
+	heapsort_u64(tmp, n);
+	const float thres = (float)(uint64_t)n * A.q_occ_frac;
+	int k = 0;
+	for (int i = 0; i < n; ++i) {
+		const uint64_t x = mz[i].x;
+		int lo = 0, hi = n; // lower bound
+		while (lo < hi) { int mid = (lo + hi) >> 1; if (tmp[mid] < x) lo = mid + 1; else hi = mid; }
+		int lo2 = lo, hi2 = n; // upper bound
+		while (lo2 < hi2) { int mid = (lo2 + hi2) >> 1; if (tmp[mid] <= x) lo2 = mid + 1; else hi2 = mid; }
+		const int cnt = lo2 - lo;
+		const bool drop = cnt > A.q_occ_max && (float)cnt > thres;
+		// the reference zeroes x of dropped minimizers and then squeezes out x==0 entries (which also drops a genuine x==0)
+		if (!drop && x != 0) { if (k != i) mz[k] = mz[i]; ++k; }
+	}
+	A.n_mz[rd] = k;
+}
+
+__global__ void __launch_bounds__(256) lookup_kernel(SeedArgs A, int64_t total)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= total) return;
+	const int rd = find_read(A.mz_off, A.n_reads, t);
+	if (t - A.mz_off[rd] >= A.n_mz[rd]) return;
+	uint64_t off;
+	const uint32_t n = idx_get_dev(A.ix, A.mz[t].x >> 8, &off);
+	A.s_n[t] = n, A.s_off[t] = off;
+}
+
+__device__ __forceinline__ void heap_down(uint64_t *b, int i, int n) // max-heap sift-down (ksort.h:44-56 semantics)
+{
+	uint64_t tmp = b[i];
+	int k = i;
+	while ((k = (k << 1) + 1) < n) {
+		if (k != n - 1 && b[k] < b[k + 1]) ++k;
+		if (b[k] < tmp) break;
+		b[i] = b[k]; i = k;
+	}
+	b[i] = tmp;
+}
+
+__global__ void __launch_bounds__(128) select_kernel(SeedArgs A)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= A.n_reads) return;
+	const int64_t base = A.mz_off[rd];
+	const int n = A.n_mz[rd], qlen = A.qlen[rd];
+	const m128 *mz = A.mz + base;
+	const uint32_t *s_n = A.s_n + base;
+	uint32_t *kidx = A.k_idx + base;       // kept-seed list: minimizer index | tandem<<31 ; first used as the m[] list
+	uint8_t *flt = A.flt + base;
+	int n_m0 = 0;
+	for (int i = 0; i < n; ++i) { // mm_seed_collect_all (seed.c:30-52)
+		if (s_n[i] == 0) continue;
+		uint32_t tandem = 0;
+		if (i > 0 && mz[i].x >> 8 == mz[i - 1].x >> 8) tandem = 1;
+		if (i < n - 1 && mz[i].x >> 8 == mz[i + 1].x >> 8) tandem = 1;
+		kidx[n_m0] = (uint32_t)i | tandem << 31;
+		flt[n_m0] = 0;
+		++n_m0;
+	}
+#define SN(j) (s_n[kidx[j] & 0x7fffffffu])
+#define QPOS(j) ((uint32_t)mz[kidx[j] & 0x7fffffffu].y)
+	const int max_occ = A.max_occ, max_max_occ = A.max_max_occ, dist = A.occ_dist;
+	if (dist > 0 && max_max_occ > max_occ) { // mm_seed_select (seed.c:56-96)
+		int m = 0;
+		if (n_m0 > 1) for (int i = 0; i < n_m0; ++i) if ((int)SN(i) > max_occ) ++m;
+		if (m > 0) {
+			uint64_t b[128];
+			for (int i = 0, last0 = -1; i <= n_m0; ++i) {
+				if (i == n_m0 || (int)SN(i) <= max_occ) {
+					if (i - last0 > 1) {
+						const int ps = last0 < 0? 0 : (int)(QPOS(last0) >> 1);
+						const int pe = i == n_m0? qlen : (int)(QPOS(i) >> 1);
+						const int st = last0 + 1, en = i;
+						int max_high_occ = (int)((double)(pe - ps) / dist + .499);
+						if (max_high_occ > 0) {
+							if (max_high_occ > 128) max_high_occ = 128;
+							int j, k;
+							for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k) b[k] = (uint64_t)SN(j) << 32 | (uint32_t)j;
+							for (int h = (k >> 1) - 1; h >= 0; --h) heap_down(b, h, k);
+							for (; j < en; ++j)
+								if ((int32_t)SN(j) < (int32_t)(b[0] >> 32)) { b[0] = (uint64_t)SN(j) << 32 | (uint32_t)j; heap_down(b, 0, k); }
+							for (j = 0; j < k; ++j) flt[(uint32_t)b[j]] = 1;
+						}
+						for (int j = st; j < en; ++j) flt[j] ^= 1;
+						for (int j = st; j < en; ++j) if ((int)SN(j) > max_max_occ) flt[j] = 1;
+					}
+					last0 = i;
+				}
+			}
+		}
+	} else {
+		for (int i = 0; i < n_m0; ++i) if ((int)SN(i) > max_occ) flt[i] = 1;
+	}
+	// seed.c:113-130
+	int rep_st = 0, rep_en = 0, rep_len = 0, n_keep = 0;
+	int64_t n_a = 0;
+	uint64_t *mini_pos = A.mini_pos + base;
+	uint32_t *k_aoff = A.k_aoff + base;
+	for (int i = 0; i < n_m0; ++i) {
+		const uint32_t e = kidx[i], mi = e & 0x7fffffffu;
+		const uint32_t q_pos = (uint32_t)mz[mi].y, q_span = (uint32_t)(mz[mi].x & 0xff);
+		if (flt[i]) {
+			const int en = (int)(q_pos >> 1) + 1, st = en - (int)q_span;
+			if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st, rep_en = en; }
+			else rep_en = en;
+		} else {
+			k_aoff[n_keep] = (uint32_t)n_a;
+			n_a += s_n[mi];
+			mini_pos[n_keep] = (uint64_t)q_span << 32 | q_pos >> 1;
+			kidx[n_keep] = e;
+			++n_keep;
+		}
+	}
+	rep_len += rep_en - rep_st;
+	A.n_keep[rd] = n_keep, A.rep_len[rd] = rep_len, A.n_a[rd] = n_a;
+#undef SN
+#undef QPOS
+}
+
+__global__ void __launch_bounds__(256) expand_kernel(SeedArgs A, int64_t total) // map.c:176-199
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= total) return;
+	const int rd = find_read(A.mz_off, A.n_reads, t);
+	const int64_t base = A.mz_off[rd];
+	const int k = (int)(t - base);
+	if (k >= A.n_keep[rd]) return;
+	const uint32_t e = A.k_idx[t], mi = e & 0x7fffffffu;
+	const m128 q = A.mz[base + mi];
+	const uint32_t q_pos = (uint32_t)q.y, q_span = (uint32_t)(q.x & 0xff), seg_id = (uint32_t)(q.y >> 32);
+	const uint32_t n = A.s_n[base + mi];
+	const uint64_t *cr = A.ix.pos + A.s_off[base + mi];
+	m128 *a = A.a + A.a_off[rd] + A.k_aoff[t];
+	const int qlen = A.qlen[rd];
+	const bool qstrand = (A.flag & MM_F_QSTRAND) != 0;
+	for (uint32_t j = 0; j < n; ++j) {
+		const uint64_t r = cr[j];
+		const int32_t rpos = (int32_t)((uint32_t)r >> 1);
+		m128 p;
+		if ((r & 1) == (q_pos & 1)) {
+			p.x = (r & 0xffffffff00000000ULL) | (uint32_t)rpos;
+			p.y = (uint64_t)q_span << 32 | q_pos >> 1;
+		} else if (!qstrand) {
+			p.x = 1ULL << 63 | (r & 0xffffffff00000000ULL) | (uint32_t)rpos;
+			p.y = (uint64_t)q_span << 32 | (uint32_t)(qlen - ((int32_t)(q_pos >> 1) + 1 - (int32_t)q_span) - 1);
+		} else {
+			const int32_t len = (int32_t)A.ix.seq_len[r >> 32];
+			p.x = 1ULL << 63 | (r & 0xffffffff00000000ULL) | (uint32_t)(len - (rpos + 1 - (int32_t)q_span) - 1);
+			p.y = (uint64_t)q_span << 32 | q_pos >> 1;
+		}
+		p.y |= (uint64_t)seg_id << MMX_SEED_SEG_SHIFT;
+		if (e >> 31) p.y |= MMX_SEED_TANDEM;
+		a[j] = p;
+	}
+}
+
+__global__ void __launch_bounds__(128) sort_kernel(m128 *a, const int64_t *a_off, int n_reads, int32_t *stk, const int64_t *stk_off)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= n_reads) return;
+	const int64_t off = a_off[rd], n = a_off[rd + 1] - off;
+	if (n > 1) mmx_rs_sort(a + off, n, stk + stk_off[rd], KeyX128());
+}
+
+__global__ void stk_len_kernel2(const int64_t *a_off, int n_reads, int64_t *stk_off)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_reads) stk_off[i] = mmx_rs_stack_len(a_off[i + 1] - a_off[i]);
+}
+
+__global__ void copy_na_kernel(const int64_t *n_a, int n, int64_t *a_off)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) a_off[i] = n_a[i];
+}
+
+} // namespace
+
+// Runs mz-filter, lookup and selection; leaves A.n_a[] filled. Then the caller scans n_a into a_off, sizes the anchor
+// buffer and calls mmb_seed_expand_sort.
+void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz)
+{
+	if (A.n_reads <= 0) return;
+	const int rb = (A.n_reads + 127) / 128;
+	ProfScope prof(ctx, MMB_PROF_SEED, (uint64_t)total_mz);
+	if (A.flag & (MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_FOR_ONLY | MM_F_REV_ONLY | MM_F_HEAP_SORT)) {
+		fprintf(stderr, "[ERROR] minimap2_b200: --for-only/--rev-only/ava (-X) /sr heap-sort seeding are not supported by this build yet\n");
+		abort();
+	}
+	mzflt_kernel<<<rb, 128, 0, ctx->stream>>>(A);
+	if (total_mz > 0) lookup_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
+	select_kernel<<<rb, 128, 0, ctx->stream>>>(A);
+	MMB_CUDA_CHECK(cudaGetLastError());
+	ctx->n_launch += 3;
+}
+
+void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, int64_t total_a, DevBuf &stkbuf)
+{
+	if (A.n_reads <= 0) return;
+	{
+		ProfScope prof(ctx, MMB_PROF_SEED, 0);
+		if (total_mz > 0) expand_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
+		++ctx->n_launch;
+	}
+	int64_t *d_stk_off = (int64_t*)stkbuf.reserve(((size_t)A.n_reads + 1) * 8 + ((size_t)total_a / 65 * 24 + (size_t)A.n_reads * 48 + 64) * 4);
+	stk_len_kernel2<<<(A.n_reads + 255) / 256, 256, 0, ctx->stream>>>(A.a_off, A.n_reads, d_stk_off);
+	++ctx->n_launch;
+	mmb_exclusive_scan_i64_async(ctx, d_stk_off, A.n_reads);
+	{
+		ProfScope prof(ctx, MMB_PROF_SORT, (uint64_t)total_a);
+		sort_kernel<<<(A.n_reads + 127) / 128, 128, 0, ctx->stream>>>(A.a, A.a_off, A.n_reads, (int32_t*)(d_stk_off + A.n_reads + 1), d_stk_off);
+		++ctx->n_launch;
+	}
+	MMB_CUDA_CHECK(cudaGetLastError());
+}

@@ -32,7 +32,7 @@ struct SketchArgs {
 	const int64_t *chunk_off;   // n_seq+1: first chunk id of each sequence
 	const uint32_t *rid;        // optional per-sequence rid (NULL: rid0 + seq index)
 	uint32_t rid0;
-	int n_seq, w, k, is_hpc, chunk;
+	int n_seq, w, k, is_hpc, chunk, same_rid;
 	int64_t n_chunks;
 	int64_t *cnt;               // per chunk count (pass 0) / exclusive offsets (pass 1 input)
 	m128 *out;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) sketch_kernel(SketchArgs A)
 	const int64_t base = A.seq_off[s];
 	const int len = (int)(A.seq_off[s + 1] - base);
 	const int w = A.w, k = A.k;
-	const uint32_t rid = A.rid? A.rid[s] : A.rid0 + (uint32_t)s;
+	const uint32_t rid = A.rid? A.rid[s] : A.same_rid? A.rid0 : A.rid0 + (uint32_t)s;
 	int cs, ce;
 	if (A.is_hpc) { cs = 0, ce = len; }           // HPC: one chunk per sequence (positions jump over homopolymers)
 	else { cs = (int)((c - A.chunk_off[s]) * A.chunk); ce = min(len, cs + A.chunk); }
@@ -175,7 +175,7 @@ __global__ void seq_count_kernel(const int64_t *chunk_off, const int64_t *cnt_ex
 // Returns the total count (synchronises the stream once to size the output).
 int64_t mmb_sketch_device(mmb_ctx_t *ctx, const uint8_t *d_bytes, const uint32_t *d_packed, const int64_t *d_seq_off, int n_seq,
 						  const uint32_t *d_rid, uint32_t rid0, int w, int k, int is_hpc, int64_t total_bases,
-						  DevBuf &out, int64_t *d_mz_off, DevBuf &tmp_a, DevBuf &tmp_b)
+						  DevBuf &out, int64_t *d_mz_off, DevBuf &tmp_a, DevBuf &tmp_b, int same_rid)
 {
 	if (n_seq <= 0) return 0;
 	if (!(w > 0 && w < 256 && k > 0 && k <= 28)) { fprintf(stderr, "[ERROR] mm_sketch: invalid w=%d k=%d\n", w, k); abort(); }
@@ -193,7 +193,7 @@ int64_t mmb_sketch_device(mmb_ctx_t *ctx, const uint8_t *d_bytes, const uint32_t
 	SketchArgs A;
 	A.src.bytes = d_bytes, A.src.packed = d_packed;
 	A.seq_off = d_seq_off, A.chunk_off = d_chunk_off, A.rid = d_rid, A.rid0 = rid0;
-	A.n_seq = n_seq, A.w = w, A.k = k, A.is_hpc = is_hpc, A.chunk = chunk, A.n_chunks = n_chunks, A.cnt = d_cnt, A.out = nullptr;
+	A.n_seq = n_seq, A.w = w, A.k = k, A.is_hpc = is_hpc, A.chunk = chunk, A.n_chunks = n_chunks, A.cnt = d_cnt, A.out = nullptr, A.same_rid = same_rid;
 	const int threads = 128;
 	const unsigned grid = (unsigned)((n_chunks + threads - 1) / threads);
 	sketch_kernel<false><<<grid, threads, 0, ctx->stream>>>(A);
@@ -222,7 +222,7 @@ extern "C" int64_t mmb_sketch_batch_host(mmb_ctx_t *ctx, int n_seq, const char *
 	int64_t *d_mz_off = ctx->d_c.as<int64_t>((size_t)n_seq + 1);
 	MMB_CUDA_CHECK(cudaMemcpyAsync(d_seq, seqs, tot, cudaMemcpyHostToDevice, ctx->stream));
 	MMB_CUDA_CHECK(cudaMemcpyAsync(d_off, off, sizeof(int64_t) * (n_seq + 1), cudaMemcpyHostToDevice, ctx->stream));
-	int64_t total = mmb_sketch_device(ctx, d_seq, nullptr, d_off, n_seq, nullptr, rid0, w, k, is_hpc, tot, ctx->d_d, d_mz_off, ctx->d_e, ctx->d_f);
+	int64_t total = mmb_sketch_device(ctx, d_seq, nullptr, d_off, n_seq, nullptr, rid0, w, k, is_hpc, tot, ctx->d_d, d_mz_off, ctx->d_e, ctx->d_f, 0);
 	if (n_out) {
 		std::vector<int64_t> mo(n_seq + 1);
 		MMB_CUDA_CHECK(cudaMemcpyAsync(mo.data(), d_mz_off, sizeof(int64_t) * (n_seq + 1), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1,0 +1,66 @@
+"""GPU end-to-end parity: the B200 mapper's CLI output vs the unmodified reference binary (oracle/_ref/minimap2) on the
+same inputs -- every PAF column and tag (NM ms AS nn tp cm s1 s2 de/dv zd rl cg) must match byte for byte."""
+import os
+import subprocess
+import numpy as np
+import pytest
+import oracle_lib as O
+import synth
+
+pytestmark = pytest.mark.gpu
+ROOT = O.ROOT
+MINE = os.path.join(ROOT, "minimap2_b200", "minimap2-b200")
+DATA = os.path.join(ROOT, "tests", "golden", "data")
+
+
+def run(binary, args):
+    p = subprocess.run([binary] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    return p.stdout.decode().splitlines()
+
+
+def compare(args, sam=False):
+    ref = run(O.REF_BIN, ["-t", "4"] + args)
+    got = run(MINE, ["-t", "8"] + args)
+    if sam:
+        ref = [l for l in ref if not l.startswith("@PG")]
+        got = [l for l in got if not l.startswith("@PG")]
+    assert len(ref) == len(got), (len(ref), len(got))
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert a == b, "line %d differs:\nref: %s\ngot: %s" % (i, a[:600], b[:600])
+    return len(ref)
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_mt_paf():
+    assert compare(["-c", os.path.join(DATA, "MT-human.fa"), os.path.join(DATA, "MT-orang.fa")]) == 1
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_mt_sam_config0():
+    """BASELINE.json configs[0]: minimap2 -a test/MT-human.fa test/MT-orang.fa"""
+    compare(["-a", os.path.join(DATA, "MT-human.fa"), os.path.join(DATA, "MT-orang.fa")], sam=True)
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_mt_nocigar():
+    compare([os.path.join(DATA, "MT-human.fa"), os.path.join(DATA, "MT-orang.fa")])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_inversion_pair():
+    assert compare(["-c", os.path.join(DATA, "t-inv.fa"), os.path.join(DATA, "q-inv.fa")]) == 6
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg", [dict(seed=1, glen=2_000_000, n=300, rlen=10000, err=0.10, rep=0.0, chim=0.0),
+                                 dict(seed=2, glen=1_000_000, n=200, rlen=8000, err=0.12, rep=0.2, chim=0.1),
+                                 dict(seed=3, glen=500_000, n=300, rlen=3000, err=0.05, rep=0.1, chim=0.05)])
+def test_synthetic_map_ont(tmp_path, cfg):
+    contigs = synth.random_genome(cfg["glen"], cfg["seed"], n_contigs=3, repeat_frac=cfg["rep"])
+    reads = synth.make_reads(contigs, cfg["n"], cfg["rlen"], cfg["err"], cfg["seed"] + 100, chimeric_frac=cfg["chim"])
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    n = compare(["-x", "map-ont", "-c", "--cs", rf, qf])
+    assert n >= cfg["n"] * 0.9

@@ -10,7 +10,10 @@
 // is therefore replayed exactly by one thread over its own slice of the batch-wide SoA arrays in HBM; a launch covers
 // the whole batch (grid = ceil(n_reads/128)), scratch comes from one arena sized by the anchor count.
 #include "mmb_internal.h"
+#include <cstring>
 #include "mm_algo.cuh"
+#include "mm_rmq.cuh"
+#include "pipeline.h"
 
 namespace {
 
@@ -44,6 +47,55 @@ __device__ int32_t bk_end(int32_t max_drop, const m128 *z, const int32_t *f, con
 	} while (i >= 0 && t[i] == 0);
 	for (i = (int32_t)z[k].y; i >= 0 && i != end_i; i = p[i]) t[i] = 0;
 	return max_i;
+}
+
+
+// mg_chain_backtrack + compact_a (lchain.c:27-111) for one read; `ao` may alias `a`
+__device__ void backtrack_compact(const m128 *a, int32_t n, const int32_t *f, const int32_t *p, int32_t *v, int32_t *t, m128 *z, m128 *b,
+								  int32_t *stk, int32_t min_sc, int32_t min_cnt, int32_t max_drop, uint64_t *u, m128 *ao, int32_t *n_u_, int32_t *n_v_)
+{
+	int32_t n_z = 0;
+	*n_u_ = *n_v_ = 0;
+	for (int32_t i = 0; i < n; ++i) if (f[i] >= min_sc) z[n_z].x = (uint64_t)(int64_t)f[i], z[n_z++].y = (uint64_t)i;
+	if (n_z == 0) return;
+	mmx_rs_sort(z, (int64_t)n_z, stk, KeyX128());
+	int32_t n_u = 0, n_v = 0;
+	// the reference makes a counting pass and a filling pass with identical traversals; one filling pass suffices here
+	// because v[] (reused as the index list, as in the reference) and u[] have capacity n
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	for (int32_t k = n_z - 1; k >= 0; --k) {
+		if (t[z[k].y] == 0) {
+			const int32_t n_v0 = n_v, end_i = bk_end(max_drop, z, f, p, t, k);
+			int32_t i, sc;
+			for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
+			sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+			if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+			else n_v = n_v0;
+		}
+	}
+	*n_u_ = n_u, *n_v_ = n_v;
+	if (n_u == 0) return;
+	m128 *w = z; // z is free now; n_u <= n_z
+	int32_t k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t k0 = k, ni = (int32_t)u[i];
+		for (int32_t j = 0; j < ni; ++j) b[k++] = a[v[k0 + (ni - j - 1)]];
+	}
+	k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint64_t)i;
+		k += (int32_t)u[i];
+	}
+	mmx_rs_sort(w, (int64_t)n_u, stk, KeyX128());
+	k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t j = (int32_t)w[i].y, nn = (int32_t)u[j];
+		const int32_t src = (int32_t)(w[i].y >> 32);
+		w[i].x = u[j]; // keep the chain's u value next to its order (w[i].x is no longer needed)
+		for (int32_t q = 0; q < nn; ++q) ao[k + q] = b[src + q];
+		k += nn;
+	}
+	for (int32_t i = 0; i < n_u; ++i) u[i] = w[i].x;
 }
 
 __global__ void __launch_bounds__(128) chain_dp_kernel(ChainArgs A)
@@ -99,57 +151,116 @@ __global__ void __launch_bounds__(128) chain_dp_kernel(ChainArgs A)
 		if (best_prev < 0 || (ai.x - a[best_prev].x <= (uint64_t)(int64_t)max_dist_x && f[best_prev] < f[i])) best_prev = i;
 	}
 
-	// ---- backtrack (lchain.c:27-76) ----
-	m128 *z = A.z + off;
-	int32_t n_z = 0;
-	const int32_t min_sc = P.min_sc, min_cnt = P.min_cnt;
-	for (int32_t i = 0; i < n; ++i) if (f[i] >= min_sc) z[n_z].x = (uint64_t)(int64_t)f[i], z[n_z++].y = (uint64_t)i;
-	if (n_z == 0) return;
-	mmx_rs_sort(z, (int64_t)n_z, A.stk + A.stk_off[rd], KeyX128());
-	uint64_t *u = A.u + off;
-	int32_t n_u = 0, n_v = 0;
-	// the reference makes a counting pass and a filling pass with identical traversals; one filling pass suffices here
-	// because v[] (reused as the index list, as in the reference) and u[] have capacity n
-	for (int32_t i = 0; i < n; ++i) t[i] = 0;
-	for (int32_t k = n_z - 1; k >= 0; --k) {
-		if (t[z[k].y] == 0) {
-			const int32_t n_v0 = n_v, end_i = bk_end(max_drop, z, f, p, t, k);
-			int32_t i, sc;
-			for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
-			sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
-			if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
-			else n_v = n_v0;
-		}
-	}
+	int32_t n_u, n_v;
+	backtrack_compact(a, n, f, p, v, t, A.z + off, A.b + off, A.stk + A.stk_off[rd], P.min_sc, P.min_cnt, max_drop, A.u + off, A.a_out + off, &n_u, &n_v);
 	A.n_u[rd] = n_u, A.n_v[rd] = n_v;
-	if (n_u == 0) return;
+}
 
-	// ---- compact (lchain.c:78-111) ----
-	m128 *b = A.b + off, *w = z; // z is free now; n_u <= n_z
-	int32_t k = 0;
-	for (int32_t i = 0; i < n_u; ++i) {
-		const int32_t k0 = k, ni = (int32_t)u[i];
-		for (int32_t j = 0; j < ni; ++j) b[k++] = a[v[k0 + (ni - j - 1)]];
+// ---------------------------------------------------------------------------------------------------------
+// Long-join rescue (map.c:283-292): reads whose first-round chaining left more than one chain and whose best chain
+// leaves a long unchained part are re-sorted (radix_sort_128x, exact tie order) and re-chained with mg_lchain_rmq
+// (lchain.c:250-368) at bw_long. One thread per read; the two balanced trees of the reference live in per-read slices of
+// an HBM arena (mm_rmq.cuh).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ RmqTree tree_at(uint8_t *base, int32_t n)
+{
+	RmqTree T;
+	const size_t m = (size_t)n + 1;
+	T.pri = (double*)base;
+	T.c[0] = (int32_t*)(base + 8 * m), T.c[1] = T.c[0] + m, T.s = T.c[1] + m;
+	T.size = (uint32_t*)(T.s + m), T.y = (int32_t*)(T.size + m);
+	T.bal = (int8_t*)(T.y + m);
+	T.root = RMQ_NIL, T.n = n;
+	return T;
+}
+
+__global__ void __launch_bounds__(64) chain_rescue_kernel(ChainArgs A, RescuePar R)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= A.n_reads) return;
+	const int32_t n_u0 = A.n_u[rd];
+	if (n_u0 <= 1) return;
+	const int64_t off = A.a_off[rd];
+	m128 *a = A.a_out + off;
+	uint64_t *u = A.u + off;
+	const int32_t n = A.n_v[rd], qlen = R.qlen[rd];
+	{
+		const int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
+		if (!(qlen - (en - st) > R.rescue_size || (float)(en - st) > (float)qlen * R.rescue_ratio)) return;
 	}
-	k = 0;
-	for (int32_t i = 0; i < n_u; ++i) {
-		w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint64_t)i;
-		k += (int32_t)u[i];
+	int32_t *stk = A.stk + A.stk_off[rd];
+	mmx_rs_sort(a, (int64_t)n, stk, KeyX128());
+	int32_t *f = A.f + off, *p = A.p + off, *v = A.v + off, *t = A.t + off;
+	int32_t max_dist = R.max_dist, max_dist_inner = R.max_dist_inner;
+	const int32_t bw = R.bw, max_chn_skip = R.max_skip, cap = R.rmq_size_cap;
+	const float pen_gap = R.pen_gap, pen_skip = R.pen_skip;
+	if (max_dist < bw) max_dist = bw;
+	if (max_dist_inner < 0) max_dist_inner = 0;
+	if (max_dist_inner > max_dist) max_dist_inner = max_dist;
+	uint8_t *tb = R.tree + ((size_t)R.tree_off[rd] + (size_t)rd) * 64;
+	RmqTree T0 = tree_at(tb, n), T1 = tree_at(tb + (size_t)32 * (n + 1), n);
+	for (int32_t i = 0; i < n; ++i) t[i] = 0;
+	int32_t i0 = 0, st = 0, st_inner = 0;
+	for (int32_t i = 0; i < n; ++i) {
+		int32_t max_j = -1, q_span = (int32_t)(a[i].y >> 32 & 0xff), max_f = q_span;
+		if (i0 < i && a[i0].x != a[i].x) { // add in-range anchors (lchain.c:281-294)
+			for (int32_t j = i0; j < i; ++j) {
+				const double pri = -((double)f[j] + 0.5 * (double)pen_gap * (double)(int32_t)((uint32_t)a[j].x + (uint32_t)a[j].y));
+				T0.y[j] = (int32_t)a[j].y, T0.pri[j] = pri;
+				rmq_insert(T0, j);
+				if (max_dist_inner > 0) { T1.y[j] = (int32_t)a[j].y, T1.pri[j] = pri; rmq_insert(T1, j); }
+			}
+			i0 = i;
+		}
+		// drop anchors that fell out of range (lchain.c:296-313)
+		while (st < i && (a[i].x >> 32 != a[st].x >> 32 || a[i].x > a[st].x + (uint64_t)(int64_t)max_dist || (T0.root >= 0? (int32_t)T0.size[T0.root] : 0) > cap)) {
+			if (rmq_find(T0, (int32_t)a[st].y, st) >= 0) rmq_erase(T0, (int32_t)a[st].y, st);
+			++st;
+		}
+		if (max_dist_inner > 0) {
+			while (st_inner < i && (a[i].x >> 32 != a[st_inner].x >> 32 || a[i].x > a[st_inner].x + (uint64_t)(int64_t)max_dist_inner || (T1.root >= 0? (int32_t)T1.size[T1.root] : 0) > cap)) {
+				if (rmq_find(T1, (int32_t)a[st_inner].y, st_inner) >= 0) rmq_erase(T1, (int32_t)a[st_inner].y, st_inner);
+				++st_inner;
+			}
+		}
+		// RMQ (lchain.c:315-350)
+		const int32_t yi = (int32_t)a[i].y;
+		int32_t q = rmq_query(T0, yi - max_dist, (int64_t)INT32_MAX, yi, 0);
+		if (q >= 0) {
+			int32_t sc, exact, width, n_skip = 0, j = q;
+			sc = f[j] + mmx_comput_sc_simple(a[i], a[j], pen_gap, pen_skip, &exact, &width);
+			if (width <= bw && sc > max_f) max_f = sc, max_j = j;
+			if (!exact && T1.root >= 0 && yi > 0) {
+				int32_t lo, hi;
+				rmq_interval(T1, yi - 1, (int64_t)n, &lo, &hi);
+				if (lo >= 0) {
+					RmqItr itr;
+					rmq_itr_find(T1, T1.y[lo], (int64_t)lo, &itr);
+					int32_t qq;
+					while ((qq = rmq_itr_at(&itr)) >= 0) {
+						if (T1.y[qq] < yi - max_dist_inner) break;
+						j = qq;
+						sc = f[j] + mmx_comput_sc_simple(a[i], a[j], pen_gap, pen_skip, 0, &width);
+						if (width <= bw) {
+							if (sc > max_f) {
+								max_f = sc, max_j = j;
+								if (n_skip > 0) --n_skip;
+							} else if (t[j] == i) {
+								if (++n_skip > max_chn_skip) break;
+							}
+							if (p[j] >= 0) t[p[j]] = i;
+						}
+						if (!rmq_itr_next_bidir(T1, &itr, 0)) break;
+					}
+				}
+			}
+		}
+		f[i] = max_f, p[i] = max_j;
+		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
 	}
-	mmx_rs_sort(w, (int64_t)n_u, A.stk + A.stk_off[rd], KeyX128());
-	// u2 -> stored temporarily in f/p space (8 bytes per entry): reuse t,v? use (uint64_t*)f with capacity n/2: not enough
-	// in general, so write the reordered u[] through the (now free) v/t pair viewed as uint64 when n_u*2 <= n, else in place
-	// via a second buffer carved from b's tail. Simplest exact approach: stash old u into z's y-field copies first.
-	m128 *ao = A.a_out + off;
-	k = 0;
-	for (int32_t i = 0; i < n_u; ++i) {
-		const int32_t j = (int32_t)w[i].y, nn = (int32_t)u[j];
-		const int32_t src = (int32_t)(w[i].y >> 32);
-		w[i].x = u[j]; // keep the chain's u value next to its order (w[i].x is no longer needed)
-		for (int32_t q = 0; q < nn; ++q) ao[k + q] = b[src + q];
-		k += nn;
-	}
-	for (int32_t i = 0; i < n_u; ++i) u[i] = w[i].x;
+	int32_t n_u, n_v;
+	backtrack_compact(a, n, f, p, v, t, A.z + off, A.b + off, stk, R.min_sc, R.min_cnt, bw, u, a, &n_u, &n_v);
+	A.n_u[rd] = n_u, A.n_v[rd] = n_v;
 }
 
 __global__ void stk_len_kernel(const int64_t *a_off, int n_reads, int64_t *stk_off)
@@ -209,4 +320,28 @@ extern "C" int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, 
 	MMB_CUDA_CHECK(cudaMemcpyAsync(a_out_xy, d_ao, sizeof(m128) * n_tot, cudaMemcpyDeviceToHost, ctx->stream));
 	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	return 0;
+}
+
+// Re-chain (on the device) the reads that qualify for the long-join rescue. Must follow mmb_chain_device on the same
+// buffers (it reuses the scratch set up there). d_tree_off: per-read exclusive offsets of n_v (n_reads+1), total tot_v.
+void mmb_chain_rescue_device(mmb_ctx_t *ctx, const RescuePar *rp, int n_reads, const int64_t *d_a_off, int64_t n_tot,
+							 int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf, int64_t tot_v)
+{
+	if (n_reads <= 0) return;
+	ChainArgs A;
+	memset(&A, 0, sizeof(A));
+	A.n_reads = n_reads, A.a_off = d_a_off, A.a = nullptr;
+	const size_t n = (size_t)n_tot + 4;
+	uint8_t *s = (uint8_t*)scratch.p;
+	A.f = (int32_t*)s, A.p = A.f + n, A.v = A.p + n, A.t = A.v + n;
+	A.z = (m128*)(s + n * 16), A.b = A.z + n;
+	int64_t *d_stk_off = (int64_t*)scratch2.p;
+	A.stk_off = d_stk_off, A.stk = (int32_t*)(d_stk_off + n_reads + 1);
+	A.n_u = d_n_u, A.n_v = d_n_v, A.u = d_u, A.a_out = d_a_out;
+	RescuePar R = *rp;
+	R.tree = (uint8_t*)treebuf.reserve(((size_t)tot_v + (size_t)n_reads + 8) * 64);
+	ProfScope prof(ctx, MMB_PROF_CHAIN, 0);
+	chain_rescue_kernel<<<(n_reads + 63) / 64, 64, 0, ctx->stream>>>(A, R);
+	MMB_CUDA_CHECK(cudaGetLastError());
+	++ctx->n_launch;
 }

@@ -218,11 +218,21 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	uint64_t *d_u = bb.u.as<uint64_t>((size_t)total_a + 4);
 	m128 *d_a_out = bb.a_out.as<m128>((size_t)total_a + 4);
 	mmb_chain_device(ctx, &cp, n, S.a, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2);
-	// TODO(long-join rescue, map.c:283-292): re-chain with mg_lchain_rmq on the device when n_regs0>1
-
 	// dense copies for the host: offsets for u, a and mini_pos
 	int64_t *d_doff = bb.doff.as<int64_t>((size_t)(n + 1) * 3);
 	int64_t *d_uo = d_doff, *d_vo = d_doff + (n + 1), *d_mo = d_doff + 2 * (n + 1);
+	// long-join rescue (map.c:283-292): re-chain on the device with mg_lchain_rmq at bw_long
+	if (opt->bw_long > opt->bw && (opt->flag & (MM_F_SPLICE | MM_F_SR | MM_F_NO_LJOIN)) == 0) {
+		to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_n_v, n, d_vo);
+		++ctx->n_launch;
+		const int64_t tv = mmb_exclusive_scan_i64(ctx, d_vo, n, true);
+		RescuePar rp;
+		rp.qlen = d_qlen, rp.rescue_size = opt->rmq_rescue_size, rp.rescue_ratio = opt->rmq_rescue_ratio;
+		rp.max_dist = opt->max_gap, rp.max_dist_inner = opt->rmq_inner_dist, rp.bw = opt->bw_long, rp.max_skip = opt->max_chain_skip;
+		rp.rmq_size_cap = opt->rmq_size_cap, rp.min_cnt = opt->min_cnt, rp.min_sc = opt->min_chain_score;
+		rp.pen_gap = cp.chn_pen_gap, rp.pen_skip = cp.chn_pen_skip, rp.tree = nullptr, rp.tree_off = d_vo;
+		mmb_chain_rescue_device(ctx, &rp, n, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2, bb.t1, tv);
+	}
 	to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_n_u, n, d_uo);
 	to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_n_v, n, d_vo);
 	to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(S.n_keep, n, d_mo);

@@ -27,3 +27,13 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 
 void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
 					  int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2);
+
+struct RescuePar {            // long-join rescue with mg_lchain_rmq (map.c:283-292)
+	const int32_t *qlen;
+	int32_t rescue_size; float rescue_ratio;
+	int32_t max_dist, max_dist_inner, bw, max_skip, rmq_size_cap, min_cnt, min_sc;
+	float pen_gap, pen_skip;
+	uint8_t *tree; const int64_t *tree_off;
+};
+void mmb_chain_rescue_device(mmb_ctx_t *ctx, const RescuePar *rp, int n_reads, const int64_t *d_a_off, int64_t n_tot,
+							 int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf, int64_t tot_v);

@@ -111,27 +111,59 @@ __device__ __forceinline__ void push_cigar(uint32_t *cig, int &n, uint32_t op, i
 	else cig[n - 1] += (uint32_t)len << 4;
 }
 
-// ksw2.h:130-162 (rotated layout), off/off_end recomputed
-__device__ int backtrack(const uint8_t *p, int n_col, int qlen, int tlen, int w, int i0, int j0, uint32_t *cig)
+// ksw2.h:130-162 (rotated layout), off/off_end recomputed. The walk is inherently serial (one state machine), but each
+// step only needs one traceback byte that lies inside a 32-row x 32-column window below-left of the current cell (a step
+// lowers r by 1 or 2 and i by 0 or 1). The warp therefore stages that window from HBM/L2 into shared memory with 32
+// independent loads per lane (one memory latency per ~16-32 steps instead of one per step), then lane 0 walks inside it.
+__device__ int backtrack_tiled(const uint8_t *p, int n_col, int qlen, int tlen, int w, int i0, int j0, uint32_t *cig, uint8_t *tile, int lane)
 {
 	int n = 0, i = i0, j = j0, state = 0;
-	while (i >= 0 && j >= 0) {
-		int r = i + j, st0, en0, force = -1;
-		diag_bounds(r, qlen, tlen, w, st0, en0);
-		int off = st0 / 16 * 16, off_end = (en0 + 16) / 16 * 16 - 1;
-		if (i < off) force = 2;
-		if (i > off_end) force = 1;
-		uint32_t tmp = force < 0? p[(size_t)r * n_col + i - off] : 0;
-		if (state == 0) state = tmp & 7;
-		else if (!(tmp >> (state + 2) & 1)) state = 0;
-		if (state == 0) state = tmp & 7;
-		if (force >= 0) state = force;
-		if (state == 0) push_cigar(cig, n, 0, 1), --i, --j;
-		else if (state == 1 || state == 3) push_cigar(cig, n, 2, 1), --i;
-		else push_cigar(cig, n, 1, 1), --j;
+	for (;;) {
+		int go = i >= 0 && j >= 0;
+		go = __shfl_sync(0xffffffffu, go, 0);
+		if (!go) break;
+		const int rt = __shfl_sync(0xffffffffu, i + j, 0), it = __shfl_sync(0xffffffffu, i, 0); // tile anchor: row rt, right column it
+		{ // lane k stages row rt-k, columns it-31..it
+			const int rr = rt - lane;
+			uint8_t *trow = tile + lane * 32;
+			if (rr >= 0) {
+				int st0, en0;
+				diag_bounds(rr, qlen, tlen, w, st0, en0);
+				const int off = st0 / 16 * 16, off_end = (en0 + 16) / 16 * 16 - 1;
+				const uint8_t *prow = p + (size_t)rr * n_col - off;
+				#pragma unroll 8
+				for (int c = 0; c < 32; ++c) {
+					const int col = it - 31 + c;
+					trow[c] = (col >= off && col <= off_end)? prow[col] : 0;
+				}
+			}
+		}
+		__syncwarp();
+		if (lane == 0) {
+			while (i >= 0 && j >= 0) {
+				const int r = i + j;
+				if (rt - r > 31) break; // left the staged window
+				int st0, en0, force = -1;
+				diag_bounds(r, qlen, tlen, w, st0, en0);
+				const int off = st0 / 16 * 16, off_end = (en0 + 16) / 16 * 16 - 1;
+				if (i < off) force = 2;
+				if (i > off_end) force = 1;
+				const uint32_t tmp = force < 0? tile[(rt - r) * 32 + (i - (it - 31))] : 0;
+				if (state == 0) state = tmp & 7;
+				else if (!(tmp >> (state + 2) & 1)) state = 0;
+				if (state == 0) state = tmp & 7;
+				if (force >= 0) state = force;
+				if (state == 0) push_cigar(cig, n, 0, 1), --i, --j;
+				else if (state == 1 || state == 3) push_cigar(cig, n, 2, 1), --i;
+				else push_cigar(cig, n, 1, 1), --j;
+			}
+		}
+		__syncwarp();
 	}
-	if (i >= 0) push_cigar(cig, n, 2, i + 1);
-	if (j >= 0) push_cigar(cig, n, 1, j + 1);
+	if (lane == 0) {
+		if (i >= 0) push_cigar(cig, n, 2, i + 1);
+		if (j >= 0) push_cigar(cig, n, 1, j + 1);
+	}
 	return n;
 }
 
@@ -145,8 +177,9 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 	const int wk = threadIdx.x / G, g = threadIdx.x % G;
 	const int worker = blockIdx.x * NW + wk;
 	const int L = A.L, LQ = A.LQ;
-	const size_t wbytes = (size_t)15 * L + LQ + 64;
+	const size_t wbytes = (size_t)15 * L + LQ + 64 + 1024;
 	uint8_t *base = smem_raw + wbytes * wk;
+	uint8_t *bt_tile = base + wbytes - 1024;
 	// state arrays (all offsets multiples of 16)
 	uint8_t *u = base, *y = u + L, *y2 = y + L, *s = y2 + L, *sf = s + L;
 	uint8_t *vb[2] = { sf + L, sf + 2 * L }, *xb[2] = { sf + 3 * L, sf + 4 * L }, *x2b[2] = { sf + 5 * L, sf + 6 * L };
@@ -386,7 +419,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 			else if (ez.max_t >= 0 && ez.max_q >= 0) bi = ez.max_t, bj = ez.max_q;
 			__threadfence_block();
 			gsync<G>();
-			if (g == 0 && bi >= 0) n_cig = backtrack(p, n_col, qlen, tlen, w, bi, bj, cig);
+			if (g < 32 && bi >= 0) n_cig = backtrack_tiled(p, n_col, qlen, tlen, w, bi, bj, cig, bt_tile, g);
 			if (G == 32) n_cig = __shfl_sync(0xffffffffu, n_cig, 0);
 			else { if (g == 0) s_red[0] = n_cig; __syncthreads(); n_cig = s_red[0]; __syncthreads(); }
 		}
@@ -546,12 +579,13 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 	const Tier tiers[] = { {256, 32, 8}, {512, 32, 8}, {1024, 32, 4}, {13000, 256, 1} };
 	const int n_tiers = 4;
 	std::vector<std::vector<int>> tj(n_tiers + 1);
-	uint64_t cells = 0;
+	uint64_t cells = 0, io_bytes = 0;
 	std::vector<int> llj;
 	for (int i = 0; i < n_jobs; ++i) {
 		if (h_jobs[i].flag & MMB_JOB_LL) { llj.push_back(i); continue; }
 		int m = std::max(h_jobs[i].qlen, h_jobs[i].tlen), k = 0;
 		cells += (uint64_t)std::max(h_jobs[i].qlen, 0) * std::max(h_jobs[i].tlen, 0);
+		io_bytes += (uint64_t)std::max(h_jobs[i].qlen, 0) + std::max(h_jobs[i].tlen, 0) + 40;
 		while (k < n_tiers && m > tiers[k].maxlen) ++k;
 		tj[k].push_back(i);
 	}
@@ -581,6 +615,7 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		++ctx->n_launch;
 		MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	}
+	if (ctx->profiling) ctx->prof_bytes[MMB_PROF_KSW] += io_bytes + cells; // reference-layout algorithmic bytes: sequences + 1 B/cell traceback (+4 B per CIGAR op, added by the caller)
 	ProfScope prof(ctx, MMB_PROF_KSW, cells);
 	for (int k = 0; k < n_tiers; ++k) {
 		std::vector<int> &v = tj[k];
@@ -599,7 +634,7 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		}
 		A.L = (maxt + 15) / 16 * 16, A.LQ = (maxq + 15) / 16 * 16;
 		const int G = tiers[k].G, nw = tiers[k].nw, threads = G * nw;
-		size_t smem = ((size_t)15 * A.L + A.LQ + 64) * nw;
+		size_t smem = ((size_t)15 * A.L + A.LQ + 64 + 1024) * nw;
 		int cta_per_sm = 1;
 		if (G == 32) {
 			MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smem, ctx->smem_optin)));

@@ -60,6 +60,17 @@ extern "C" void mmb_profile_enable(mmb_ctx_t *c, int on) { c->profiling = on; }
 extern "C" double mmb_profile_ms(mmb_ctx_t *c, int which, int reset)
 {
 	if (which < 0 || which >= MMB_PROF_N) return 0.0;
+	if (!c->ev_pending[which].empty()) { // resolve queued event pairs
+		MMB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+		for (auto &pr : c->ev_pending[which]) {
+			float ms = 0;
+			MMB_CUDA_CHECK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+			c->prof_ms[which] += ms;
+			++c->prof_launches[which];
+			c->ev_pool.push_back(pr.first); c->ev_pool.push_back(pr.second);
+		}
+		c->ev_pending[which].clear();
+	}
 	double v = c->prof_ms[which];
 	if (reset) c->prof_ms[which] = 0;
 	return v;
@@ -97,3 +108,28 @@ extern "C" int64_t mmb_ksw_batch_host(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc,
 	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	return (int64_t)used;
 }
+
+mmb_ctx_t *mmb_default_ctx(void);
+extern "C" void *mmb_default_ctx_c(void) { return (void*)mmb_default_ctx(); }
+extern "C" void mmb_free(void *p) { free(p); }
+
+extern "C" uint64_t mmb_profile_scopes(mmb_ctx_t *c, int which, int reset)
+{
+	if (which < 0 || which >= MMB_PROF_N) return 0;
+	mmb_profile_ms(c, which, 0);
+	uint64_t v = c->prof_launches[which];
+	if (reset) c->prof_launches[which] = 0;
+	return v;
+}
+
+extern "C" uint64_t mmb_profile_bytes(mmb_ctx_t *c, int which, int reset)
+{
+	if (which < 0 || which >= MMB_PROF_N) return 0;
+	uint64_t v = c->prof_bytes[which];
+	if (reset) c->prof_bytes[which] = 0;
+	return v;
+}
+static int g_resident_reads = 0;
+extern "C" void mmb_set_resident_reads(int on) { g_resident_reads = on; }
+int mmb_resident_reads(void) { return g_resident_reads; }
+extern "C" uint64_t mmb_last_d2h_bytes(void) { return mmb_default_ctx()->last_d2h_bytes; }

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <utility>
 #include "mm_b200.h"
 
 extern "C" int mm_verbose;
@@ -61,23 +62,31 @@ struct mmb_ctx_s {
 	double prof_ms[MMB_PROF_N] = {0};
 	uint64_t prof_units[MMB_PROF_N] = {0};
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::vector<cudaEvent_t> ev_pool;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pending[MMB_PROF_N];
+	uint64_t prof_launches[MMB_PROF_N] = {0};
+	uint64_t prof_bytes[MMB_PROF_N] = {0};   // algorithmic bytes (SURVEY 8d definitions)
+	uint64_t last_d2h_bytes = 0, last_h2d_bytes = 0;
 	// scratch used by the kernel-level host entry points
 	DevBuf d_a, d_b, d_c, d_d, d_e, d_f, d_g, d_h;
 };
 
-// RAII-ish timing of one kernel family on the ctx stream (only when profiling is enabled; synchronous then)
+// Timing of one kernel family on the ctx stream with CUDA events (only when profiling is enabled). Asynchronous: the event
+// pairs are queued and resolved by mmb_profile_ms(), so enabling profiling does not serialise the pipeline.
 struct ProfScope {
-	mmb_ctx_t *c; int which;
+	mmb_ctx_t *c; int which; cudaEvent_t e0 = nullptr, e1 = nullptr;
 	ProfScope(mmb_ctx_t *ctx, int w, uint64_t units) : c(ctx), which(w) {
-		if (c->profiling) { MMB_CUDA_CHECK(cudaEventRecord(c->ev0, c->stream)); c->prof_units[w] += units; }
+		if (c->profiling) {
+			c->prof_units[w] += units;
+			if (!c->ev_pool.empty()) { e0 = c->ev_pool.back(); c->ev_pool.pop_back(); } else MMB_CUDA_CHECK(cudaEventCreate(&e0));
+			if (!c->ev_pool.empty()) { e1 = c->ev_pool.back(); c->ev_pool.pop_back(); } else MMB_CUDA_CHECK(cudaEventCreate(&e1));
+			MMB_CUDA_CHECK(cudaEventRecord(e0, c->stream));
+		}
 	}
 	~ProfScope() {
-		if (c->profiling) {
-			float ms = 0;
-			MMB_CUDA_CHECK(cudaEventRecord(c->ev1, c->stream));
-			MMB_CUDA_CHECK(cudaEventSynchronize(c->ev1));
-			MMB_CUDA_CHECK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-			c->prof_ms[which] += ms;
+		if (e0) {
+			MMB_CUDA_CHECK(cudaEventRecord(e1, c->stream));
+			c->ev_pending[which].push_back(std::make_pair(e0, e1));
 		}
 	}
 };

@@ -554,6 +554,11 @@ __global__ void __launch_bounds__(128) ksw_ll_kernel(LLArgs A)
 
 } // namespace
 
+bool mmb_ksw_fast_eligible(const mmb_ksw_job_t &j);
+void mmb_ksw_fast_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vector<int> &idx, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
+						 const uint8_t *d_query, const void *d_target, int t_packed, mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap,
+						 unsigned long long *d_cigar_used, DevBuf &pws, DevBuf &cigws, DevBuf &orderbuf);
+
 // Host-side tiering + launch. Tiers by max(qlen,tlen): warp-per-job for <=1024, CTA-per-job above.
 void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
 					const uint8_t *d_query, const void *d_target, int t_packed,
@@ -580,9 +585,15 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 	const int n_tiers = 4;
 	std::vector<std::vector<int>> tj(n_tiers + 1);
 	uint64_t cells = 0, io_bytes = 0;
-	std::vector<int> llj;
+	std::vector<int> llj, fastj;
+	static const bool use_fast = getenv("MM_B200_NO_FAST_KSW") == nullptr;
 	for (int i = 0; i < n_jobs; ++i) {
 		if (h_jobs[i].flag & MMB_JOB_LL) { llj.push_back(i); continue; }
+		if (use_fast && mmb_ksw_fast_eligible(h_jobs[i])) {
+			fastj.push_back(i);
+			cells += (uint64_t)h_jobs[i].qlen * h_jobs[i].tlen, io_bytes += (uint64_t)h_jobs[i].qlen + h_jobs[i].tlen + 40;
+			continue;
+		}
 		int m = std::max(h_jobs[i].qlen, h_jobs[i].tlen), k = 0;
 		cells += (uint64_t)std::max(h_jobs[i].qlen, 0) * std::max(h_jobs[i].tlen, 0);
 		io_bytes += (uint64_t)std::max(h_jobs[i].qlen, 0) + std::max(h_jobs[i].tlen, 0) + 40;
@@ -605,7 +616,7 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		int grid = (groups * 8 + 127) / 128;
 		groups = grid * 16;
 		L.ws = (int16_t*)ctx->d_e.reserve(L.ws_stride * (size_t)groups);
-		int *d_order = (int*)ctx->d_g.reserve((llj.size() + 1) * sizeof(int));
+		int *d_order = (int*)ctx->d_g.reserve(((size_t)n_jobs * 3 + 256) * sizeof(int)) + (size_t)n_jobs * 2 + 128;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, llj.data(), llj.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		L.counter = d_order, L.order = d_order + 1;
@@ -613,10 +624,12 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		ksw_ll_kernel<<<grid, 128, 0, ctx->stream>>>(L);
 		MMB_CUDA_CHECK(cudaGetLastError());
 		++ctx->n_launch;
-		MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	}
 	if (ctx->profiling) ctx->prof_bytes[MMB_PROF_KSW] += io_bytes + cells; // reference-layout algorithmic bytes: sequences + 1 B/cell traceback (+4 B per CIGAR op, added by the caller)
 	ProfScope prof(ctx, MMB_PROF_KSW, cells);
+	ctx->d_g.reserve(((size_t)n_jobs * 3 + 256) * sizeof(int)); // queues: [0,n) fast path | [n+64,2n+..) universal tiers | [2n+128,..) ll
+	size_t g_off = (size_t)n_jobs + 64;
+	mmb_ksw_fast_launch(ctx, sc, fastj, h_jobs, d_jobs, d_query, d_target, t_packed, d_res, d_cigar, cigar_cap, d_cigar_used, ctx->d_e, ctx->d_f, ctx->d_g);
 	for (int k = 0; k < n_tiers; ++k) {
 		std::vector<int> &v = tj[k];
 		if (v.empty()) continue;
@@ -657,7 +670,7 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		A.pws_stride = maxp, A.cigws_stride = (size_t)maxsum + 8;
 		A.pws = (uint8_t*)ctx->d_e.reserve(A.pws_stride * (size_t)grid * nw);
 		A.cigws = (uint32_t*)ctx->d_f.reserve(A.cigws_stride * 4 * (size_t)grid * nw);
-		int *d_order = (int*)ctx->d_g.reserve((v.size() + 1) * sizeof(int));
+		int *d_order = (int*)ctx->d_g.reserve(((size_t)n_jobs * 3 + 256) * sizeof(int)) + g_off; g_off += v.size() + 1;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		A.counter = d_order, A.order = d_order + 1, A.n = (int)v.size();
@@ -665,8 +678,5 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		else ksw_extd2_kernel<256><<<grid, threads, smem, ctx->stream>>>(A);
 		MMB_CUDA_CHECK(cudaGetLastError());
 		++ctx->n_launch;
-		// the order buffer / workspaces are reused by the next tier: serialise on the stream (same stream => ordered),
-		// but the host vector must stay alive until the copy is done
-		MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 	}
 }

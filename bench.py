@@ -275,10 +275,10 @@ def main():
     log("warm-up x%d" % a.warmup)
     run_steps(max(a.warmup, 1), True)
     # --- timed region A: `value` (read bases resident in HBM) ---
-    L.mmb_profile_enable(ctx, 1)
+    L.mmb_profile_enable_all(1)
     for k in range(6):
-        L.mmb_profile_ms(ctx, k, 1); L.mmb_profile_units(ctx, k, 1); L.mmb_profile_bytes(ctx, k, 1); L.mmb_profile_scopes(ctx, k, 1)
-    L.mmb_launch_count(ctx, 1)
+        L.mmb_profile_ms_all(k, 1); L.mmb_profile_units_all(k, 1); L.mmb_profile_bytes_all(k, 1); L.mmb_profile_scopes_all(k, 1)
+    L.mmb_launch_count_all(1)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -287,12 +287,12 @@ def main():
     bases, times_a = run_steps(a.steps, True)
     barrier()
     t_a = time.perf_counter() - t_a0
-    launches = int(L.mmb_launch_count(ctx, 0))
+    launches = int(L.mmb_launch_count_all(0))
     prof = {}
     for k, nm in enumerate(["sketch", "seed", "sort", "chain", "ksw", "other"]):
-        prof[nm] = {"ms": L.mmb_profile_ms(ctx, k, 0), "units": int(L.mmb_profile_units(ctx, k, 0)), "bytes": int(L.mmb_profile_bytes(ctx, k, 0)),
-                    "scopes": int(L.mmb_profile_scopes(ctx, k, 0))}
-    L.mmb_profile_enable(ctx, 0)
+        prof[nm] = {"ms": L.mmb_profile_ms_all(k, 0), "units": int(L.mmb_profile_units_all(k, 0)), "bytes": int(L.mmb_profile_bytes_all(k, 0)),
+                    "scopes": int(L.mmb_profile_scopes_all(k, 0))}
+    L.mmb_profile_enable_all(0)
     # --- timed region B: `e2e` (host buffers in, results out) ---
     barrier()
     t_b0 = time.perf_counter()

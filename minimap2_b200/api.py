@@ -107,6 +107,14 @@ def _setup():
     L.mmb_profile_scopes.restype = C.c_uint64
     L.mmb_profile_scopes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.mmb_set_resident_reads.argtypes = [C.c_int]
+    L.mmb_profile_enable_all.argtypes = [C.c_int]
+    L.mmb_profile_ms_all.restype = C.c_double
+    L.mmb_profile_ms_all.argtypes = [C.c_int, C.c_int]
+    for nm in ("mmb_profile_units_all", "mmb_profile_bytes_all", "mmb_profile_scopes_all"):
+        getattr(L, nm).restype = C.c_uint64
+        getattr(L, nm).argtypes = [C.c_int, C.c_int]
+    L.mmb_launch_count_all.restype = C.c_uint64
+    L.mmb_launch_count_all.argtypes = [C.c_int]
     L.mmb_last_d2h_bytes.restype = C.c_uint64
     _setup_done = True
     return L

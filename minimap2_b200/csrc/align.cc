@@ -80,22 +80,22 @@ struct Driver {
 
 	// cache lookup; on a miss the job is queued for the GPU and false is returned
 	bool fetch(const KswKey &k, Ez *ez) {
-		auto it = ra.cache.find(k);
-		if (it != ra.cache.end() && it->second >= 0) {
-			const KswDone &d = ra.done[it->second];
+		int slot = ra.find(k);
+		if (slot >= 0 && ra.done_idx[slot] >= 0) {
+			const KswDone &d = ra.done[ra.done_idx[slot]];
 			ez->max = d.r.max, ez->zdropped = d.r.zdropped, ez->max_q = d.r.max_q, ez->max_t = d.r.max_t;
 			ez->mqe = d.r.mqe, ez->mqe_t = d.r.mqe_t, ez->mte = d.r.mte, ez->mte_q = d.r.mte_q;
 			ez->score = d.r.score, ez->n_cigar = d.r.n_cigar, ez->reach_end = d.r.reach_end;
-			ez->cigar = ra.cigar_pool.data() + d.pool_off;
+			ez->cigar = d.cig;
 			return true;
 		}
-		if (it == ra.cache.end()) {
-			ra.cache.emplace(k, -1);
+		if (slot < 0) {
+			ra.keys.push_back(k); ra.done_idx.push_back(-1);
 			mmb_ksw_job_t j;
 			j.q_start = k.q_start, j.t_start = k.t_start, j.q_step = k.q_step, j.t_step = k.t_step;
 			j.qlen = k.qlen, j.tlen = k.tlen, j.w = k.w, j.zdrop = k.zdrop, j.end_bonus = k.end_bonus, j.flag = k.flag;
 			ra.want.push_back(j);
-			ra.want_key.push_back(k);
+			ra.want_slot.push_back((int)ra.keys.size() - 1);
 		}
 		ra.incomplete = true;
 		pending = true;
@@ -120,7 +120,7 @@ struct Driver {
 		return true;
 	}
 
-	const uint8_t *qptr(int rev, int qs) const { return ra.qseq[rev].data() + qs; }
+	const uint8_t *qptr(int rev, int qs) const { return ra.qseq[rev] + qs; }
 	void get_tseq(uint32_t rid, int st, int en, std::vector<uint8_t> &buf) const {
 		buf.resize(en > st? en - st : 0);
 		if (en > st) mm_idx_getseq(mi, rid, st, en, buf.data());
@@ -352,7 +352,7 @@ struct Driver {
 	}
 	void adjust_minier(const m128 *a, int32_t *r, int32_t *q) const { // align.c:418-433
 		if (mi->flag & MM_I_HPC) {
-			const uint8_t *qs = ra.qseq[a->x >> 63].data();
+			const uint8_t *qs = ra.qseq[a->x >> 63];
 			int i, c;
 			*q = (int32_t)a->y;
 			for (i = *q - 1, c = qs[*q]; i > 0; --i) if (qs[i] != c) break;

@@ -47,21 +47,23 @@ struct KswKeyHash {
 	}
 };
 
-struct KswDone {            // a finished job: ksw_extz_t fields + where its CIGAR lives in ReadAlign::cigar_pool
+struct KswDone {            // a finished job: ksw_extz_t fields + its CIGAR (points into the wave's pinned result buffer)
 	mmb_ksw_res_t r;
-	uint32_t pool_off;
+	const uint32_t *cig;
 };
 
-struct ReadAlign {          // per-read alignment working set (lives across waves)
+struct ReadAlign {          // per-read alignment working set (lives across waves; pooled across batches, so the vectors keep their capacity)
 	int qlen = 0;
 	int64_t q_dev_off = 0;  // offset of this read's first base in the device query array
-	std::vector<uint8_t> qseq[2]; // nt4 forward / reverse complement (align.c:1056-1061)
-	std::unordered_map<KswKey, int, KswKeyHash> cache; // key -> index into done (-1: requested, not delivered yet)
+	const uint8_t *qseq[2] = {nullptr, nullptr}; // nt4 forward / reverse complement (align.c:1056-1061), slices of a pooled buffer
+	std::vector<KswKey> keys;      // job cache: keys[i] -> done_idx[i] (-1: requested, not delivered yet); ~50-100 entries, linear probe
+	std::vector<int> done_idx;
 	std::vector<KswDone> done;
-	std::vector<uint32_t> cigar_pool;
 	std::vector<mmb_ksw_job_t> want; // jobs requested by the current replay
-	std::vector<KswKey> want_key;
+	std::vector<int> want_slot;      // their slots in keys[]
 	bool incomplete = false;
+	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); incomplete = false; }
+	int find(const KswKey &k) const { for (size_t i = 0; i < keys.size(); ++i) if (keys[i] == k) return (int)i; return -1; }
 };
 
 // Runs the whole per-read alignment (mm_align_skeleton semantics) using cached ksw results; missing results are appended

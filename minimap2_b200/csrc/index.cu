@@ -354,7 +354,15 @@ extern "C" int mm_idx_getseq(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint
 	if (rid >= mi->n_seq || st >= mi->seq[rid].len) return -1;
 	if (en > mi->seq[rid].len) en = mi->seq[rid].len;
 	const uint64_t st1 = mi->seq[rid].offset + st, en1 = mi->seq[rid].offset + en;
-	for (uint64_t i = st1; i < en1; ++i) seq[i - st1] = (uint8_t)mmx_seq4_get(mi->S, i);
+	uint64_t i = st1;
+	for (; i < en1 && (i & 7); ++i) seq[i - st1] = (uint8_t)mmx_seq4_get(mi->S, i);
+	for (; i + 8 <= en1; i += 8) { // one 32-bit word = 8 bases
+		uint32_t w = mi->S[i >> 3];
+		uint8_t *o = seq + (i - st1);
+		o[0] = w & 0xf, o[1] = w >> 4 & 0xf, o[2] = w >> 8 & 0xf, o[3] = w >> 12 & 0xf;
+		o[4] = w >> 16 & 0xf, o[5] = w >> 20 & 0xf, o[6] = w >> 24 & 0xf, o[7] = w >> 28 & 0xf;
+	}
+	for (; i < en1; ++i) seq[i - st1] = (uint8_t)mmx_seq4_get(mi->S, i);
 	return (int)(en - st);
 }
 

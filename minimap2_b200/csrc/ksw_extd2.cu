@@ -21,6 +21,7 @@
 #include "mmb_internal.h"
 #include <algorithm>
 #include <numeric>
+#include <mutex>
 
 #define KSW_NEG_INF (-0x40000000)
 
@@ -649,14 +650,16 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		const int G = tiers[k].G, nw = tiers[k].nw, threads = G * nw;
 		size_t smem = ((size_t)15 * A.L + A.LQ + 64 + 1024) * nw;
 		int cta_per_sm = 1;
-		if (G == 32) {
-			MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smem, ctx->smem_optin)));
-			MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<32>, threads, smem));
-		} else {
-			MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min(smem, ctx->smem_optin)));
-			MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<256>, threads, smem));
+		{ // opt in to the full shared-memory carve-out once (never lowered: several scheduler groups launch concurrently)
+			static std::once_flag once;
+			std::call_once(once, [&]() {
+				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
+				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
+			});
 		}
-		if (smem > ctx->smem_optin || cta_per_sm < 1) {
+		if (G == 32) MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<32>, threads, smem));
+		else MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<256>, threads, smem));
+		if (smem > ctx->smem_optin - 1024 || cta_per_sm < 1) {
 			fprintf(stderr, "[ERROR] ksw tier %d needs %zu B shared memory per CTA\n", k, smem);
 			abort();
 		}

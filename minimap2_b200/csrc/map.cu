@@ -17,6 +17,7 @@
 #include <functional>
 #include <cstring>
 #include <algorithm>
+#include <mutex>
 
 extern "C" double realtime(void);
 extern "C" double cputime(void);
@@ -100,14 +101,6 @@ inline uint32_t wang_hash(uint32_t key) // khash.h:400-409
 	return key;
 }
 
-struct BatchBufs { // device arenas reused across batches (per context)
-	DevBuf seq, off, mz, mz_off, n_mz, qlen, s_n, s_off, k_idx, k_aoff, flt, mini_pos, n_keep, rep_len, n_a, a_off, a, stk;
-	DevBuf n_u, n_v, u, a_out, ch1, ch2, t1, t2, doff, dense_u, dense_a, dense_mp;
-	DevBuf jobs, res, cig;
-	PinBuf h_seq, h_misc;
-};
-BatchBufs *g_bufs = nullptr;
-
 struct ReadState {
 	int qlen = 0;
 	const char *seq = nullptr, *name = nullptr;
@@ -117,12 +110,27 @@ struct ReadState {
 	const m128 *a_src = nullptr;
 	int n_regs0 = 0;
 	mm_reg1_t *regs0 = nullptr;            // after chain_post/est_err (pristine, no ->p)
-	std::vector<m128> a;                   // working copy of the anchors for the alignment replay
-	ReadAlign *ra = nullptr;
+	std::vector<m128> a;                   // working copy of the anchors for the alignment replay (capacity kept across batches)
+	ReadAlign *ra = nullptr;               // points into the pooled ReadAlign array
 	int n_regs = 0;
 	mm_reg1_t *regs = nullptr;             // final
 	bool done = false;
 };
+
+struct BatchBufs { // device arenas reused across batches (per context)
+	DevBuf a2, seq, off, mz, mz_off, n_mz, qlen, s_n, s_off, k_idx, k_aoff, flt, mini_pos, n_keep, rep_len, n_a, a_off, a, stk;
+	DevBuf n_u, n_v, u, a_out, ch1, ch2, t1, t2, doff, dense_u, dense_a, dense_mp;
+	DevBuf jobs, res, cig;
+	PinBuf h_seq, h_misc, h_jobs, h_res, h_cig[16];
+	std::vector<ReadState> rs_pool;        // persistent per-read objects: their vectors keep capacity => no allocation in steady state
+	std::vector<ReadAlign> ra_pool;
+	std::vector<uint8_t> qseq_pool;        // nt4 forward + reverse-complement copies of the batch (2 x total bases)
+};
+struct GroupCtx { mmb_ctx_t *ctx = nullptr; BatchBufs bb; int64_t res_n = -1, res_bases = -1; const char *res_first = nullptr; };
+const int MAX_GROUPS = 8;
+GroupCtx *g_groups[MAX_GROUPS] = {nullptr};
+std::mutex g_group_mu;
+
 
 void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 {
@@ -142,22 +150,25 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 
 } // namespace
 
-extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
-							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
+static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
+					 int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
 {
 	if (n_reads <= 0) return 0;
-	unsupported_check(mi, opt);
+	static const bool timing = getenv("MM_B200_TIMING") != nullptr;
+	double t_last = realtime();
+	auto lap = [&](const char *what) { if (timing) { cudaStreamSynchronize(G.ctx->stream); double t = realtime(); fprintf(stderr, "[timing g%d] %-28s %.1f ms\n", G.ctx->group_id, what, 1e3 * (t - t_last)); t_last = t; } };
 	mm_idx_bucket_s *B = mi->B;
-	mmb_ctx_t *ctx = B->ctx;
+	mmb_ctx_t *ctx = G.ctx;
 	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
-	if (!g_bufs) g_bufs = new BatchBufs();
-	BatchBufs &bb = *g_bufs;
+	BatchBufs &bb = G.bb;
 	if (n_threads < 1) n_threads = 1;
-	std::vector<ReadState> rs(n_reads);
+	if ((int)bb.rs_pool.size() < n_reads) bb.rs_pool.resize(n_reads), bb.ra_pool.resize(n_reads);
+	std::vector<ReadState> &rs = bb.rs_pool;
 	std::vector<int64_t> off(n_reads + 1, 0);
 	std::vector<int> live; // reads that go through the pipeline (non-empty, within max_qlen)
 	for (int i = 0; i < n_reads; ++i) {
 		rs[i].qlen = qlens[i], rs[i].seq = seqs[i], rs[i].name = names? names[i] : nullptr;
+		rs[i].ra = nullptr, rs[i].regs0 = nullptr, rs[i].regs = nullptr, rs[i].n_regs = rs[i].n_regs0 = 0, rs[i].done = false;
 		n_regs_out[i] = 0, regs_out[i] = nullptr;
 		if (rep_len_out) rep_len_out[i] = 0;
 		bool ok = qlens[i] > 0 && !(opt->max_qlen > 0 && qlens[i] > opt->max_qlen); // map.c:243-244
@@ -168,16 +179,17 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	for (int j = 0; j < n; ++j) off[j + 1] = off[j] + rs[live[j]].qlen;
 	const int64_t total_bases = off[n];
 
+	lap("setup");
 	// ---------------- stage 1: device ----------------
 	uint8_t *h_seq = bb.h_seq.as<uint8_t>((size_t)total_bases + 16);
 	parallel_for(n, n_threads, [&](int64_t j, int) { memcpy(h_seq + off[j], rs[live[j]].seq, rs[live[j]].qlen); });
+	lap("host concat");
 	uint8_t *d_seq = bb.seq.as<uint8_t>((size_t)total_bases + 16);
 	int64_t *d_off = bb.off.as<int64_t>((size_t)n + 1);
 	int32_t *d_qlen = bb.qlen.as<int32_t>((size_t)n);
 	std::vector<int32_t> h_qlen(n);
 	for (int j = 0; j < n; ++j) h_qlen[j] = rs[live[j]].qlen;
-	static int64_t res_n = -1, res_bases = -1; static const char *res_first = nullptr;
-	const bool resident_hit = mmb_resident_reads() && res_n == n && res_bases == total_bases && res_first == rs[live[0]].seq;
+	const bool resident_hit = mmb_resident_reads() && G.res_n == n && G.res_bases == total_bases && G.res_first == rs[live[0]].seq;
 	ctx->last_d2h_bytes = 0, ctx->last_h2d_bytes = 0;
 	if (!resident_hit) {
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_seq, h_seq, total_bases, cudaMemcpyHostToDevice, ctx->stream));
@@ -189,7 +201,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 		encode_kernel<<<(unsigned)((total_bases / 4 + 256) / 256), 256, 0, ctx->stream>>>(d_seq, total_bases);
 		++ctx->n_launch;
 	}
-	res_n = n, res_bases = total_bases, res_first = rs[live[0]].seq;
+	G.res_n = n, G.res_bases = total_bases, G.res_first = rs[live[0]].seq;
 	int64_t *d_mz_off = bb.mz_off.as<int64_t>((size_t)n + 1);
 	const int64_t total_mz = mmb_sketch_device(ctx, d_seq, nullptr, d_off, n, nullptr, 0, mi->w, mi->k, mi->flag & MM_I_HPC, total_bases,
 											   bb.mz, d_mz_off, bb.t1, bb.t2, 1 /* rid = segment index 0 for every read (map.c:65) */);
@@ -210,7 +222,9 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	++ctx->n_launch;
 	const int64_t total_a = mmb_exclusive_scan_i64(ctx, d_a_off, n, true);
 	S.a = bb.a.as<m128>((size_t)total_a + 4), S.a_off = d_a_off;
+	S.a_sorted = bb.a2.as<m128>((size_t)total_a + 4);
 	mmb_seed_expand_sort_device(ctx, S, total_mz, total_a, bb.stk);
+	lap("h2d+sketch+seed+sort");
 	// chaining parameters (map.c:262-281)
 	mmb_chain_par_t cp;
 	memset(&cp, 0, sizeof(cp));
@@ -227,7 +241,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	int32_t *d_n_u = bb.n_u.as<int32_t>((size_t)n), *d_n_v = bb.n_v.as<int32_t>((size_t)n);
 	uint64_t *d_u = bb.u.as<uint64_t>((size_t)total_a + 4);
 	m128 *d_a_out = bb.a_out.as<m128>((size_t)total_a + 4);
-	mmb_chain_device(ctx, &cp, n, S.a, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2);
+	mmb_chain_device(ctx, &cp, n, S.a_sorted, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2);
 	// dense copies for the host: offsets for u, a and mini_pos
 	int64_t *d_doff = bb.doff.as<int64_t>((size_t)(n + 1) * 3);
 	int64_t *d_uo = d_doff, *d_vo = d_doff + (n + 1), *d_mo = d_doff + 2 * (n + 1);
@@ -279,8 +293,10 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 		ctx->prof_bytes[MMB_PROF_CHAIN] += 16ull * (uint64_t)total_a + 16ull * (uint64_t)tot_v + 8ull * (uint64_t)tot_u;
 	}
 
+	lap("chain+rescue+d2h");
 	// ---------------- stage 2: chains -> hits (map.c:317-336) ----------------
 	const bool with_cigar = (opt->flag & MM_F_CIGAR) != 0;
+	if (with_cigar && bb.qseq_pool.size() < (size_t)total_bases * 2 + 16) bb.qseq_pool.resize((size_t)total_bases * 2 + 16);
 	parallel_for(n, n_threads, [&](int64_t j, int) {
 		ReadState &r = rs[live[j]];
 		r.rep_len = h_rep[j];
@@ -301,17 +317,30 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 		n_regs0 = hl_filter_strand_retained(n_regs0, regs0);
 		r.n_regs0 = n_regs0, r.regs0 = regs0;
 		if (with_cigar && n_regs0 > 0) {
-			ReadAlign *ra = new ReadAlign();
+			ReadAlign *ra = &bb.ra_pool[live[j]];
+			ra->reset();
 			ra->qlen = r.qlen, ra->q_dev_off = off[j];
-			ra->qseq[0].resize(r.qlen), ra->qseq[1].resize(r.qlen);
-			for (int i = 0; i < r.qlen; ++i) { // align.c:1056-1061
-				uint8_t c = mmx_nt4((uint8_t)r.seq[i]);
-				ra->qseq[0][i] = c, ra->qseq[1][r.qlen - 1 - i] = c < 4? 3 - c : 4;
-			}
 			r.ra = ra;
 		} else r.done = true, r.n_regs = n_regs0, r.regs = regs0, r.regs0 = nullptr;
 	});
 
+	lap("stage2 host hits");
+	if (with_cigar) { // nt4 forward / reverse-complement copies of the reads that will be aligned (align.c:1056-1061)
+		static uint8_t lut[256]; static bool lut_ok = false;
+		if (!lut_ok) { for (int i = 0; i < 256; ++i) lut[i] = mmx_nt4((uint8_t)i); lut_ok = true; }
+		parallel_for(n, n_threads, [&](int64_t j, int) {
+			ReadState &r = rs[live[j]];
+			if (!r.ra) return;
+			uint8_t *q0 = bb.qseq_pool.data() + 2 * off[j], *q1 = q0 + r.qlen;
+			const uint8_t *sq = (const uint8_t*)r.seq;
+			for (int i = 0; i < r.qlen; ++i) {
+				const uint8_t c = lut[sq[i]];
+				q0[i] = c, q1[r.qlen - 1 - i] = c < 4? 3 - c : 4;
+			}
+			r.ra->qseq[0] = q0, r.ra->qseq[1] = q1;
+		});
+	}
+	lap("stage2 qseq encode");
 	// ---------------- stage 3: alignment waves ----------------
 	if (with_cigar) {
 		mmb_ksw_score_t sc;
@@ -335,7 +364,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 			parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
 				ReadState &r = rs[active[t]];
 				ReadAlign &ra = *r.ra;
-				ra.want.clear(); ra.want_key.clear();
+				ra.want.clear(); ra.want_slot.clear();
 				r.a.assign(r.a_src, r.a_src + r.n_a); // pristine anchors (IGNORE/LONG_JOIN marks cleared)
 				int n_regs = r.n_regs0;
 				mm_reg1_t *regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
@@ -353,6 +382,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 					r.n_regs = n_regs, r.regs = regs, r.done = true;
 				}
 			});
+			lap("  wave replay");
 			// gather jobs
 			std::vector<int> still;
 			std::vector<int64_t> joff(active.size() + 1, 0);
@@ -362,16 +392,21 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 			}
 			const int64_t n_jobs = joff[active.size()];
 			if (n_jobs > 0) {
-				std::vector<mmb_ksw_job_t> jobs((size_t)n_jobs);
+				if (wave >= 16) { fprintf(stderr, "[ERROR] minimap2_b200: too many alignment waves\n"); abort(); }
+				mmb_ksw_job_t *jobs = bb.h_jobs.as<mmb_ksw_job_t>((size_t)n_jobs);
 				parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
 					ReadState &r = rs[active[t]];
 					if (!r.done && !r.ra->want.empty()) memcpy(&jobs[joff[t]], r.ra->want.data(), sizeof(mmb_ksw_job_t) * r.ra->want.size());
 				});
-				// run in chunks to bound the result buffers
+				// run in chunks to bound the device result buffers; results land in pinned host memory that stays alive until
+				// the end of the batch, so per-read caches just point into it
 				const int64_t CH = 1 << 20;
-				std::vector<mmb_ksw_res_t> res((size_t)n_jobs);
-				std::vector<std::vector<uint32_t>> cig_chunks;
-				std::vector<int64_t> chunk_of_job_base;
+				mmb_ksw_res_t *res = bb.h_res.as<mmb_ksw_res_t>((size_t)n_jobs);
+				int64_t cap_tot = 0;
+				for (int64_t i = 0; i < n_jobs; ++i) if (!(jobs[i].flag & MMB_JOB_LL)) cap_tot += (jobs[i].qlen + jobs[i].tlen) / 2 + 8;
+				uint32_t *h_cig = bb.h_cig[wave].as<uint32_t>((size_t)cap_tot + 64);
+				std::vector<int64_t> chunk_base; // offset of each chunk's CIGAR block inside h_cig
+				int64_t cig_fill = 0;
 				for (int64_t b = 0; b < n_jobs; b += CH) {
 					const int64_t m = std::min(CH, n_jobs - b);
 					int64_t cap = 0;
@@ -389,49 +424,106 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 						MMB_CUDA_CHECK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, ctx->stream));
 						MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 						if ((int64_t)used > cap) { cap = (int64_t)used + 16; continue; } // rare: rerun the chunk with a larger CIGAR arena
+						if (cig_fill + (int64_t)used > cap_tot) { fprintf(stderr, "[ERROR] minimap2_b200: CIGAR staging overflow\n"); abort(); }
 						ctx->last_d2h_bytes += sizeof(mmb_ksw_res_t) * (uint64_t)m + 4ull * used;
 						ctx->last_h2d_bytes += sizeof(mmb_ksw_job_t) * (uint64_t)m;
 						if (ctx->profiling) ctx->prof_bytes[MMB_PROF_KSW] += 4ull * used;
-						cig_chunks.emplace_back((size_t)used + 1);
-						if (used) MMB_CUDA_CHECK(cudaMemcpyAsync(cig_chunks.back().data(), d_cig + 2, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+						chunk_base.push_back(cig_fill);
+						if (used) MMB_CUDA_CHECK(cudaMemcpyAsync(h_cig + cig_fill, d_cig + 2, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+						cig_fill += (int64_t)used;
 						MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 						break;
 					}
 				}
-				// scatter results into the per-read caches
+				lap("  wave gpu");
+				// hand the results to the per-read caches (pointers only)
 				parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
 					ReadState &r = rs[active[t]];
 					if (r.done) return;
 					ReadAlign &ra = *r.ra;
 					for (size_t i = 0; i < ra.want.size(); ++i) {
 						const int64_t jid = joff[t] + (int64_t)i;
-						const mmb_ksw_res_t &rr = res[jid];
-						KswDone d; d.r = rr, d.pool_off = (uint32_t)ra.cigar_pool.size();
-						const std::vector<uint32_t> &cc = cig_chunks[jid / CH];
-						ra.cigar_pool.insert(ra.cigar_pool.end(), cc.begin() + rr.cigar_off, cc.begin() + rr.cigar_off + rr.n_cigar);
-						ra.cache[ra.want_key[i]] = (int)ra.done.size();
+						KswDone d; d.r = res[jid], d.cig = h_cig + chunk_base[jid / CH] + res[jid].cigar_off;
+						ra.done_idx[ra.want_slot[i]] = (int)ra.done.size();
 						ra.done.push_back(d);
 					}
 				});
 			}
+			lap("  wave scatter");
 			for (size_t t = 0; t < active.size(); ++t) if (!rs[active[t]].done) still.push_back(active[t]);
 			if (!still.empty() && n_jobs == 0) { fprintf(stderr, "[ERROR] minimap2_b200: alignment scheduler made no progress\n"); abort(); }
 			active.swap(still);
-			if (++wave > 64) { fprintf(stderr, "[ERROR] minimap2_b200: too many alignment waves\n"); abort(); }
+			++wave;
 		}
 	}
 
+	lap("waves end");
 	// ---------------- stage 4: finalize (map.c:338-343) ----------------
 	parallel_for(n, n_threads, [&](int64_t j, int) {
 		ReadState &r = rs[live[j]];
 		if (r.regs0) free(r.regs0);
-		delete r.ra;
+		r.regs0 = nullptr, r.ra = nullptr;
 		r.regs = (mm_reg1_t*)realloc(r.regs, sizeof(mm_reg1_t) * (r.n_regs > 0? r.n_regs : 1));
 		hl_set_mapq(r.n_regs, r.regs, opt->min_chain_score, opt->a, r.rep_len, 0, 0);
 		if (r.n_regs == 0) { free(r.regs); r.regs = nullptr; }
 		n_regs_out[live[j]] = r.n_regs, regs_out[live[j]] = r.regs;
 		if (rep_len_out) rep_len_out[live[j]] = r.rep_len;
 	});
+	lap("finalize");
+	return 0;
+}
+
+mmb_ctx_t *mmb_default_ctx(void);
+void mmb_register_ctx(mmb_ctx_t *c);
+
+static GroupCtx &get_group(int g, int device)
+{
+	std::lock_guard<std::mutex> lk(g_group_mu);
+	if (!g_groups[g]) {
+		g_groups[g] = new GroupCtx();
+		g_groups[g]->ctx = mmb_ctx_create(device);
+		if (!g_groups[g]->ctx) abort();
+		g_groups[g]->ctx->group_id = g;
+		g_groups[g]->ctx->profiling = mmb_default_ctx()->profiling;
+		mmb_register_ctx(g_groups[g]->ctx);
+	}
+	return *g_groups[g];
+}
+
+// The batch is split into NG contiguous groups (balanced by bases) that run the whole pipeline concurrently, each on its
+// own CUDA stream with its own arenas: while one group is in a host phase (hit logic, alignment replay) the others keep
+// the GPU busy. This is the scheduler that replaces kt_pipeline/kt_for (map.c:541-691, kthread.c:54-159).
+extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
+							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
+{
+	if (n_reads <= 0) return 0;
+	unsupported_check(mi, opt);
+	static int ng_env = getenv("MM_B200_GROUPS")? atoi(getenv("MM_B200_GROUPS")) : 3;
+	int NG = ng_env < 1? 1 : ng_env > MAX_GROUPS? MAX_GROUPS : ng_env;
+	int64_t total = 0;
+	for (int i = 0; i < n_reads; ++i) total += qlens[i] > 0? qlens[i] : 0;
+	if (n_reads < 64 * NG || total < 4000000) NG = 1;
+	const int device = mi->B->ctx->device;
+	for (int g = 0; g < NG; ++g) get_group(g, device).ctx->profiling = mmb_default_ctx()->profiling;
+	if (NG == 1) return map_group(get_group(0, device), mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads);
+	std::vector<int> cut(NG + 1, 0);
+	{
+		int64_t acc = 0; int g = 1;
+		for (int i = 0; i < n_reads && g < NG; ++i) {
+			acc += qlens[i] > 0? qlens[i] : 0;
+			if (acc >= total * g / NG) cut[g++] = i + 1;
+		}
+		for (; g < NG; ++g) cut[g] = n_reads;
+		cut[NG] = n_reads;
+	}
+	std::vector<std::thread> th;
+	for (int g = 0; g < NG; ++g)
+		th.emplace_back([&, g]() {
+			const int b = cut[g], m = cut[g + 1] - cut[g];
+			if (m > 0) map_group(get_group(g, device), mi, m, qlens + b, seqs + b, names? names + b : nullptr, n_regs_out + b, regs_out + b,
+								 rep_len_out? rep_len_out + b : nullptr, opt, n_threads);
+		});
+	for (auto &x : th) x.join();
 	return 0;
 }
 

@@ -15,6 +15,11 @@ extern "C" int mmb_device_count(void)
 	return n;
 }
 
+#include <mutex>
+static std::vector<mmb_ctx_t*> g_all_ctx;
+static std::mutex g_all_mu;
+void mmb_register_ctx(mmb_ctx_t *c) { std::lock_guard<std::mutex> lk(g_all_mu); g_all_ctx.push_back(c); }
+
 extern "C" mmb_ctx_t *mmb_ctx_create(int device)
 {
 	int n = mmb_device_count();
@@ -132,4 +137,55 @@ extern "C" uint64_t mmb_profile_bytes(mmb_ctx_t *c, int which, int reset)
 static int g_resident_reads = 0;
 extern "C" void mmb_set_resident_reads(int on) { g_resident_reads = on; }
 int mmb_resident_reads(void) { return g_resident_reads; }
-extern "C" uint64_t mmb_last_d2h_bytes(void) { return mmb_default_ctx()->last_d2h_bytes; }
+extern "C" uint64_t mmb_last_d2h_bytes_all(void);
+extern "C" uint64_t mmb_last_d2h_bytes(void) { return mmb_last_d2h_bytes_all(); }
+
+// aggregated over every context of this process (default context + the scheduler's group contexts); which as in mmb_profile_ms
+extern "C" void mmb_profile_enable_all(int on)
+{
+	mmb_default_ctx()->profiling = on;
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) c->profiling = on;
+}
+extern "C" double mmb_profile_ms_all(int which, int reset)
+{
+	double v = mmb_profile_ms(mmb_default_ctx(), which, reset);
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) v += mmb_profile_ms(c, which, reset);
+	return v;
+}
+extern "C" uint64_t mmb_profile_units_all(int which, int reset)
+{
+	uint64_t v = mmb_profile_units(mmb_default_ctx(), which, reset);
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) v += mmb_profile_units(c, which, reset);
+	return v;
+}
+extern "C" uint64_t mmb_profile_bytes_all(int which, int reset)
+{
+	uint64_t v = mmb_profile_bytes(mmb_default_ctx(), which, reset);
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) v += mmb_profile_bytes(c, which, reset);
+	return v;
+}
+extern "C" uint64_t mmb_profile_scopes_all(int which, int reset)
+{
+	uint64_t v = mmb_profile_scopes(mmb_default_ctx(), which, reset);
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) v += mmb_profile_scopes(c, which, reset);
+	return v;
+}
+extern "C" uint64_t mmb_launch_count_all(int reset)
+{
+	uint64_t v = mmb_launch_count(mmb_default_ctx(), reset);
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) v += mmb_launch_count(c, reset);
+	return v;
+}
+extern "C" uint64_t mmb_last_d2h_bytes_all(void)
+{
+	uint64_t v = mmb_default_ctx()->last_d2h_bytes;
+	std::lock_guard<std::mutex> lk(g_all_mu);
+	for (auto *c : g_all_ctx) v += c->last_d2h_bytes;
+	return v;
+}

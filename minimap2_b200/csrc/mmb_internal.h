@@ -54,6 +54,7 @@ struct PinBuf { // pinned host staging buffer
 
 struct mmb_ctx_s {
 	int device = 0;
+	int group_id = 0;
 	int n_sm = 0;
 	size_t smem_optin = 0;
 	cudaStream_t stream = nullptr;

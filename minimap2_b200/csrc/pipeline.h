@@ -20,6 +20,7 @@ struct SeedArgs {
 	int32_t *n_keep, *rep_len; int64_t *n_a;
 	// anchors
 	m128 *a; const int64_t *a_off;
+	m128 *a_sorted;           // output of the anchor sort (a stays in expansion order for the exact-sort fallback)
 };
 
 void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz);

@@ -15,6 +15,7 @@
 #include "mm_algo.cuh"
 #include "scan.cuh"
 #include "pipeline.h"
+#include <mutex>
 
 namespace {
 
@@ -208,12 +209,84 @@ __global__ void __launch_bounds__(256) expand_kernel(SeedArgs A, int64_t total) 
 	}
 }
 
-__global__ void __launch_bounds__(128) sort_kernel(m128 *a, const int64_t *a_off, int n_reads, int32_t *stk, const int64_t *stk_off)
+// ---------------------------------------------------------------------------------------------------------
+// Anchor sort (radix_sort_128x of map.c:202). The reference's sort is unstable, but its output is fully determined
+// when all keys are distinct, and for n <= 64 it is a stable insertion sort (ksort.h:147-151). So:
+//   * sort_block_kernel: one CTA per read, bitonic sort of (x, original index) in shared memory -- the stable order;
+//     equal neighbouring keys are detected on the fly;
+//   * reads with n > 64 that do contain equal keys (two query minimizers on the same reference position: repeats), or
+//     that do not fit the largest shared-memory class, are re-sorted by sort_exact_kernel, the step-by-step emulation of
+//     the reference's in-place MSD radix sort (one thread per read).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void sort_classify_kernel(const int64_t *a_off, int n_reads, int *cls_cnt, int *cls_list, int n_cls, int cap0)
 {
 	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
 	if (rd >= n_reads) return;
+	const int64_t n = a_off[rd + 1] - a_off[rd];
+	if (n <= 0) return;
+	int c = 0, cap = cap0;
+	while (c < n_cls - 1 && n > cap) ++c, cap <<= 1;
+	if (n > cap) c = n_cls; // too large for shared memory: exact kernel
+	const int pos = atomicAdd(&cls_cnt[c], 1);
+	cls_list[(size_t)c * n_reads + pos] = rd;
+}
+
+__global__ void sort_block_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr, int cap,
+								  int *exact_cnt, int *exact_list)
+{
+	extern __shared__ __align__(16) uint8_t sm_raw[];
+	uint64_t *key = (uint64_t*)sm_raw;
+	uint16_t *idx = (uint16_t*)(key + cap);
+	__shared__ int s_tie;
+	const int n_list = *cnt_ptr;
+	for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+		const int rd = list[li];
+		const int64_t off = a_off[rd];
+		const int n = (int)(a_off[rd + 1] - off);
+		int P = 1;
+		while (P < n) P <<= 1;
+		if (threadIdx.x == 0) s_tie = 0;
+		for (int i = threadIdx.x; i < P; i += blockDim.x) {
+			key[i] = i < n? a_in[off + i].x : ~0ULL;
+			idx[i] = (uint16_t)i;
+		}
+		__syncthreads();
+		for (int k = 2; k <= P; k <<= 1) {
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+					const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); // index with bit j cleared
+					const int l = i | j;
+					const uint64_t ki = key[i], kl = key[l];
+					const uint16_t ii = idx[i], il = idx[l];
+					const bool gt = ki > kl || (ki == kl && ii > il);
+					const bool up = (i & k) == 0;
+					if (gt == up) { key[i] = kl, key[l] = ki; idx[i] = il, idx[l] = ii; }
+				}
+				__syncthreads();
+			}
+		}
+		int tie = 0;
+		for (int i = threadIdx.x; i < n; i += blockDim.x) {
+			a_out[off + i] = a_in[off + idx[i]];
+			if (i + 1 < n && key[i] == key[i + 1]) tie = 1;
+		}
+		if (tie) s_tie = 1;
+		__syncthreads();
+		if (threadIdx.x == 0 && s_tie && n > 64) exact_list[atomicAdd(exact_cnt, 1)] = rd;
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(64) sort_exact_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
+														const int *list2, const int *cnt2_ptr, int32_t *stk, const int64_t *stk_off)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int n1 = *cnt_ptr, n2 = *cnt2_ptr;
+	if (t >= n1 + n2) return;
+	const int rd = t < n1? list[t] : list2[t - n1];
 	const int64_t off = a_off[rd], n = a_off[rd + 1] - off;
-	if (n > 1) mmx_rs_sort(a + off, n, stk + stk_off[rd], KeyX128());
+	for (int64_t i = 0; i < n; ++i) a_out[off + i] = a_in[off + i];
+	if (n > 1) mmx_rs_sort(a_out + off, n, stk + stk_off[rd], KeyX128());
 }
 
 __global__ void stk_len_kernel2(const int64_t *a_off, int n_reads, int64_t *stk_off)
@@ -256,13 +329,36 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 		if (total_mz > 0) expand_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
 		++ctx->n_launch;
 	}
-	int64_t *d_stk_off = (int64_t*)stkbuf.reserve(((size_t)A.n_reads + 1) * 8 + ((size_t)total_a / 65 * 24 + (size_t)A.n_reads * 48 + 64) * 4);
+	// stack offsets for the exact fallback (sized for every read: the fallback set is not known in advance)
+	int64_t *d_stk_off = (int64_t*)stkbuf.reserve(((size_t)A.n_reads + 1) * 8 + ((size_t)total_a / 65 * 24 + (size_t)A.n_reads * 48 + 64) * 4
+												  + ((size_t)A.n_reads * 8 + 64) * sizeof(int));
 	stk_len_kernel2<<<(A.n_reads + 255) / 256, 256, 0, ctx->stream>>>(A.a_off, A.n_reads, d_stk_off);
 	++ctx->n_launch;
 	mmb_exclusive_scan_i64_async(ctx, d_stk_off, A.n_reads);
+	int32_t *d_stk = (int32_t*)(d_stk_off + A.n_reads + 1);
+	const int N_CLS = 5, CAP0 = 1024; // shared-memory classes: 1024, 2048, 4096, 8192, 16384 anchors
+	int *d_cls_cnt = (int*)(d_stk + ((size_t)total_a / 65 * 24 + (size_t)A.n_reads * 48 + 64));
+	int *d_cls_list = d_cls_cnt + 16; // (N_CLS+2) lists of n_reads entries: classes, oversize (index N_CLS), ties (N_CLS+1)
 	{
 		ProfScope prof(ctx, MMB_PROF_SORT, (uint64_t)total_a);
-		sort_kernel<<<(A.n_reads + 127) / 128, 128, 0, ctx->stream>>>(A.a, A.a_off, A.n_reads, (int32_t*)(d_stk_off + A.n_reads + 1), d_stk_off);
+		MMB_CUDA_CHECK(cudaMemsetAsync(d_cls_cnt, 0, 16 * sizeof(int), ctx->stream));
+		sort_classify_kernel<<<(A.n_reads + 255) / 256, 256, 0, ctx->stream>>>(A.a_off, A.n_reads, d_cls_cnt, d_cls_list, N_CLS, CAP0);
+		++ctx->n_launch;
+		int cap = CAP0;
+		for (int c = 0; c < N_CLS; ++c, cap <<= 1) {
+			const size_t smem = (size_t)cap * 10;
+			const int threads = cap >= 8192? 1024 : cap >= 2048? 512 : 256;
+			{ static std::once_flag once; std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024)); }); }
+			int per_sm = 1;
+			MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_block_kernel, threads, smem));
+			const int grid = ctx->n_sm * (per_sm > 0? per_sm : 1);
+			sort_block_kernel<<<grid, threads, smem, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)c * A.n_reads, d_cls_cnt + c, cap,
+																	 d_cls_cnt + N_CLS + 1, d_cls_list + (size_t)(N_CLS + 1) * A.n_reads);
+			++ctx->n_launch;
+		}
+		// exact emulation for oversize reads and reads with equal keys (upper bound on the launch: all reads; threads beyond the lists exit)
+		sort_exact_kernel<<<(A.n_reads + 63) / 64, 64, 0, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)N_CLS * A.n_reads, d_cls_cnt + N_CLS,
+																		 d_cls_list + (size_t)(N_CLS + 1) * A.n_reads, d_cls_cnt + N_CLS + 1, d_stk, d_stk_off);
 		++ctx->n_launch;
 	}
 	MMB_CUDA_CHECK(cudaGetLastError());

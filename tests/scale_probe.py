@@ -24,7 +24,7 @@ qlens = np.full(n_reads, rl, dtype=np.int32)
 ctx = L.mmb_default_ctx_c()
 names = ["r%d" % i for i in range(n_reads)]
 for it in range(3):
-    L.mmb_profile_enable(ctx, 1 if it == 2 else 0)
+    L.mmb_profile_enable_all(1 if it == 2 else 0)
     t = time.time()
     n_regs, regs, rep = al.map_batch_raw(buf, qlens, names)
     dt = time.time() - t
@@ -40,5 +40,5 @@ for it in range(3):
     al.free_batch(n_regs, regs)
 names_k = ["sketch", "seed", "sort", "chain", "ksw", "other"]
 for i, nm in enumerate(names_k):
-    print("  %-7s %.2f ms  units %d" % (nm, L.mmb_profile_ms(ctx, i, 0), L.mmb_profile_units(ctx, i, 0)))
-print("launches", L.mmb_launch_count(ctx, 0))
+    print("  %-7s %.2f ms  units %d" % (nm, L.mmb_profile_ms_all(i, 0), L.mmb_profile_units_all(i, 0)))
+print("launches", L.mmb_launch_count_all(0))

@@ -107,6 +107,7 @@ def _setup():
     L.mmb_profile_scopes.restype = C.c_uint64
     L.mmb_profile_scopes.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.mmb_set_resident_reads.argtypes = [C.c_int]
+    L.mmb_set_groups.argtypes = [C.c_int]
     L.mmb_profile_enable_all.argtypes = [C.c_int]
     L.mmb_profile_ms_all.restype = C.c_double
     L.mmb_profile_ms_all.argtypes = [C.c_int, C.c_int]
@@ -219,26 +220,35 @@ class Aligner:
         except Exception:
             pass
 
-    def map_batch_raw(self, buf, qlens, names=None, n_threads=None):
-        """buf: contiguous uint8 array holding the reads back to back (ASCII); qlens: int32 array.
-        Returns (n_regs int32[n], regs pointer array, rep_len int32[n]); call free_batch() on the result."""
-        L = _setup()
+    def prepare_batch(self, buf, qlens, names=None):
+        """Pre-builds the pointer arrays mm_map_batch() takes (so repeated calls over the same buffers cost nothing in Python)."""
         n = len(qlens)
         qlens = np.ascontiguousarray(qlens, dtype=np.int32)
         offs = np.zeros(n, dtype=np.uint64)
-        offs[1:] = np.cumsum(qlens[:-1].astype(np.uint64) + (0 if names is None else 0))
+        if n > 1:
+            offs[1:] = np.cumsum(qlens[:-1].astype(np.uint64))
         seq_ptrs = (offs + np.uint64(buf.ctypes.data)).astype(np.uint64)
+        name_arr = None
+        if names is not None:
+            keep = [s if isinstance(s, bytes) else s.encode() for s in names]
+            name_arr = ((C.c_char_p * n)(*keep), keep)
+        return dict(n=n, qlens=qlens, seq_ptrs=seq_ptrs, names=name_arr, buf=buf)
+
+    def map_prepared(self, b, n_threads=None):
+        L = _setup()
+        n = b["n"]
         n_regs = np.zeros(n, dtype=np.int32)
         rep_len = np.zeros(n, dtype=np.int32)
         regs = np.zeros(n, dtype=np.uint64)
-        name_ptrs = None
-        if names is not None:
-            self._names_keep = [s if isinstance(s, bytes) else s.encode() for s in names]
-            arr = (C.c_char_p * n)(*self._names_keep)
-            name_ptrs = C.cast(arr, C.c_void_p)
-        L.mm_map_batch(self._idx, n, qlens.ctypes.data, seq_ptrs.ctypes.data, name_ptrs, n_regs.ctypes.data, regs.ctypes.data,
+        name_ptrs = C.cast(b["names"][0], C.c_void_p) if b["names"] is not None else None
+        L.mm_map_batch(self._idx, n, b["qlens"].ctypes.data, b["seq_ptrs"].ctypes.data, name_ptrs, n_regs.ctypes.data, regs.ctypes.data,
                        rep_len.ctypes.data, C.byref(self.map_opt), n_threads or self.n_threads)
         return n_regs, regs, rep_len
+
+    def map_batch_raw(self, buf, qlens, names=None, n_threads=None):
+        """buf: contiguous uint8 array holding the reads back to back (ASCII); qlens: int32 array.
+        Returns (n_regs int32[n], regs pointer array, rep_len int32[n]); call free_batch() on the result."""
+        return self.map_prepared(self.prepare_batch(buf, qlens, names), n_threads)
 
     @staticmethod
     def free_batch(n_regs, regs):

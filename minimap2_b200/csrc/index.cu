@@ -289,7 +289,7 @@ extern "C" void mm_idx_destroy(mm_idx_t *mi) // index.c:62-91
 	if (mi->B) {
 		mm_idx_bucket_s *B = mi->B;
 		if (B->ctx) cudaSetDevice(B->ctx->device);
-		cudaFree(B->d_tab); cudaFree(B->d_pos); cudaFree(B->d_S); cudaFree(B->d_seq_off); cudaFree(B->d_seq_len); cudaFree(B->d_cnt_sorted); cudaFree(B->d_ukeys); cudaFree(B->d_ucnt); cudaFree(B->d_uoff);
+		if (!B->external) { cudaFree(B->d_tab); cudaFree(B->d_pos); cudaFree(B->d_S); cudaFree(B->d_seq_off); cudaFree(B->d_seq_len); cudaFree(B->d_cnt_sorted); } cudaFree(B->d_ukeys); cudaFree(B->d_ucnt); cudaFree(B->d_uoff);
 		delete B->h_map;
 		delete B;
 	}
@@ -652,3 +652,64 @@ extern "C" int mm_idx_bed_junc(const mm_idx_t *, int32_t, int32_t st, int32_t en
 extern "C" int32_t mm_idx_spsc_read(mm_idx_t *, const char *, int32_t) { return unsupported("--spsc"); }
 extern "C" int32_t mm_idx_spsc_read2(mm_idx_t *, const char *, int32_t, float) { return unsupported("--spsc"); }
 extern "C" int64_t mm_idx_spsc_get(const mm_idx_t *, int32_t, int64_t st0, int64_t en0, int32_t, uint8_t *sc) { memset(sc, 0, en0 - st0); return 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Multi-GPU: the device index is replicated, not sharded (reads shard). Rank 0 exports the device arrays,
+// torch.distributed (NCCL over NVLink) broadcasts them into buffers on the other ranks, which adopt them here.
+// ---------------------------------------------------------------------------------------------------------
+struct mmb_idx_desc_t {           // plain C view of the device index (include/mm_b200.h)
+	void *ptr[5];                 // tab, pos, S, seq_off, seq_len, cnt_sorted is rebuilt on import
+	uint64_t bytes[5];
+	int64_t n_keys, n_pos;
+	int32_t tab_bits, w, k, b, flag;
+	uint32_t n_seq;
+	uint64_t sum_len;
+};
+
+extern "C" void mmb_idx_export(const mm_idx_t *mi, mmb_idx_desc_t *d)
+{
+	mm_idx_bucket_s *B = mi->B;
+	uint64_t sum_len = 0;
+	for (uint32_t i = 0; i < mi->n_seq; ++i) sum_len += mi->seq[i].len;
+	d->ptr[0] = B->d_tab, d->bytes[0] = sizeof(IdxSlot) << B->tab_bits;
+	d->ptr[1] = B->d_pos, d->bytes[1] = 8ull * (uint64_t)(B->n_pos + 1);
+	d->ptr[2] = B->d_S, d->bytes[2] = ((sum_len + 7) / 8 + 4) * 4;
+	d->ptr[3] = B->d_seq_off, d->bytes[3] = 8ull * (mi->n_seq + 1);
+	d->ptr[4] = B->d_seq_len, d->bytes[4] = 4ull * (mi->n_seq + 1);
+	d->n_keys = B->n_keys, d->n_pos = B->n_pos, d->tab_bits = B->tab_bits;
+	d->w = mi->w, d->k = mi->k, d->b = mi->b, d->flag = mi->flag, d->n_seq = mi->n_seq, d->sum_len = sum_len;
+}
+
+// Build an mm_idx_t around device buffers that already hold a broadcast copy (the buffers stay owned by the caller and
+// must outlive the index). names: n_seq NUL-terminated strings; lens: n_seq lengths. The host 4-bit S is copied back
+// from the device for the host-side alignment driver.
+extern "C" mm_idx_t *mmb_idx_adopt(const mmb_idx_desc_t *d, const char **names, const uint32_t *lens, const uint32_t *cnt_sorted_dev)
+{
+	mmb_ctx_t *ctx = mmb_default_ctx();
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	mm_idx_t *mi = (mm_idx_t*)calloc(1, sizeof(mm_idx_t));
+	mi->w = d->w, mi->k = d->k, mi->b = d->b, mi->flag = d->flag, mi->n_seq = d->n_seq;
+	mi->B = new mm_idx_bucket_s();
+	mm_idx_bucket_s *B = mi->B;
+	B->ctx = ctx, B->external = true;
+	B->d_tab = (IdxSlot*)d->ptr[0], B->tab_bits = d->tab_bits, B->d_pos = (uint64_t*)d->ptr[1], B->d_S = (uint32_t*)d->ptr[2];
+	B->d_seq_off = (uint64_t*)d->ptr[3], B->d_seq_len = (uint32_t*)d->ptr[4];
+	B->n_keys = d->n_keys, B->n_pos = d->n_pos;
+	B->d_cnt_sorted = (uint32_t*)cnt_sorted_dev;
+	mi->seq = (mm_idx_seq_t*)calloc(d->n_seq + 1, sizeof(mm_idx_seq_t));
+	uint64_t off = 0;
+	for (uint32_t i = 0; i < d->n_seq; ++i) {
+		mi->seq[i].name = names && names[i]? strdup(names[i]) : 0;
+		mi->seq[i].len = lens[i], mi->seq[i].offset = off, off += lens[i];
+	}
+	mi->S = (uint32_t*)calloc((d->sum_len + 7) / 8 + 1, 4);
+	MMB_CUDA_CHECK(cudaMemcpy(mi->S, B->d_S, ((d->sum_len + 7) / 8) * 4, cudaMemcpyDeviceToHost));
+	mm_idx_index_name(mi);
+	return mi;
+}
+
+extern "C" const void *mmb_idx_cnt_sorted(const mm_idx_t *mi, uint64_t *bytes)
+{
+	*bytes = 4ull * (uint64_t)(mi->B->n_keys + 1);
+	return mi->B->d_cnt_sorted;
+}

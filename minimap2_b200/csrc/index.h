@@ -32,6 +32,7 @@ struct DevIndexView {     // passed by value to kernels
 
 struct mm_idx_bucket_s {  // the opaque "B" of mm_idx_t
 	mmb_ctx_t *ctx = nullptr;
+	bool external = false;              // device arrays are owned by the caller (adopted after an NCCL broadcast)
 	int64_t n_keys = 0, n_pos = 0;
 	// device
 	IdxSlot *d_tab = nullptr; int tab_bits = 0;

@@ -476,6 +476,9 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 mmb_ctx_t *mmb_default_ctx(void);
 void mmb_register_ctx(mmb_ctx_t *c);
 
+static int g_groups_override = 0;
+extern "C" void mmb_set_groups(int n) { g_groups_override = n; } // 0 = default (MM_B200_GROUPS or 3)
+
 static GroupCtx &get_group(int g, int device)
 {
 	std::lock_guard<std::mutex> lk(g_group_mu);
@@ -499,7 +502,9 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	if (n_reads <= 0) return 0;
 	unsupported_check(mi, opt);
 	static int ng_env = getenv("MM_B200_GROUPS")? atoi(getenv("MM_B200_GROUPS")) : 3;
-	int NG = ng_env < 1? 1 : ng_env > MAX_GROUPS? MAX_GROUPS : ng_env;
+	const bool sequential = g_groups_override < 0; // negative override: same groups, run one after another (clean per-kernel timing)
+	const int ng_req = g_groups_override > 0? g_groups_override : g_groups_override < 0? -g_groups_override : ng_env;
+	int NG = ng_req < 1? 1 : ng_req > MAX_GROUPS? MAX_GROUPS : ng_req;
 	int64_t total = 0;
 	for (int i = 0; i < n_reads; ++i) total += qlens[i] > 0? qlens[i] : 0;
 	if (n_reads < 64 * NG || total < 4000000) NG = 1;
@@ -515,6 +520,14 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 		}
 		for (; g < NG; ++g) cut[g] = n_reads;
 		cut[NG] = n_reads;
+	}
+	if (sequential) {
+		for (int g = 0; g < NG; ++g) {
+			const int b = cut[g], m = cut[g + 1] - cut[g];
+			if (m > 0) map_group(get_group(g, device), mi, m, qlens + b, seqs + b, names? names + b : nullptr, n_regs_out + b, regs_out + b,
+								 rep_len_out? rep_len_out + b : nullptr, opt, n_threads);
+		}
+		return 0;
 	}
 	std::vector<std::thread> th;
 	for (int g = 0; g < NG; ++g)

@@ -98,7 +98,112 @@ __device__ void backtrack_compact(const m128 *a, int32_t n, const int32_t *f, co
 	for (int32_t i = 0; i < n_u; ++i) u[i] = w[i].x;
 }
 
-__global__ void __launch_bounds__(128) chain_dp_kernel(ChainArgs A)
+// DP fill (lchain.c:168-207), one WARP per read. Predecessors j = i-1 .. st are scanned 32 at a time: every lane scores
+// one predecessor (coalesced loads of a/f/p/t), and the reference's sequential semantics over the 32 candidates -- strict
+// '>' running maximum, the t[] marks written by earlier-scanned predecessors, the clamped n_skip counter and its early
+// exit -- are reproduced with warp scans: an exclusive prefix-max, a prefix composition of x -> max(x+a, b) maps for the
+// counter, a reduce-or for the marks that fall inside the chunk, and ballots for the break position.
+__global__ void __launch_bounds__(128) chain_fill_kernel(ChainArgs A)
+{
+	const int lane = threadIdx.x & 31;
+	const int rd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (rd >= A.n_reads) return;
+	const int64_t off = A.a_off[rd];
+	const int32_t n = (int32_t)(A.a_off[rd + 1] - off);
+	if (n <= 0) return;
+	const unsigned full = 0xffffffffu;
+	const m128 *a = A.a + off;
+	int32_t *f = A.f + off, *p = A.p + off, *v = A.v + off, *t = A.t + off;
+	const mmb_chain_par_t &P = A.par;
+	int32_t max_dist_x = P.max_dist_x, max_dist_y = P.max_dist_y;
+	const int32_t bw = P.bw, max_skip = P.max_skip, max_iter = P.max_iter, is_cdna = P.is_cdna, n_seg = P.n_seg;
+	const float pen_gap = P.chn_pen_gap, pen_skip = P.chn_pen_skip;
+	if (max_dist_x < bw) max_dist_x = bw;
+	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
+	for (int32_t i = lane; i < n; i += 32) t[i] = 0;
+	__syncwarp();
+	int32_t st = 0, best_prev = -1;
+	for (int32_t i = 0; i < n; ++i) {
+		const m128 ai = a[i];
+		while (st < i) { // advance st (warp-uniform scalar loop; short)
+			const m128 as = a[st];
+			if (ai.x >> 32 != as.x >> 32 || ai.x > as.x + (uint64_t)(int64_t)max_dist_x) ++st; else break;
+		}
+		if (i - st > max_iter) st = i - max_iter;
+		int32_t max_f = (int32_t)(ai.y >> 32 & 0xff), max_j = -1, n_skip = 0, end_j = st - 1;
+		bool brk = false;
+		for (int32_t j_hi = i - 1; j_hi >= st && !brk; j_hi -= 32) {
+			const int32_t j = j_hi - lane;
+			bool valid = false, marked = false;
+			int32_t cand = INT32_MIN, pj = -1;
+			if (j >= st) {
+				const int32_t sc = mmx_comput_sc(ai, a[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+				if (sc != INT32_MIN) valid = true, cand = sc + f[j], pj = p[j];
+				marked = t[j] == i;
+			}
+			// marks by predecessors of this chunk that land inside the chunk (p[j'] < j', so the marker is always scanned earlier)
+			unsigned bit = 0;
+			if (valid && pj >= 0) {
+				if (pj >= j_hi - 31) bit = 1u << (j_hi - pj);
+				else t[pj] = i; // lands in a later chunk
+			}
+			const unsigned mask = __reduce_or_sync(full, bit);
+			marked = marked || (mask >> lane & 1);
+			// exclusive prefix max of the valid candidates
+			int32_t pm = valid? cand : INT32_MIN;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(full, pm, o); if (lane >= o) pm = max(pm, y); }
+			int32_t ex = __shfl_up_sync(full, pm, 1);
+			if (lane == 0) ex = INT32_MIN;
+			const int32_t run = max(max_f, ex);          // running maximum seen by this lane
+			const bool improve = valid && cand > run;
+			// n_skip as a composition of maps x -> max(x + ca, cb): improve: (-1, 0); counted skip: (+1, -inf); else identity
+			int32_t ca = 0, cb = INT32_MIN / 2;
+			const bool inc = valid && !improve && marked;
+			if (improve) ca = -1, cb = 0;
+			else if (inc) ca = 1;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { // inclusive scan: result = (later map) o (earlier map)
+				const int32_t pa = __shfl_up_sync(full, ca, o), pb = __shfl_up_sync(full, cb, o);
+				if (lane >= o) { const int32_t na = pa + ca, nb = max(pb + ca, cb); ca = na, cb = nb; }
+			}
+			const int32_t ns_after = max(n_skip + ca, cb);
+			const unsigned brk_mask = __ballot_sync(full, inc && ns_after > max_skip);
+			int lim = 32; // lanes < lim are processed
+			if (brk_mask) { const int b = __ffs(brk_mask) - 1; lim = b; brk = true; end_j = j_hi - b; }
+			const unsigned imp_mask = __ballot_sync(full, improve) & (lim >= 32? full : ((1u << lim) - 1));
+			if (imp_mask) {
+				const int last = 31 - __clz(imp_mask);   // the last improving lane holds the running maximum
+				max_f = __shfl_sync(full, cand, last), max_j = j_hi - last;
+			}
+			if (!brk) n_skip = __shfl_sync(full, ns_after, 31);
+			__syncwarp(); // order the t[] marks before the next chunk reads them
+		}
+		// max_ii shortcut (lchain.c:188-201)
+		if (best_prev < 0 || ai.x - a[best_prev].x > (uint64_t)(int64_t)max_dist_x) {
+			int32_t mx = INT32_MIN, mxj = -1;
+			for (int32_t j = i - 1 - lane; j >= st; j -= 32) { const int32_t fj = f[j]; if (mx < fj) mx = fj, mxj = j; } // per lane: descending j, strict '<'
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { // ties go to the larger j (scanned first by the reference)
+				const int32_t om = __shfl_xor_sync(full, mx, o), oj = __shfl_xor_sync(full, mxj, o);
+				if (om > mx || (om == mx && oj > mxj)) mx = om, mxj = oj;
+			}
+			best_prev = mxj;
+		}
+		if (best_prev >= 0 && best_prev < end_j) {
+			const int32_t tmp = mmx_comput_sc(ai, a[best_prev], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
+			if (tmp != INT32_MIN && max_f < tmp + f[best_prev]) max_f = tmp + f[best_prev], max_j = best_prev;
+		}
+		if (lane == 0) {
+			f[i] = max_f, p[i] = max_j;
+			v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
+		}
+		__syncwarp();
+		if (best_prev < 0 || (ai.x - a[best_prev].x <= (uint64_t)(int64_t)max_dist_x && f[best_prev] < max_f)) best_prev = i;
+	}
+}
+
+__global__ void __launch_bounds__(128) chain_bt_kernel(ChainArgs A)
 {
 	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
 	if (rd >= A.n_reads) return;
@@ -106,53 +211,11 @@ __global__ void __launch_bounds__(128) chain_dp_kernel(ChainArgs A)
 	const int32_t n = (int32_t)(A.a_off[rd + 1] - off);
 	A.n_u[rd] = 0, A.n_v[rd] = 0;
 	if (n <= 0) return;
-	const m128 *a = A.a + off;
-	int32_t *f = A.f + off, *p = A.p + off, *v = A.v + off, *t = A.t + off;
 	const mmb_chain_par_t &P = A.par;
-	int32_t max_dist_x = P.max_dist_x, max_dist_y = P.max_dist_y, max_drop = P.bw;
-	const int32_t bw = P.bw, max_skip = P.max_skip, max_iter = P.max_iter, is_cdna = P.is_cdna, n_seg = P.n_seg;
-	const float pen_gap = P.chn_pen_gap, pen_skip = P.chn_pen_skip;
-	if (max_dist_x < bw) max_dist_x = bw;
-	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
-	if (is_cdna) max_drop = INT32_MAX;
-
-	// ---- fill (lchain.c:168-207) ----
-	for (int32_t i = 0; i < n; ++i) t[i] = 0;
-	int32_t st = 0, best_prev = -1;
-	for (int32_t i = 0; i < n; ++i) {
-		const m128 ai = a[i];
-		int32_t max_j = -1, max_f = (int32_t)(ai.y >> 32 & 0xff), n_skip = 0, j, end_j;
-		while (st < i && (ai.x >> 32 != a[st].x >> 32 || ai.x > a[st].x + (uint64_t)(int64_t)max_dist_x)) ++st;
-		if (i - st > max_iter) st = i - max_iter;
-		for (j = i - 1; j >= st; --j) {
-			int32_t sc = mmx_comput_sc(ai, a[j], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
-			if (sc == INT32_MIN) continue;
-			sc += f[j];
-			if (sc > max_f) {
-				max_f = sc, max_j = j;
-				if (n_skip > 0) --n_skip;
-			} else if (t[j] == i) {
-				if (++n_skip > max_skip) break;
-			}
-			if (p[j] >= 0) t[p[j]] = i;
-		}
-		end_j = j;
-		if (best_prev < 0 || ai.x - a[best_prev].x > (uint64_t)(int64_t)max_dist_x) {
-			int32_t mx = INT32_MIN;
-			best_prev = -1;
-			for (j = i - 1; j >= st; --j) if (mx < f[j]) mx = f[j], best_prev = j;
-		}
-		if (best_prev >= 0 && best_prev < end_j) {
-			int32_t tmp = mmx_comput_sc(ai, a[best_prev], max_dist_x, max_dist_y, bw, pen_gap, pen_skip, is_cdna, n_seg);
-			if (tmp != INT32_MIN && max_f < tmp + f[best_prev]) max_f = tmp + f[best_prev], max_j = best_prev;
-		}
-		f[i] = max_f, p[i] = max_j;
-		v[i] = max_j >= 0 && v[max_j] > max_f? v[max_j] : max_f;
-		if (best_prev < 0 || (ai.x - a[best_prev].x <= (uint64_t)(int64_t)max_dist_x && f[best_prev] < f[i])) best_prev = i;
-	}
-
+	const int32_t max_drop = P.is_cdna? INT32_MAX : P.bw;
 	int32_t n_u, n_v;
-	backtrack_compact(a, n, f, p, v, t, A.z + off, A.b + off, A.stk + A.stk_off[rd], P.min_sc, P.min_cnt, max_drop, A.u + off, A.a_out + off, &n_u, &n_v);
+	backtrack_compact(A.a + off, n, A.f + off, A.p + off, A.v + off, A.t + off, A.z + off, A.b + off, A.stk + A.stk_off[rd], P.min_sc, P.min_cnt, max_drop,
+					  A.u + off, A.a_out + off, &n_u, &n_v);
 	A.n_u[rd] = n_u, A.n_v[rd] = n_v;
 }
 
@@ -294,9 +357,10 @@ void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, c
 	A.stk_off = d_stk_off, A.stk = (int32_t*)(d_stk_off + n_reads + 1);
 	A.n_u = d_n_u, A.n_v = d_n_v, A.u = d_u, A.a_out = d_a_out;
 	ProfScope prof(ctx, MMB_PROF_CHAIN, (uint64_t)n_tot);
-	chain_dp_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(A);
+	chain_fill_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
+	chain_bt_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(A);
 	MMB_CUDA_CHECK(cudaGetLastError());
-	++ctx->n_launch;
+	ctx->n_launch += 2;
 }
 
 extern "C" int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,

@@ -42,13 +42,79 @@ __device__ void heapsort_u64(uint64_t *a, int n)
 	}
 }
 
-__global__ void __launch_bounds__(128) mzflt_kernel(SeedArgs A) // seed.c:5-28
+#define MZFLT_SMEM_MAX 2048
+#define MZFLT_SLOTS 4096
+
+// mm_seed_mz_flt (seed.c:5-28) for reads with <= 2048 minimizers: one CTA per read counts the multiplicity of every
+// minimizer value in a shared-memory hash table (the reference sorts a copy; only the counts matter), then drops the values
+// occurring more than max(q_occ_max, n*q_occ_frac) times with an order-preserving compaction. Nearly always nothing is dropped.
+__global__ void __launch_bounds__(128) mzflt_smem_kernel(SeedArgs A)
+{
+	extern __shared__ __align__(16) uint8_t mz_sm[];
+	unsigned long long *hkey = (unsigned long long*)mz_sm;
+	int *hcnt = (int*)(hkey + MZFLT_SLOTS);
+	int *s_part = hcnt + MZFLT_SLOTS;
+	int &s_drop = s_part[128];
+	for (int rd = blockIdx.x; rd < A.n_reads; rd += gridDim.x) {
+		const int64_t base = A.mz_off[rd];
+		const int n = A.n_mz[rd];
+		if (n <= A.q_occ_max || A.q_occ_frac <= 0.0f || A.q_occ_max <= 0 || n > MZFLT_SMEM_MAX) continue;
+		m128 *mz = A.mz + base;
+		for (int i = threadIdx.x; i < MZFLT_SLOTS; i += blockDim.x) hkey[i] = ~0ULL, hcnt[i] = 0;
+		if (threadIdx.x == 0) s_drop = 0;
+		__syncthreads();
+		for (int i = threadIdx.x; i < n; i += blockDim.x) {
+			const unsigned long long x = mz[i].x;
+			unsigned h = (unsigned)((x * 0x9E3779B97F4A7C15ULL) >> 52) & (MZFLT_SLOTS - 1);
+			for (;;) {
+				const unsigned long long old = atomicCAS(&hkey[h], ~0ULL, x);
+				if (old == ~0ULL || old == x) { atomicAdd(&hcnt[h], 1); break; }
+				h = (h + 1) & (MZFLT_SLOTS - 1);
+			}
+		}
+		__syncthreads();
+		const float thres = (float)(uint64_t)n * A.q_occ_frac;
+		// per-thread contiguous slices so that the compaction keeps the original order
+		const int per = (n + blockDim.x - 1) / blockDim.x, b0 = threadIdx.x * per, b1 = min(n, b0 + per);
+		int keep = 0;
+		for (int i = b0; i < b1; ++i) {
+			const unsigned long long x = mz[i].x;
+			unsigned h = (unsigned)((x * 0x9E3779B97F4A7C15ULL) >> 52) & (MZFLT_SLOTS - 1);
+			while (hkey[h] != x) h = (h + 1) & (MZFLT_SLOTS - 1);
+			const int cnt = hcnt[h];
+			const bool drop = (cnt > A.q_occ_max && (float)cnt > thres) || x == 0;
+			if (drop) s_drop = 1; else ++keep;
+		}
+		s_part[threadIdx.x] = keep;
+		__syncthreads();
+		if (s_drop) { // rare: order-preserving squeeze (seed.c:24-27)
+			int start = 0;
+			for (int k = 0; k < (int)threadIdx.x; ++k) start += s_part[k];
+			m128 loc[16]; // per <= 2048/128
+			int m = 0;
+			for (int i = b0; i < b1; ++i) {
+				const unsigned long long x = mz[i].x;
+				unsigned h = (unsigned)((x * 0x9E3779B97F4A7C15ULL) >> 52) & (MZFLT_SLOTS - 1);
+				while (hkey[h] != x) h = (h + 1) & (MZFLT_SLOTS - 1);
+				const int cnt = hcnt[h];
+				if (!((cnt > A.q_occ_max && (float)cnt > thres) || x == 0)) loc[m++] = mz[i];
+			}
+			__syncthreads();
+			for (int k = 0; k < m; ++k) mz[start + k] = loc[k];
+			if (threadIdx.x == blockDim.x - 1) A.n_mz[rd] = start + m;
+		}
+		__syncthreads();
+	}
+}
+
+__global__ void __launch_bounds__(128) mzflt_kernel(SeedArgs A) // seed.c:5-28 (reads with more than 2048 minimizers)
 {
 	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
 	if (rd >= A.n_reads) return;
 	const int64_t base = A.mz_off[rd];
 	const int n = A.n_mz[rd];
 	if (n <= A.q_occ_max || A.q_occ_frac <= 0.0f || A.q_occ_max <= 0) return;
+	if (n <= MZFLT_SMEM_MAX) return; // handled by mzflt_smem_kernel
 	m128 *mz = A.mz + base;
 	uint64_t *tmp = A.mini_pos + base; // free at this point
 	for (int i = 0; i < n; ++i) tmp[i] = mz[i].x;
@@ -278,15 +344,40 @@ __global__ void sort_block_kernel(const m128 *a_in, m128 *a_out, const int64_t *
 }
 
 __global__ void __launch_bounds__(64) sort_exact_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
-														const int *list2, const int *cnt2_ptr, int32_t *stk, const int64_t *stk_off)
+														int32_t *stk, const int64_t *stk_off)
 {
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
-	const int n1 = *cnt_ptr, n2 = *cnt2_ptr;
-	if (t >= n1 + n2) return;
-	const int rd = t < n1? list[t] : list2[t - n1];
+	if (t >= *cnt_ptr) return;
+	const int rd = list[t];
 	const int64_t off = a_off[rd], n = a_off[rd + 1] - off;
 	for (int64_t i = 0; i < n; ++i) a_out[off + i] = a_in[off + i];
 	if (n > 1) mmx_rs_sort(a_out + off, n, stk + stk_off[rd], KeyX128());
+}
+
+// Exact emulation for the reads whose anchors contain equal keys: the sequential American-flag walk is latency-bound, so
+// it runs on a shared-memory copy of (x, original index) -- one warp per read, lane 0 walks, all lanes copy in/out.
+struct KeyIdx { uint64_t x; uint32_t i; };
+struct KeyOfKeyIdx { MM_HD uint64_t operator()(const KeyIdx &v) const { return v.x; } };
+
+__global__ void __launch_bounds__(32) sort_exact_smem_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
+															 int cap, int *over_cnt, int *over_list)
+{
+	extern __shared__ __align__(16) uint8_t sm_raw[];
+	KeyIdx *e = (KeyIdx*)sm_raw;
+	int32_t *stk = (int32_t*)(e + cap);
+	const int n_list = *cnt_ptr;
+	for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+		const int rd = list[li];
+		const int64_t off = a_off[rd];
+		const int n = (int)(a_off[rd + 1] - off);
+		if (n > cap) { if (threadIdx.x == 0) over_list[atomicAdd(over_cnt, 1)] = rd; continue; }
+		for (int i = threadIdx.x; i < n; i += 32) e[i].x = a_in[off + i].x, e[i].i = (uint32_t)i;
+		__syncwarp();
+		if (threadIdx.x == 0) mmx_rs_sort(e, (int64_t)n, stk, KeyOfKeyIdx());
+		__syncwarp();
+		for (int i = threadIdx.x; i < n; i += 32) a_out[off + i] = a_in[off + e[i].i];
+		__syncwarp();
+	}
 }
 
 __global__ void stk_len_kernel2(const int64_t *a_off, int n_reads, int64_t *stk_off)
@@ -314,7 +405,14 @@ void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz)
 		fprintf(stderr, "[ERROR] minimap2_b200: --for-only/--rev-only/ava (-X) /sr heap-sort seeding are not supported by this build yet\n");
 		abort();
 	}
+	{
+		const size_t smem = (size_t)MZFLT_SLOTS * 12 + 129 * 4 + 16;
+		static std::once_flag once;
+		std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(mzflt_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+		mzflt_smem_kernel<<<ctx->n_sm * 4, 128, smem, ctx->stream>>>(A);
+	}
 	mzflt_kernel<<<rb, 128, 0, ctx->stream>>>(A);
+	++ctx->n_launch;
 	if (total_mz > 0) lookup_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
 	select_kernel<<<rb, 128, 0, ctx->stream>>>(A);
 	MMB_CUDA_CHECK(cudaGetLastError());
@@ -356,9 +454,17 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 																	 d_cls_cnt + N_CLS + 1, d_cls_list + (size_t)(N_CLS + 1) * A.n_reads);
 			++ctx->n_launch;
 		}
-		// exact emulation for oversize reads and reads with equal keys (upper bound on the launch: all reads; threads beyond the lists exit)
-		sort_exact_kernel<<<(A.n_reads + 63) / 64, 64, 0, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)N_CLS * A.n_reads, d_cls_cnt + N_CLS,
-																		 d_cls_list + (size_t)(N_CLS + 1) * A.n_reads, d_cls_cnt + N_CLS + 1, d_stk, d_stk_off);
+		// exact emulation: reads with equal keys go through the shared-memory walker (cap 12288 anchors: 16 B/entry + stack);
+		// whatever does not fit, and the oversize class, falls back to the global-memory walker (one thread per read)
+		{
+			const int cap = 12288;
+			const size_t smem = (size_t)cap * sizeof(KeyIdx) + (size_t)mmx_rs_stack_len(cap) * 4;
+			{ static std::once_flag once; std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(sort_exact_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024)); }); }
+			sort_exact_smem_kernel<<<ctx->n_sm, 32, smem, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)(N_CLS + 1) * A.n_reads, d_cls_cnt + N_CLS + 1,
+																		 cap, d_cls_cnt + N_CLS, d_cls_list + (size_t)N_CLS * A.n_reads);
+			++ctx->n_launch;
+		}
+		sort_exact_kernel<<<(A.n_reads + 63) / 64, 64, 0, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)N_CLS * A.n_reads, d_cls_cnt + N_CLS, d_stk, d_stk_off);
 		++ctx->n_launch;
 	}
 	MMB_CUDA_CHECK(cudaGetLastError());

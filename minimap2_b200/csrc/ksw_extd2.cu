@@ -19,6 +19,7 @@
 //    traceback instead of being stored.
 //  * Jobs are pulled from a queue (atomic counter) by persistent workers: grid = SMs x resident CTAs.
 #include "mmb_internal.h"
+#include "ksw_plan.h"
 #include <algorithm>
 #include <numeric>
 #include <mutex>
@@ -556,9 +557,9 @@ __global__ void __launch_bounds__(128) ksw_ll_kernel(LLArgs A)
 } // namespace
 
 bool mmb_ksw_fast_eligible(const mmb_ksw_job_t &j);
-void mmb_ksw_fast_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vector<int> &idx, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
-						 const uint8_t *d_query, const void *d_target, int t_packed, mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap,
-						 unsigned long long *d_cigar_used, DevBuf &pws, DevBuf &cigws, DevBuf &orderbuf);
+void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vector<int> &idx, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
+					   const uint8_t *d_query, const void *d_target, int t_packed, mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap,
+					   unsigned long long *d_cigar_used, int *d_order_all, std::vector<KswPlan> &plans);
 
 // Host-side tiering + launch. Tiers by max(qlen,tlen): warp-per-job for <=1024, CTA-per-job above.
 void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
@@ -627,16 +628,14 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		++ctx->n_launch;
 	}
 	if (ctx->profiling) ctx->prof_bytes[MMB_PROF_KSW] += io_bytes + cells; // reference-layout algorithmic bytes: sequences + 1 B/cell traceback (+4 B per CIGAR op, added by the caller)
-	ProfScope prof(ctx, MMB_PROF_KSW, cells);
-	ctx->d_g.reserve(((size_t)n_jobs * 3 + 256) * sizeof(int)); // queues: [0,n) fast path | [n+64,2n+..) universal tiers | [2n+128,..) ll
+	int *d_queues = (int*)ctx->d_g.reserve(((size_t)n_jobs * 3 + 256) * sizeof(int)); // queues: [0,n+64) fast path | [n+64,2n+128) universal tiers | [2n+128,..) ll
 	size_t g_off = (size_t)n_jobs + 64;
-	mmb_ksw_fast_launch(ctx, sc, fastj, h_jobs, d_jobs, d_query, d_target, t_packed, d_res, d_cigar, cigar_cap, d_cigar_used, ctx->d_e, ctx->d_f, ctx->d_g);
+	std::vector<KswPlan> plans;
+	mmb_ksw_fast_plan(ctx, sc, fastj, h_jobs, d_jobs, d_query, d_target, t_packed, d_res, d_cigar, cigar_cap, d_cigar_used, d_queues, plans);
 	for (int k = 0; k < n_tiers; ++k) {
 		std::vector<int> &v = tj[k];
 		if (v.empty()) continue;
-		std::sort(v.begin(), v.end(), [&](int a, int b) {
-			int64_t ca = (int64_t)h_jobs[a].qlen * h_jobs[a].tlen, cb = (int64_t)h_jobs[b].qlen * h_jobs[b].tlen;
-			return ca != cb? ca > cb : a < b; });
+		mmb_order_by_cells(v, h_jobs);
 		int maxq = 0, maxt = 0; size_t maxp = 0; int maxsum = 0;
 		for (int i : v) {
 			const mmb_ksw_job_t &j = h_jobs[i];
@@ -671,15 +670,28 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		// bound the traceback workspace (8 GB): fewer resident workers for very large matrices
 		while ((size_t)workers * maxp > ((size_t)8 << 30) && grid > 1) grid = (grid + 1) / 2;
 		A.pws_stride = maxp, A.cigws_stride = (size_t)maxsum + 8;
-		A.pws = (uint8_t*)ctx->d_e.reserve(A.pws_stride * (size_t)grid * nw);
-		A.cigws = (uint32_t*)ctx->d_f.reserve(A.cigws_stride * 4 * (size_t)grid * nw);
-		int *d_order = (int*)ctx->d_g.reserve(((size_t)n_jobs * 3 + 256) * sizeof(int)) + g_off; g_off += v.size() + 1;
+		int *d_order = d_queues + g_off; g_off += v.size() + 1;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		A.counter = d_order, A.order = d_order + 1, A.n = (int)v.size();
-		if (G == 32) ksw_extd2_kernel<32><<<grid, threads, smem, ctx->stream>>>(A);
-		else ksw_extd2_kernel<256><<<grid, threads, smem, ctx->stream>>>(A);
-		MMB_CUDA_CHECK(cudaGetLastError());
-		++ctx->n_launch;
+		KswPlan pl;
+		pl.pws_bytes = A.pws_stride * (size_t)grid * nw, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nw;
+		const KswArgs A0 = A;
+		pl.go = [=](uint8_t *pws, uint32_t *cigws) {
+			KswArgs B = A0;
+			B.pws = pws, B.cigws = cigws;
+			if (G == 32) ksw_extd2_kernel<32><<<grid, threads, smem, ctx->stream>>>(B);
+			else ksw_extd2_kernel<256><<<grid, threads, smem, ctx->stream>>>(B);
+			MMB_CUDA_CHECK(cudaGetLastError());
+			++ctx->n_launch;
+		};
+		plans.push_back(pl);
 	}
+	// one workspace sized for the largest launch (they run one after another on the stream), then the kernels back to back
+	size_t pws_bytes = 0, cigws_bytes = 0;
+	for (const KswPlan &pl : plans) pws_bytes = std::max(pws_bytes, pl.pws_bytes), cigws_bytes = std::max(cigws_bytes, pl.cigws_bytes);
+	uint8_t *pws = (uint8_t*)ctx->d_e.reserve(pws_bytes);
+	uint32_t *cigws = (uint32_t*)ctx->d_f.reserve(cigws_bytes);
+	ProfScope prof(ctx, MMB_PROF_KSW, cells);
+	for (const KswPlan &pl : plans) pl.go(pws, cigws);
 }

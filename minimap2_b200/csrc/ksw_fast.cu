@@ -18,6 +18,7 @@
 // Jobs that do not qualify (exact max / extension / right-aligned / clipped band / long) go to the universal kernel
 // in ksw_extd2.cu, which emulates the SSE lane semantics exactly.
 #include "mmb_internal.h"
+#include "ksw_plan.h"
 #include <algorithm>
 
 #define KSW_NEG_INF (-0x40000000)
@@ -251,7 +252,244 @@ __global__ void __launch_bounds__(128) ksw_fast_kernel(FastArgs A)
 	}
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Packed variant: two DP cells per 32-bit operation.
+//
+// The kernel above is issue-bound (~40 integer instructions per cell). Every quantity of the difference recurrence fits
+// in 8 bits, so two cells are packed as 16-bit halves of one register and updated with VIMNMX(3).S16x2 and plain 32-bit
+// adds. Layout of a half: ((value + 128) << 7) | low bits. Biasing keeps both halves non-negative, hence a 32-bit
+// add/subtract of packed words never carries between halves; the 7 low bits are scratch: a candidate carries the tag
+// 7-k of the state k it stands for, so one 3-input maximum returns both max(z) and the reference's tie rule (the earlier
+// state wins, ksw2_extd2_sse.c:235-243), and the gap-open floor carries one "not extended" bit per gap state, so the
+// four continuation flags (:244-273) drop out of the maxima as well. ~28 instructions per PAIR of cells.
+// The two cells of a pair must be independent: lane l owns columns [l*C, l*C+C), split in a left block A and a right
+// block B of H = C/2 columns; B runs one query row behind A (its left input is A's right edge of the previous step), and
+// lane l+1 runs two rows behind lane l. Traceback bytes are stored as (tag | flags), i.e. the reference byte XOR 0x7f.
+template<int H>
+__global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
+{
+	extern __shared__ uint8_t smem[];
+	constexpr int C = 2 * H;
+	constexpr int CPH = H <= 1? 1 : H <= 2? 2 : H <= 4? 4 : 8; // traceback bytes per block per row (one aligned store)
+	constexpr int CP = 2 * CPH;
+	constexpr int NW = (H + 3) / 4;
+	const int lane = threadIdx.x & 31, wk = threadIdx.x >> 5, nwk = blockDim.x >> 5;
+	const int worker = blockIdx.x * nwk + wk;
+	uint8_t *qs = smem + (size_t)wk * (A.qmax + 1024);   // staged query, one-hot (0x80 = ambiguous)
+	uint8_t *p = A.pws + A.pws_stride * worker;
+	uint32_t *cig = A.cigws + A.cigws_stride * worker;
+	const int W = 32 * CP;
+	const int q = A.q, e = A.e, q2 = A.q2, e2 = A.e2, qe = q + e, qe2 = q2 + e2;
+	const unsigned full = 0xffffffffu;
+	#define PK_ENC(v) ((uint32_t)((v) + 128) << 7)
+	#define PK2(v) (PK_ENC(v) * 0x10001u)
+	const uint32_t BB2 = 0x40004000u, CLEAN = 0xff80ff80u, FLAGM = 0x00780078u, TAGM = 0x00070007u;
+	const uint32_t K_A = 0x00060006u - BB2, K_B = 0x00050005u - BB2, K_A2 = 0x00040004u - BB2, K_B2 = 0x00030003u - BB2;
+	const uint32_t KX = BB2 - ((uint32_t)e << 7) * 0x10001u - 0x00060006u, KY = BB2 - ((uint32_t)e << 7) * 0x10001u - 0x00050005u;
+	const uint32_t KX2 = BB2 - ((uint32_t)e2 << 7) * 0x10001u - 0x00040004u, KY2 = BB2 - ((uint32_t)e2 << 7) * 0x10001u - 0x00030003u;
+	const uint32_t NQX = PK2(-qe) | 0x00080008u, NQY = PK2(-qe) | 0x00100010u, NQX2 = PK2(-qe2) | 0x00200020u, NQY2 = PK2(-qe2) | 0x00400040u;
+	const uint32_t MCH8 = PK2((int)A.mch), SCN_T = PK2((int)A.scn) + 0x00070007u;
+	const uint32_t KMM = (uint32_t)((int)A.mch - (int)A.mis) << 7;
+
+	#pragma unroll 1
+	for (;;) {
+		int slot = 0;
+		if (lane == 0) slot = atomicAdd(A.counter, 1);
+		slot = __shfl_sync(full, slot, 0);
+		if (slot >= A.n) break;
+		const int jid = A.order[slot];
+		const mmb_ksw_job_t jb = A.jobs[jid];
+		const int qlen = jb.qlen, tlen = jb.tlen;
+		for (int i = lane; i < qlen; i += 32) {
+			uint8_t c = A.query[jb.q_start + (long long)i * jb.q_step];
+			if ((jb.flag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
+			qs[i] = c < 4? (uint8_t)(1u << c) : (uint8_t)0x80;
+		}
+		const int t0 = lane * C;
+		uint32_t TBM[H], MSC[H], U[H], Y[H], Y2[H];
+		#pragma unroll
+		for (int c = 0; c < H; ++c) {
+			uint32_t tbm = 0, msc = 0, u = 0;
+			#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const int t = t0 + h * H + c;
+				const int b = t < tlen? fetch_t(A.target, A.t_packed, jb.t_start + (long long)t * jb.t_step) : 4;
+				// top boundary (ksw2_extd2_sse.c:159-162)
+				const int u0 = t == 0? -q - e : t < A.long_thres? -e : t == A.long_thres? A.long_diff : -e2;
+				tbm |= (b < 4? 1u << b : 0u) << (16 * h);
+				msc |= (PK_ENC(b == 4? (int)A.scn : (int)A.mis) + 7u) << (16 * h);
+				u |= PK_ENC(u0) << (16 * h);
+			}
+			TBM[c] = tbm, MSC[c] = msc, U[c] = u, Y[c] = PK2(-q - e), Y2[c] = PK2(-q2 - e2);
+		}
+		__syncwarp();
+		int hcol0 = 0, hrow = 0;
+		uint32_t vl_end = PK2(0), xl_end = PK2(-q - e), x2l_end = PK2(-q2 - e2); // right edges of the previous step (lo: block A, hi: block B)
+		uint32_t oh_prev = 0x80;           // one-hot query base of row jA-1
+		const int n_lanes = (tlen + C - 1) / C;
+		const int n_steps = qlen + 2 * (n_lanes - 1) + 1;
+		#pragma unroll 1
+		for (int s = 0; s < n_steps; ++s) {
+			const int jA = s - 2 * lane; // block A row; block B is at jA - 1
+			const uint32_t sv = __shfl_up_sync(full, vl_end, 1), sx = __shfl_up_sync(full, xl_end, 1), sx2 = __shfl_up_sync(full, x2l_end, 1);
+			if (jA >= 0 && jA <= qlen && t0 < tlen) {
+				uint32_t vl, xl, x2l;
+				if (lane == 0) { // left boundary (ksw2_extd2_sse.c:149-158 with st == 0)
+					const int v0 = jA == 0? -q - e : jA < A.long_thres? -e : jA == A.long_thres? A.long_diff : -e2;
+					vl = PK_ENC(v0) | vl_end << 16, xl = PK_ENC(-q - e) | xl_end << 16, x2l = PK_ENC(-q2 - e2) | x2l_end << 16;
+				} else {
+					vl = __byte_perm(sv, vl_end, 0x5432), xl = __byte_perm(sx, xl_end, 0x5432), x2l = __byte_perm(sx2, x2l_end, 0x5432);
+				}
+				const uint32_t oh = jA < qlen? qs[jA] : 0x80;
+				const uint32_t qbm = (oh & 0xf) | (oh_prev & 0xf) << 16;
+				const uint32_t mN = ((oh & 0x80)? 0xffffu : 0u) | ((oh_prev & 0x80)? 0xffff0000u : 0u);
+				oh_prev = oh;
+				uint32_t sU[H], sY[H], sY2[H];
+				if (jA == 0) { // block B has no row yet: its column state must survive this step
+					#pragma unroll
+					for (int c = 0; c < H; ++c) sU[c] = U[c], sY[c] = Y[c], sY2[c] = Y2[c];
+				}
+				uint32_t wd[NW * 4], v_first = 0;
+				#pragma unroll
+				for (int c = 0; c < NW * 4; ++c) wd[c] = 0;
+				#pragma unroll
+				for (int c = 0; c < H; ++c) {
+					const uint32_t f = __vminu2(TBM[c] & qbm, 0x00010001u);
+					uint32_t sc = f * KMM + MSC[c];
+					sc = (sc & ~mN) | (SCN_T & mN);
+					const uint32_t uc = U[c];
+					const uint32_t a = xl + vl + K_A, a2 = x2l + vl + K_A2, b = Y[c] + uc + K_B, b2 = Y2[c] + uc + K_B2;
+					uint32_t zt = __vimax3_s16x2(sc, a, b);
+					zt = __vimax3_s16x2(zt, a2, b2);
+					const uint32_t z8 = __vmins2(zt & CLEAN, MCH8);
+					const uint32_t un = z8 - vl + BB2, vn = z8 - uc + BB2;
+					const uint32_t xt = __vmaxs2(a - z8 + KX, NQX), yt = __vmaxs2(b - z8 + KY, NQY);
+					const uint32_t x2t = __vmaxs2(a2 - z8 + KX2, NQX2), y2t = __vmaxs2(b2 - z8 + KY2, NQY2);
+					wd[c] = (zt & TAGM) | ((xt | yt | x2t | y2t) & FLAGM);
+					xl = xt & CLEAN, Y[c] = yt & CLEAN, x2l = x2t & CLEAN, Y2[c] = y2t & CLEAN;
+					U[c] = un, vl = vn;
+					if (c == 0) v_first = vn;
+				}
+				vl_end = vl, xl_end = xl, x2l_end = x2l;
+				if (jA == 0) {
+					#pragma unroll
+					for (int c = 0; c < H; ++c)
+						U[c] = __byte_perm(U[c], sU[c], 0x7610), Y[c] = __byte_perm(Y[c], sY[c], 0x7610), Y2[c] = __byte_perm(Y2[c], sY2[c], 0x7610);
+				}
+				// score pieces: H(t, qlen-1) = H(t-1, qlen-1) + u(t, qlen-1) along the last row; H(0, j) down column 0
+				if (jA == qlen - 1) {
+					#pragma unroll
+					for (int c = 0; c < H; ++c) if (t0 + c >= 1 && t0 + c < tlen) hrow += (int)((U[c] & 0xffffu) >> 7) - 128;
+				}
+				if (jA == qlen) {
+					#pragma unroll
+					for (int c = 0; c < H; ++c) if (t0 + H + c < tlen) hrow += (int)(U[c] >> 23) - 128;
+				}
+				if (lane == 0 && jA < qlen) { const int v0 = (int)((v_first & 0xffffu) >> 7) - 128; hcol0 += jA == 0? v0 - qe : v0; }
+				// traceback bytes: lo bytes of the words -> row jA (block A), byte 2 of the words -> row jA-1 (block B)
+				uint32_t lo[NW], hi[NW];
+				#pragma unroll
+				for (int k = 0; k < NW; ++k) {
+					const uint32_t r01 = __byte_perm(wd[4 * k], wd[4 * k + 1], 0x6240), r23 = __byte_perm(wd[4 * k + 2], wd[4 * k + 3], 0x6240);
+					lo[k] = __byte_perm(r01, r23, 0x5410), hi[k] = __byte_perm(r01, r23, 0x7632);
+				}
+				if (jA < qlen) {
+					uint8_t *pa = p + (size_t)jA * W + lane * CP;
+					if (CPH == 1) *pa = (uint8_t)lo[0];
+					else if (CPH == 2) *(uint16_t*)pa = (uint16_t)lo[0];
+					else if (CPH == 4) *(uint32_t*)pa = lo[0];
+					else *(uint2*)pa = make_uint2(lo[0], lo[NW - 1]);
+				}
+				if (jA >= 1) {
+					uint8_t *pb = p + (size_t)(jA - 1) * W + lane * CP + CPH;
+					if (CPH == 1) *pb = (uint8_t)hi[0];
+					else if (CPH == 2) *(uint16_t*)pb = (uint16_t)hi[0];
+					else if (CPH == 4) *(uint32_t*)pb = hi[0];
+					else *(uint2*)pb = make_uint2(hi[0], hi[NW - 1]);
+				}
+			}
+		}
+		int score = hrow;
+		for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(full, score, o);
+		score += __shfl_sync(full, hcol0, 0);
+		__syncwarp();
+		// ---- traceback from (tlen-1, qlen-1) (ksw2.h:130-162; no forced states: the band is never clipped) ----
+		// The path is walked run by run instead of cell by cell: in the H state the 32 lanes look down the diagonal, in a gap
+		// state along the row/column, and a ballot finds where the run ends -- the per-cell rule of ksw_backtrack is unchanged.
+		int n = 0, i = tlen - 1, jj = qlen - 1, state = 0;
+		uint32_t run_op = 0, run_len = 0; // pending CIGAR run (lane 0 writes it when the operator changes)
+		#define PK_EMIT(op_, len_) do { const uint32_t o__ = (op_), l__ = (len_); if (l__) { if (run_len && o__ == run_op) run_len += l__; \
+			else { if (run_len && lane == 0) cig[n] = run_len << 4 | run_op; n += run_len? 1 : 0; run_op = o__, run_len = l__; } } } while (0)
+		while (i >= 0 && jj >= 0) {
+			const int di = (state == 0 || state == 1 || state == 3)? 1 : 0, dj = (state == 0 || state == 2 || state == 4)? 1 : 0;
+			const int ci = i - lane * di, cj = jj - lane * dj;
+			const bool inr = ci >= 0 && cj >= 0;
+			uint32_t tmp = 0;
+			if (inr) {
+				const int wi = ci % C;
+				tmp = p[(size_t)cj * W + (ci / C) * CP + (wi < H? wi : CPH + wi - H)] ^ 0x7fu;
+			}
+			const bool cont = inr && (state == 0? (tmp & 7) == 0 : (tmp >> (state + 2) & 1) != 0);
+			const unsigned stop = __ballot_sync(full, !cont);
+			const int r = stop? __ffs(stop) - 1 : 32;
+			PK_EMIT(state == 0? 0u : di? 2u : 1u, (uint32_t)r);
+			i -= r * di, jj -= r * dj;
+			if (r < 32) {
+				const uint32_t tr = __shfl_sync(full, tmp, r);
+				const bool in_r = __shfl_sync(full, (int)inr, r) != 0;
+				if (!in_r) break;              // ran off the matrix: the leftover is a leading gap (below)
+				if (state == 0) {              // first cell that leaves the diagonal: its own step, in its new state
+					state = tr & 7;
+					if (state == 1 || state == 3) { PK_EMIT(2u, 1u); --i; } else { PK_EMIT(1u, 1u); --jj; }
+				} else state = 0;              // the gap closes here: re-read this cell in the H state
+			}
+		}
+		if (i >= 0) PK_EMIT(2u, (uint32_t)(i + 1));
+		if (jj >= 0) PK_EMIT(1u, (uint32_t)(jj + 1));
+		if (run_len) { if (lane == 0) cig[n] = run_len << 4 | run_op; ++n; }
+		#undef PK_EMIT
+		__syncwarp();
+		n = __shfl_sync(full, n, 0);
+		unsigned long long coff = 0;
+		if (n > 0) {
+			if (lane == 0) coff = atomicAdd(A.cigar_used, (unsigned long long)n);
+			coff = __shfl_sync(full, coff, 0);
+			const bool rev_cigar = (jb.flag & MMB_KSW_REV_CIGAR) != 0;
+			if ((long long)(coff + n) <= A.cigar_cap)
+				for (int k = lane; k < n; k += 32) A.cigar[coff + k] = rev_cigar? cig[k] : cig[n - 1 - k];
+		}
+		if (lane == 0) {
+			mmb_ksw_res_t o;
+			o.max = 0, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1, o.mqe = o.mte = KSW_NEG_INF;
+			o.score = score, o.n_cigar = n, o.reach_end = 0, o.cigar_off = (uint32_t)coff;
+			A.res[jid] = o;
+		}
+		__syncwarp();
+	}
+	#undef PK_ENC
+	#undef PK2
+}
+
 } // namespace
+
+// Longest-first queue order for the persistent kernels (dynamic scheduling then has a short tail). A counting sort on a
+// 4-bit-mantissa logarithmic key is enough: O(n), deterministic, stable within a bucket.
+void mmb_order_by_cells(std::vector<int> &v, const mmb_ksw_job_t *h_jobs)
+{
+	const int NB = 40 * 16;
+	auto key = [&](int i) {
+		uint64_t c = (uint64_t)std::max(h_jobs[i].qlen, 1) * (uint64_t)std::max(h_jobs[i].tlen, 1);
+		int lg = 63 - __builtin_clzll(c);
+		int mant = lg >= 4? (int)(c >> (lg - 4)) & 15 : (int)(c << (4 - lg)) & 15;
+		return NB - 1 - std::min(NB - 1, lg * 16 + mant);
+	};
+	std::vector<int> cnt(NB + 1, 0), out(v.size());
+	for (int i : v) ++cnt[key(i) + 1];
+	for (int b = 0; b < NB; ++b) cnt[b + 1] += cnt[b];
+	for (int i : v) out[cnt[key(i)]++] = i;
+	v.swap(out);
+}
 
 bool mmb_ksw_fast_eligible(const mmb_ksw_job_t &j)
 {
@@ -265,9 +503,9 @@ bool mmb_ksw_fast_eligible(const mmb_ksw_job_t &j)
 
 // Launches the fast kernel over the eligible jobs listed in `idx` (indices into the batch). Asynchronous on ctx->stream
 // except for the queue-order upload, which is synchronised before returning.
-void mmb_ksw_fast_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vector<int> &idx, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
-						 const uint8_t *d_query, const void *d_target, int t_packed, mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap,
-						 unsigned long long *d_cigar_used, DevBuf &pws, DevBuf &cigws, DevBuf &orderbuf)
+void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vector<int> &idx, const mmb_ksw_job_t *h_jobs, const mmb_ksw_job_t *d_jobs,
+					   const uint8_t *d_query, const void *d_target, int t_packed, mmb_ksw_res_t *d_res, uint32_t *d_cigar, int64_t cigar_cap,
+					   unsigned long long *d_cigar_used, int *d_order_all, std::vector<KswPlan> &plans)
 {
 	if (idx.empty()) return;
 	FastArgs A;
@@ -281,23 +519,27 @@ void mmb_ksw_fast_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::v
 	int lt = e != e2? (q2 - q) / (e - e2) - 1 : 0;
 	if (q2 + e2 + lt * e2 > q + e + lt * e) ++lt;
 	A.long_thres = lt, A.long_diff = lt * (e - e2) - (q2 - q) - e2;
+	// The packed kernel needs every intermediate of the recurrence inside [-128, 127] with room to spare, and the simple
+	// match/mismatch scoring; anything else runs the scalar kernel.
+	static const bool no_pk = getenv("MM_B200_NO_PK_KSW") != nullptr;
+	const int amax = std::max(std::abs((int)A.mch), std::max(std::abs((int)A.mis), std::abs((int)A.scn)));
+	const bool pk_ok = !no_pk && 2 * std::max(q + e, q2 + e2) + amax + 8 <= 127 && A.mch > 0 && A.mis <= 0 && A.scn <= 0;
 	// column strips: the smallest C with 32*C >= tlen keeps the idle-lane fraction low (C is a template parameter)
-	static const int CW[] = { 2, 4, 6, 7, 8, 9, 10, 12, 14, 16 };
-	static const int CPW[] = { 4, 4, 8, 8, 8, 16, 16, 16, 16, 16 };
-	const int NC = sizeof(CW) / sizeof(CW[0]);
+	static const int CW[] = { 2, 4, 6, 7, 8, 9, 10, 12, 14, 16,   2, 4, 6, 8, 10, 12, 14, 16 };
+	static const int CPW[] = { 4, 4, 8, 8, 8, 16, 16, 16, 16, 16,   2, 4, 8, 8, 16, 16, 16, 16 };
+	const int NS = 10, NC = 18; // [0,NS): scalar kernel widths, [NS,NC): packed kernel widths
 	std::vector<int> v[NC];
 	for (int i : idx) {
-		int k = 0;
-		while (k < NC - 1 && 32 * CW[k] < h_jobs[i].tlen) ++k;
+		const bool pk = pk_ok && !(h_jobs[i].flag & MMB_KSW_GENERIC_SC);
+		int k = pk? NS : 0;
+		const int last = pk? NC - 1 : NS - 1;
+		while (k < last && 32 * CW[k] < h_jobs[i].tlen) ++k;
 		v[k].push_back(i);
 	}
-	int *d_order_all = (int*)orderbuf.reserve((idx.size() + NC + 1) * sizeof(int));
 	size_t order_off = 0;
 	for (int k = 0; k < NC; ++k) {
 		if (v[k].empty()) continue;
-		std::sort(v[k].begin(), v[k].end(), [&](int a, int b) {
-			int64_t ca = (int64_t)h_jobs[a].qlen * h_jobs[a].tlen, cb = (int64_t)h_jobs[b].qlen * h_jobs[b].tlen;
-			return ca != cb? ca > cb : a < b; });
+		mmb_order_by_cells(v[k], h_jobs);
 		int maxq = 1, maxsum = 2;
 		for (int i : v[k]) maxq = std::max(maxq, h_jobs[i].qlen), maxsum = std::max(maxsum, h_jobs[i].qlen + h_jobs[i].tlen);
 		const int C = CW[k], W = 32 * CPW[k];
@@ -305,7 +547,13 @@ void mmb_ksw_fast_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::v
 		const int threads = 128, nwk = threads / 32;
 		const size_t smem = (size_t)(A.qmax + 1024) * nwk;
 		void (*kern)(FastArgs) = nullptr;
-		switch (C) {
+		if (k >= NS) switch (C) {
+		case 2: kern = ksw_pk_kernel<1>; break;   case 4: kern = ksw_pk_kernel<2>; break;
+		case 6: kern = ksw_pk_kernel<3>; break;   case 8: kern = ksw_pk_kernel<4>; break;
+		case 10: kern = ksw_pk_kernel<5>; break;  case 12: kern = ksw_pk_kernel<6>; break;
+		case 14: kern = ksw_pk_kernel<7>; break;  default: kern = ksw_pk_kernel<8>; break;
+		}
+		else switch (C) {
 		case 2: kern = ksw_fast_kernel<2>; break;   case 4: kern = ksw_fast_kernel<4>; break;
 		case 6: kern = ksw_fast_kernel<6>; break;   case 7: kern = ksw_fast_kernel<7>; break;
 		case 8: kern = ksw_fast_kernel<8>; break;   case 9: kern = ksw_fast_kernel<9>; break;
@@ -319,14 +567,20 @@ void mmb_ksw_fast_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::v
 		grid = std::max(1, std::min(grid, ((int)v[k].size() + nwk - 1) / nwk));
 		A.pws_stride = ((size_t)maxq * W + 255) & ~(size_t)255;
 		A.cigws_stride = (size_t)maxsum + 8;
-		A.pws = (uint8_t*)pws.reserve(A.pws_stride * (size_t)grid * nwk);   // may grow (cudaFree synchronises) -- rare after warm-up
-		A.cigws = (uint32_t*)cigws.reserve(A.cigws_stride * 4 * (size_t)grid * nwk);
 		int *d_order = d_order_all + order_off; order_off += v[k].size() + 1;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v[k].data(), v[k].size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		A.counter = d_order, A.order = d_order + 1, A.n = (int)v[k].size();
-		kern<<<grid, threads, smem, ctx->stream>>>(A);
-		MMB_CUDA_CHECK(cudaGetLastError());
-		++ctx->n_launch;
+		KswPlan pl;
+		pl.pws_bytes = A.pws_stride * (size_t)grid * nwk, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nwk;
+		const FastArgs A0 = A;
+		pl.go = [=](uint8_t *pws, uint32_t *cigws) {
+			FastArgs B = A0;
+			B.pws = pws, B.cigws = cigws;
+			kern<<<grid, threads, smem, ctx->stream>>>(B);
+			MMB_CUDA_CHECK(cudaGetLastError());
+			++ctx->n_launch;
+		};
+		plans.push_back(pl);
 	}
 }

@@ -18,6 +18,9 @@
 #include <cstring>
 #include <algorithm>
 #include <mutex>
+#include <condition_variable>
+#include <deque>
+#include <memory>
 
 extern "C" double realtime(void);
 extern "C" double cputime(void);
@@ -29,26 +32,100 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 
 namespace {
 
+// A persistent host worker pool shared by every group: a group's host phase is one Task (an index range consumed in
+// grains); workers swarm the oldest unfinished task, and the submitting thread works on its own task too. This replaces
+// kt_for (kthread.c:54-70) -- persistent threads keep their malloc arenas and avoid spawning ~100 threads per phase.
+struct Task {
+	const std::function<void(int64_t, int)> *fn;
+	int64_t n, grain;
+	std::atomic<int64_t> next{0}, done{0};
+};
+class HostPool {
+public:
+	explicit HostPool(int n_workers) {
+		for (int t = 0; t < n_workers; ++t) th_.emplace_back([this, t]() { worker(t + 1); });
+	}
+	int size() const { return (int)th_.size(); }
+	void run(int64_t n, const std::function<void(int64_t, int)> &fn) {
+		if (n <= 0) return;
+		auto task = std::make_shared<Task>();
+		task->fn = &fn, task->n = n, task->grain = std::max<int64_t>(1, n / ((int64_t)(th_.size() + 1) * 8));
+		{ std::lock_guard<std::mutex> lk(mu_); q_.push_back(task); }
+		cv_.notify_all();
+		work_on(*task, 0);
+		if (task->done.load(std::memory_order_acquire) < n) { // wait for grains still running on workers
+			std::unique_lock<std::mutex> lk(mu_);
+			done_cv_.wait(lk, [&]() { return task->done.load(std::memory_order_acquire) >= n; });
+		}
+		std::lock_guard<std::mutex> lk(mu_);
+		for (size_t i = 0; i < q_.size(); ++i) if (q_[i] == task) { q_.erase(q_.begin() + i); break; }
+	}
+private:
+	void work_on(Task &t, int tid) {
+		for (;;) {
+			const int64_t b = t.next.fetch_add(t.grain);
+			if (b >= t.n) break;
+			const int64_t e = std::min(t.n, b + t.grain);
+			for (int64_t i = b; i < e; ++i) (*t.fn)(i, tid);
+			if (t.done.fetch_add(e - b, std::memory_order_acq_rel) + (e - b) >= t.n) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+		}
+	}
+	void worker(int tid) {
+		for (;;) {
+			std::shared_ptr<Task> t;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_.wait(lk, [&]() {
+					for (auto &x : q_) if (x->next.load(std::memory_order_relaxed) < x->n) { t = x; return true; }
+					return false;
+				});
+			}
+			work_on(*t, tid);
+		}
+	}
+	std::mutex mu_;
+	std::condition_variable cv_, done_cv_;
+	std::deque<std::shared_ptr<Task>> q_;
+	std::vector<std::thread> th_;
+};
+HostPool *g_pool = nullptr;
+std::once_flag g_pool_once;
+
 void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t, int)> &fn)
 {
 	if (n <= 0) return;
-	if (n_threads < 1) n_threads = 1;
-	if (n_threads > n) n_threads = (int)n;
-	if (n_threads == 1) { for (int64_t i = 0; i < n; ++i) fn(i, 0); return; }
-	std::atomic<int64_t> next(0);
-	std::vector<std::thread> th;
-	const int64_t grain = std::max<int64_t>(1, n / (n_threads * 16));
-	for (int t = 0; t < n_threads; ++t)
-		th.emplace_back([&, t]() {
-			for (;;) {
-				int64_t b = next.fetch_add(grain);
-				if (b >= n) break;
-				int64_t e = std::min(n, b + grain);
-				for (int64_t i = b; i < e; ++i) fn(i, t);
-			}
-		});
-	for (auto &x : th) x.join();
+	if (n_threads <= 1 || n == 1) { for (int64_t i = 0; i < n; ++i) fn(i, 0); return; }
+	std::call_once(g_pool_once, [&]() { g_pool = new HostPool(n_threads - 1); }); // sized by the first caller; never torn down
+	g_pool->run(n, fn);
 }
+
+int g_gpu_slots = getenv("MM_B200_GPU_SLOTS")? std::max(1, atoi(getenv("MM_B200_GPU_SLOTS"))) : 2;
+// FIFO gate bounding how many groups are in a device phase at once: with more groups than slots, the groups fall out of
+// lock-step and one group's host phase overlaps the others' kernels.
+class GpuGate {
+public:
+	void acquire() {
+		std::unique_lock<std::mutex> lk(mu_);
+		const uint64_t my = tail_++;
+		cv_.wait(lk, [&]() { return my == head_ && in_ < slots(); });
+		++head_, ++in_;
+		cv_.notify_all();
+	}
+	void release() { std::lock_guard<std::mutex> lk(mu_); --in_; cv_.notify_all(); }
+	static int slots() { return g_gpu_slots; }
+private:
+	std::mutex mu_;
+	std::condition_variable cv_;
+	uint64_t head_ = 0, tail_ = 0;
+	int in_ = 0;
+};
+GpuGate g_gate;
+struct GateHold {
+	bool on;
+	explicit GateHold(bool use) : on(use) { if (on) g_gate.acquire(); }
+	void drop() { if (on) g_gate.release(), on = false; }
+	~GateHold() { drop(); }
+};
 
 __global__ void encode_kernel(uint8_t *s, int64_t n)
 {
@@ -126,8 +203,8 @@ struct BatchBufs { // device arenas reused across batches (per context)
 	std::vector<ReadAlign> ra_pool;
 	std::vector<uint8_t> qseq_pool;        // nt4 forward + reverse-complement copies of the batch (2 x total bases)
 };
-struct GroupCtx { mmb_ctx_t *ctx = nullptr; BatchBufs bb; int64_t res_n = -1, res_bases = -1; const char *res_first = nullptr; };
-const int MAX_GROUPS = 8;
+struct GroupCtx { mmb_ctx_t *ctx = nullptr; BatchBufs bb; bool gated = false; int64_t res_n = -1, res_bases = -1; const char *res_first = nullptr; };
+const int MAX_GROUPS = 16;
 GroupCtx *g_groups[MAX_GROUPS] = {nullptr};
 std::mutex g_group_mu;
 
@@ -184,6 +261,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	uint8_t *h_seq = bb.h_seq.as<uint8_t>((size_t)total_bases + 16);
 	parallel_for(n, n_threads, [&](int64_t j, int) { memcpy(h_seq + off[j], rs[live[j]].seq, rs[live[j]].qlen); });
 	lap("host concat");
+	GateHold gate1(G.gated);
 	uint8_t *d_seq = bb.seq.as<uint8_t>((size_t)total_bases + 16);
 	int64_t *d_off = bb.off.as<int64_t>((size_t)n + 1);
 	int32_t *d_qlen = bb.qlen.as<int32_t>((size_t)n);
@@ -285,6 +363,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	MMB_CUDA_CHECK(cudaMemcpyAsync(h_dm, d_dm, sizeof(uint64_t) * (size_t)tot_m, cudaMemcpyDeviceToHost, ctx->stream));
 	MMB_CUDA_CHECK(cudaMemcpyAsync(h_rep, S.rep_len, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
 	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	gate1.drop();
 	ctx->last_d2h_bytes += misc_bytes;
 	if (ctx->profiling) {
 		ctx->prof_bytes[MMB_PROF_SKETCH] += (uint64_t)(total_bases / 4) + 16ull * (uint64_t)total_mz;
@@ -405,6 +484,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				int64_t cap_tot = 0;
 				for (int64_t i = 0; i < n_jobs; ++i) if (!(jobs[i].flag & MMB_JOB_LL)) cap_tot += (jobs[i].qlen + jobs[i].tlen) / 2 + 8;
 				uint32_t *h_cig = bb.h_cig[wave].as<uint32_t>((size_t)cap_tot + 64);
+				GateHold gatew(G.gated);
 				std::vector<int64_t> chunk_base; // offset of each chunk's CIGAR block inside h_cig
 				int64_t cig_fill = 0;
 				for (int64_t b = 0; b < n_jobs; b += CH) {
@@ -435,6 +515,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 						break;
 					}
 				}
+				gatew.drop();
 				lap("  wave gpu");
 				// hand the results to the per-read caches (pointers only)
 				parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
@@ -477,6 +558,7 @@ mmb_ctx_t *mmb_default_ctx(void);
 void mmb_register_ctx(mmb_ctx_t *c);
 
 static int g_groups_override = 0;
+extern "C" void mmb_set_gpu_slots(int n) { g_gpu_slots = n < 1? 1 : n; }
 extern "C" void mmb_set_groups(int n) { g_groups_override = n; } // 0 = default (MM_B200_GROUPS or 3)
 
 static GroupCtx &get_group(int g, int device)
@@ -509,7 +591,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	for (int i = 0; i < n_reads; ++i) total += qlens[i] > 0? qlens[i] : 0;
 	if (n_reads < 64 * NG || total < 4000000) NG = 1;
 	const int device = mi->B->ctx->device;
-	for (int g = 0; g < NG; ++g) get_group(g, device).ctx->profiling = mmb_default_ctx()->profiling;
+	for (int g = 0; g < NG; ++g) { GroupCtx &gc = get_group(g, device); gc.ctx->profiling = mmb_default_ctx()->profiling; gc.gated = NG > 1 && !sequential; }
 	if (NG == 1) return map_group(get_group(0, device), mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads);
 	std::vector<int> cut(NG + 1, 0);
 	{

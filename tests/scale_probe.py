@@ -23,11 +23,16 @@ print("reads: %.2fs" % (t2 - t1), flush=True)
 qlens = np.full(n_reads, rl, dtype=np.int32)
 ctx = L.mmb_default_ctx_c()
 names = ["r%d" % i for i in range(n_reads)]
-for it in range(3):
-    L.mmb_profile_enable_all(1 if it == 2 else 0)
-    t = time.time()
+sweep = os.environ.get("SWEEP", "")
+cfgs = [tuple(int(x) for x in c.split(":")) for c in sweep.split(",")] if sweep else [None] * 3
+for it, cfg in enumerate(cfgs):
+    if cfg is not None:
+        L.mmb_set_groups(cfg[0]); L.mmb_set_gpu_slots(cfg[1])
+        print("groups %d slots %d" % cfg, flush=True)
+    L.mmb_profile_enable_all(1 if (it == len(cfgs) - 1 and (not sweep or cfg[0] < 0)) else 0)
+    t = time.time(); c0 = time.process_time()
     n_regs, regs, rep = al.map_batch_raw(buf, qlens, names)
-    dt = time.time() - t
+    dt = time.time() - t; print('  cpu seconds %.2f' % (time.process_time() - c0))
     # aligned bases over primary records
     tot = 0
     for i in range(0, n_reads):

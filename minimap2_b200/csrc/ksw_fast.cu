@@ -266,7 +266,9 @@ __global__ void __launch_bounds__(128) ksw_fast_kernel(FastArgs A)
 // The two cells of a pair must be independent: lane l owns columns [l*C, l*C+C), split in a left block A and a right
 // block B of H = C/2 columns; B runs one query row behind A (its left input is A's right edge of the previous step), and
 // lane l+1 runs two rows behind lane l. Traceback bytes are stored as (tag | flags), i.e. the reference byte XOR 0x7f.
-template<int H>
+// Jobs with tlen <= 256 use LN = 16 lanes (two jobs per warp, up to 16 columns per lane): more columns per lane amortise
+// the per-step overhead (shuffles, stores, row bookkeeping) and halve the pipeline fill/drain of the lane skew.
+template<int H, int LN>
 __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 {
 	extern __shared__ uint8_t smem[];
@@ -274,12 +276,13 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 	constexpr int CPH = H <= 1? 1 : H <= 2? 2 : H <= 4? 4 : 8; // traceback bytes per block per row (one aligned store)
 	constexpr int CP = 2 * CPH;
 	constexpr int NW = (H + 3) / 4;
+	constexpr int NJ = 32 / LN;                                // jobs per warp
+	constexpr int W = LN * CP;                                 // traceback row stride
 	const int lane = threadIdx.x & 31, wk = threadIdx.x >> 5, nwk = blockDim.x >> 5;
-	const int worker = blockIdx.x * nwk + wk;
-	uint8_t *qs = smem + (size_t)wk * (A.qmax + 1024);   // staged query, one-hot (0x80 = ambiguous)
-	uint8_t *p = A.pws + A.pws_stride * worker;
-	uint32_t *cig = A.cigws + A.cigws_stride * worker;
-	const int W = 32 * CP;
+	const int sub = lane & (LN - 1), grp = lane / LN, lead = lane & ~(LN - 1);
+	const int worker0 = (blockIdx.x * nwk + wk) * NJ;
+	uint8_t *qs = smem + (size_t)(wk * NJ + grp) * A.qmax;   // staged query, one-hot (0x80 = ambiguous), one sentinel past the end
+	uint8_t *p = A.pws + A.pws_stride * (size_t)(worker0 + grp);
 	const int q = A.q, e = A.e, q2 = A.q2, e2 = A.e2, qe = q + e, qe2 = q2 + e2;
 	const unsigned full = 0xffffffffu;
 	#define PK_ENC(v) ((uint32_t)((v) + 128) << 7)
@@ -291,22 +294,28 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 	const uint32_t NQX = PK2(-qe) | 0x00080008u, NQY = PK2(-qe) | 0x00100010u, NQX2 = PK2(-qe2) | 0x00200020u, NQY2 = PK2(-qe2) | 0x00400040u;
 	const uint32_t MCH8 = PK2((int)A.mch), SCN_T = PK2((int)A.scn) + 0x00070007u;
 	const uint32_t KMM = (uint32_t)((int)A.mch - (int)A.mis) << 7;
+	const uint32_t E_QE = PK_ENC(-q - e), E_E = PK_ENC(-e), E_E2 = PK_ENC(-e2), E_LD = PK_ENC(A.long_diff), E_QE2 = PK_ENC(-q2 - e2);
+	const int lt = A.long_thres;
 
 	#pragma unroll 1
 	for (;;) {
 		int slot = 0;
-		if (lane == 0) slot = atomicAdd(A.counter, 1);
-		slot = __shfl_sync(full, slot, 0);
-		if (slot >= A.n) break;
-		const int jid = A.order[slot];
-		const mmb_ksw_job_t jb = A.jobs[jid];
-		const int qlen = jb.qlen, tlen = jb.tlen;
-		for (int i = lane; i < qlen; i += 32) {
-			uint8_t c = A.query[jb.q_start + (long long)i * jb.q_step];
-			if ((jb.flag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
+		if (sub == 0) slot = atomicAdd(A.counter, 1);
+		slot = __shfl_sync(full, slot, lead);
+		const bool act = slot < A.n;
+		if (!__any_sync(full, act)) break;
+		int jid = -1, qlen = 0, tlen = 0, jflag = 0;
+		mmb_ksw_job_t jb;
+		if (act) { jid = A.order[slot]; jb = A.jobs[jid]; qlen = jb.qlen, tlen = jb.tlen, jflag = jb.flag; }
+		for (int i = sub; i <= qlen; i += LN) {
+			uint8_t c = 4;
+			if (i < qlen) {
+				c = A.query[jb.q_start + (long long)i * jb.q_step];
+				if ((jflag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
+			}
 			qs[i] = c < 4? (uint8_t)(1u << c) : (uint8_t)0x80;
 		}
-		const int t0 = lane * C;
+		const int t0 = sub * C;
 		uint32_t TBM[H], MSC[H], U[H], Y[H], Y2[H];
 		#pragma unroll
 		for (int c = 0; c < H; ++c) {
@@ -316,40 +325,42 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 				const int t = t0 + h * H + c;
 				const int b = t < tlen? fetch_t(A.target, A.t_packed, jb.t_start + (long long)t * jb.t_step) : 4;
 				// top boundary (ksw2_extd2_sse.c:159-162)
-				const int u0 = t == 0? -q - e : t < A.long_thres? -e : t == A.long_thres? A.long_diff : -e2;
+				const uint32_t u0 = t == 0? E_QE : t < lt? E_E : t == lt? E_LD : E_E2;
 				tbm |= (b < 4? 1u << b : 0u) << (16 * h);
 				msc |= (PK_ENC(b == 4? (int)A.scn : (int)A.mis) + 7u) << (16 * h);
-				u |= PK_ENC(u0) << (16 * h);
+				u |= u0 << (16 * h);
 			}
-			TBM[c] = tbm, MSC[c] = msc, U[c] = u, Y[c] = PK2(-q - e), Y2[c] = PK2(-q2 - e2);
+			TBM[c] = tbm, MSC[c] = msc, U[c] = u, Y[c] = E_QE * 0x10001u, Y2[c] = E_QE2 * 0x10001u;
 		}
 		__syncwarp();
-		int hcol0 = 0, hrow = 0;
-		uint32_t vl_end = PK2(0), xl_end = PK2(-q - e), x2l_end = PK2(-q2 - e2); // right edges of the previous step (lo: block A, hi: block B)
+		int hrow = 0;
+		uint32_t hcol_acc = 0;             // sum over rows of enc(v) in column 0 (only meaningful in the group's first lane)
+		uint32_t vl_end = PK2(0), xl_end = E_QE * 0x10001u, x2l_end = E_QE2 * 0x10001u; // right edges of the previous step (lo: block A, hi: block B)
 		uint32_t oh_prev = 0x80;           // one-hot query base of row jA-1
 		const int n_lanes = (tlen + C - 1) / C;
-		const int n_steps = qlen + 2 * (n_lanes - 1) + 1;
+		int n_steps = act? qlen + 2 * (n_lanes - 1) + 1 : 0;
+		if (NJ == 2) n_steps = max(n_steps, __shfl_xor_sync(full, n_steps, 16));
+		uint8_t *pa = p + sub * CP - (ptrdiff_t)(2 * sub) * W; // traceback row jA of this lane's block A
+		const bool lane_on = t0 < tlen;
 		#pragma unroll 1
-		for (int s = 0; s < n_steps; ++s) {
-			const int jA = s - 2 * lane; // block A row; block B is at jA - 1
-			const uint32_t sv = __shfl_up_sync(full, vl_end, 1), sx = __shfl_up_sync(full, xl_end, 1), sx2 = __shfl_up_sync(full, x2l_end, 1);
-			if (jA >= 0 && jA <= qlen && t0 < tlen) {
-				uint32_t vl, xl, x2l;
-				if (lane == 0) { // left boundary (ksw2_extd2_sse.c:149-158 with st == 0)
-					const int v0 = jA == 0? -q - e : jA < A.long_thres? -e : jA == A.long_thres? A.long_diff : -e2;
-					vl = PK_ENC(v0) | vl_end << 16, xl = PK_ENC(-q - e) | xl_end << 16, x2l = PK_ENC(-q2 - e2) | x2l_end << 16;
-				} else {
-					vl = __byte_perm(sv, vl_end, 0x5432), xl = __byte_perm(sx, xl_end, 0x5432), x2l = __byte_perm(sx2, x2l_end, 0x5432);
-				}
-				const uint32_t oh = jA < qlen? qs[jA] : 0x80;
-				const uint32_t qbm = (oh & 0xf) | (oh_prev & 0xf) << 16;
-				const uint32_t mN = ((oh & 0x80)? 0xffffu : 0u) | ((oh_prev & 0x80)? 0xffff0000u : 0u);
+		for (int s = 0; s < n_steps; ++s, pa += W) {
+			const int jA = s - 2 * sub; // block A row; block B is at jA - 1
+			const uint32_t sv = __shfl_up_sync(full, vl_end, 1, LN), sx = __shfl_up_sync(full, xl_end, 1, LN), sx2 = __shfl_up_sync(full, x2l_end, 1, LN);
+			if (jA >= 0 && jA <= qlen && lane_on) {
+				// left inputs: lo <- right edge of the previous lane's block B (same row), hi <- this lane's block A, previous row;
+				// the group's first lane takes the left boundary instead (ksw2_extd2_sse.c:149-158 with st == 0)
+				uint32_t bv = jA < lt? E_E : E_E2;
+				bv = jA == lt? E_LD : bv;
+				bv = jA == 0? E_QE : bv;
+				const bool first = sub == 0;
+				uint32_t vl = __byte_perm(first? bv : sv >> 16, vl_end, 0x5410);
+				uint32_t xl = __byte_perm(first? E_QE : sx >> 16, xl_end, 0x5410);
+				uint32_t x2l = __byte_perm(first? E_QE2 : sx2 >> 16, x2l_end, 0x5410);
+				const uint32_t oh = qs[jA];
+				const uint32_t ohx = oh | oh_prev << 16;
+				const uint32_t qbm = ohx & 0x000f000fu;
+				const uint32_t mN = (ohx >> 7 & 0x00010001u) * 0xffffu;
 				oh_prev = oh;
-				uint32_t sU[H], sY[H], sY2[H];
-				if (jA == 0) { // block B has no row yet: its column state must survive this step
-					#pragma unroll
-					for (int c = 0; c < H; ++c) sU[c] = U[c], sY[c] = Y[c], sY2[c] = Y2[c];
-				}
 				uint32_t wd[NW * 4], v_first = 0;
 				#pragma unroll
 				for (int c = 0; c < NW * 4; ++c) wd[c] = 0;
@@ -372,12 +383,16 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 					if (c == 0) v_first = vn;
 				}
 				vl_end = vl, xl_end = xl, x2l_end = x2l;
-				if (jA == 0) {
+				if (jA < qlen) hcol_acc += v_first & 0xffffu;
+				if (jA == 0) { // block B has not started: put its column state (hi halves) back to the top boundary
 					#pragma unroll
-					for (int c = 0; c < H; ++c)
-						U[c] = __byte_perm(U[c], sU[c], 0x7610), Y[c] = __byte_perm(Y[c], sY[c], 0x7610), Y2[c] = __byte_perm(Y2[c], sY2[c], 0x7610);
+					for (int c = 0; c < H; ++c) {
+						const int t = t0 + H + c;
+						const uint32_t u0 = t < lt? E_E : t == lt? E_LD : E_E2; // t >= 1 here
+						U[c] = (U[c] & 0xffffu) | u0 << 16, Y[c] = (Y[c] & 0xffffu) | E_QE << 16, Y2[c] = (Y2[c] & 0xffffu) | E_QE2 << 16;
+					}
 				}
-				// score pieces: H(t, qlen-1) = H(t-1, qlen-1) + u(t, qlen-1) along the last row; H(0, j) down column 0
+				// score pieces: H(t, qlen-1) = H(t-1, qlen-1) + u(t, qlen-1) along the last row
 				if (jA == qlen - 1) {
 					#pragma unroll
 					for (int c = 0; c < H; ++c) if (t0 + c >= 1 && t0 + c < tlen) hrow += (int)((U[c] & 0xffffu) >> 7) - 128;
@@ -386,7 +401,6 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 					#pragma unroll
 					for (int c = 0; c < H; ++c) if (t0 + H + c < tlen) hrow += (int)(U[c] >> 23) - 128;
 				}
-				if (lane == 0 && jA < qlen) { const int v0 = (int)((v_first & 0xffffu) >> 7) - 128; hcol0 += jA == 0? v0 - qe : v0; }
 				// traceback bytes: lo bytes of the words -> row jA (block A), byte 2 of the words -> row jA-1 (block B)
 				uint32_t lo[NW], hi[NW];
 				#pragma unroll
@@ -395,14 +409,13 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 					lo[k] = __byte_perm(r01, r23, 0x5410), hi[k] = __byte_perm(r01, r23, 0x7632);
 				}
 				if (jA < qlen) {
-					uint8_t *pa = p + (size_t)jA * W + lane * CP;
 					if (CPH == 1) *pa = (uint8_t)lo[0];
 					else if (CPH == 2) *(uint16_t*)pa = (uint16_t)lo[0];
 					else if (CPH == 4) *(uint32_t*)pa = lo[0];
 					else *(uint2*)pa = make_uint2(lo[0], lo[NW - 1]);
 				}
 				if (jA >= 1) {
-					uint8_t *pb = p + (size_t)(jA - 1) * W + lane * CP + CPH;
+					uint8_t *pb = pa - W + CPH;
 					if (CPH == 1) *pb = (uint8_t)hi[0];
 					else if (CPH == 2) *(uint16_t*)pb = (uint16_t)hi[0];
 					else if (CPH == 4) *(uint32_t*)pb = hi[0];
@@ -410,62 +423,73 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 				}
 			}
 		}
+		// score = H(tlen-1, qlen-1): down column 0 (H(0,0) = v - (q+e), :366), then along the last row
 		int score = hrow;
-		for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(full, score, o);
-		score += __shfl_sync(full, hcol0, 0);
+		#pragma unroll
+		for (int o = LN / 2; o > 0; o >>= 1) score += __shfl_xor_sync(full, score, o);
+		score += (int)(hcol_acc >> 7) - 128 * qlen - qe;
+		score = __shfl_sync(full, score, lead);
 		__syncwarp();
 		// ---- traceback from (tlen-1, qlen-1) (ksw2.h:130-162; no forced states: the band is never clipped) ----
 		// The path is walked run by run instead of cell by cell: in the H state the 32 lanes look down the diagonal, in a gap
 		// state along the row/column, and a ballot finds where the run ends -- the per-cell rule of ksw_backtrack is unchanged.
-		int n = 0, i = tlen - 1, jj = qlen - 1, state = 0;
-		uint32_t run_op = 0, run_len = 0; // pending CIGAR run (lane 0 writes it when the operator changes)
-		#define PK_EMIT(op_, len_) do { const uint32_t o__ = (op_), l__ = (len_); if (l__) { if (run_len && o__ == run_op) run_len += l__; \
-			else { if (run_len && lane == 0) cig[n] = run_len << 4 | run_op; n += run_len? 1 : 0; run_op = o__, run_len = l__; } } } while (0)
-		while (i >= 0 && jj >= 0) {
-			const int di = (state == 0 || state == 1 || state == 3)? 1 : 0, dj = (state == 0 || state == 2 || state == 4)? 1 : 0;
-			const int ci = i - lane * di, cj = jj - lane * dj;
-			const bool inr = ci >= 0 && cj >= 0;
-			uint32_t tmp = 0;
-			if (inr) {
-				const int wi = ci % C;
-				tmp = p[(size_t)cj * W + (ci / C) * CP + (wi < H? wi : CPH + wi - H)] ^ 0x7fu;
+		#pragma unroll 1
+		for (int g = 0; g < NJ; ++g) {
+			const int src = g * LN;
+			if (!__shfl_sync(full, (int)act, src)) continue;
+			const int g_tlen = __shfl_sync(full, tlen, src), g_qlen = __shfl_sync(full, qlen, src), g_jid = __shfl_sync(full, jid, src);
+			const int g_flag = __shfl_sync(full, jflag, src), g_score = __shfl_sync(full, score, src);
+			const uint8_t *gp = A.pws + A.pws_stride * (size_t)(worker0 + g);
+			uint32_t *cig = A.cigws + A.cigws_stride * (size_t)(worker0 + g);
+			int n = 0, i = g_tlen - 1, jj = g_qlen - 1, state = 0;
+			uint32_t run_op = 0, run_len = 0; // pending CIGAR run (lane 0 writes it when the operator changes)
+			#define PK_EMIT(op_, len_) do { const uint32_t o__ = (op_), l__ = (len_); if (l__) { if (run_len && o__ == run_op) run_len += l__; \
+				else { if (run_len && lane == 0) cig[n] = run_len << 4 | run_op; n += run_len? 1 : 0; run_op = o__, run_len = l__; } } } while (0)
+			while (i >= 0 && jj >= 0) {
+				const int di = (state == 0 || state == 1 || state == 3)? 1 : 0, dj = (state == 0 || state == 2 || state == 4)? 1 : 0;
+				const int ci = i - lane * di, cj = jj - lane * dj;
+				const bool inr = ci >= 0 && cj >= 0;
+				uint32_t tmp = 0;
+				if (inr) {
+					const int wi = ci % C;
+					tmp = gp[(size_t)cj * W + (ci / C) * CP + (wi < H? wi : CPH + wi - H)] ^ 0x7fu;
+				}
+				const bool cont = inr && (state == 0? (tmp & 7) == 0 : (tmp >> (state + 2) & 1) != 0);
+				const unsigned stop = __ballot_sync(full, !cont);
+				const int r = stop? __ffs(stop) - 1 : 32;
+				PK_EMIT(state == 0? 0u : di? 2u : 1u, (uint32_t)r);
+				i -= r * di, jj -= r * dj;
+				if (r < 32) {
+					const uint32_t tr = __shfl_sync(full, tmp, r);
+					const bool in_r = __shfl_sync(full, (int)inr, r) != 0;
+					if (!in_r) break;              // ran off the matrix: the leftover is a leading gap (below)
+					if (state == 0) {              // first cell that leaves the diagonal: its own step, in its new state
+						state = tr & 7;
+						if (state == 1 || state == 3) { PK_EMIT(2u, 1u); --i; } else { PK_EMIT(1u, 1u); --jj; }
+					} else state = 0;              // the gap closes here: re-read this cell in the H state
+				}
 			}
-			const bool cont = inr && (state == 0? (tmp & 7) == 0 : (tmp >> (state + 2) & 1) != 0);
-			const unsigned stop = __ballot_sync(full, !cont);
-			const int r = stop? __ffs(stop) - 1 : 32;
-			PK_EMIT(state == 0? 0u : di? 2u : 1u, (uint32_t)r);
-			i -= r * di, jj -= r * dj;
-			if (r < 32) {
-				const uint32_t tr = __shfl_sync(full, tmp, r);
-				const bool in_r = __shfl_sync(full, (int)inr, r) != 0;
-				if (!in_r) break;              // ran off the matrix: the leftover is a leading gap (below)
-				if (state == 0) {              // first cell that leaves the diagonal: its own step, in its new state
-					state = tr & 7;
-					if (state == 1 || state == 3) { PK_EMIT(2u, 1u); --i; } else { PK_EMIT(1u, 1u); --jj; }
-				} else state = 0;              // the gap closes here: re-read this cell in the H state
+			if (i >= 0) PK_EMIT(2u, (uint32_t)(i + 1));
+			if (jj >= 0) PK_EMIT(1u, (uint32_t)(jj + 1));
+			if (run_len) { if (lane == 0) cig[n] = run_len << 4 | run_op; ++n; }
+			#undef PK_EMIT
+			__syncwarp();
+			unsigned long long coff = 0;
+			if (n > 0) {
+				if (lane == 0) coff = atomicAdd(A.cigar_used, (unsigned long long)n);
+				coff = __shfl_sync(full, coff, 0);
+				const bool rev_cigar = (g_flag & MMB_KSW_REV_CIGAR) != 0;
+				if ((long long)(coff + n) <= A.cigar_cap)
+					for (int k = lane; k < n; k += 32) A.cigar[coff + k] = rev_cigar? cig[k] : cig[n - 1 - k];
 			}
+			if (lane == 0) {
+				mmb_ksw_res_t o;
+				o.max = 0, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1, o.mqe = o.mte = KSW_NEG_INF;
+				o.score = g_score, o.n_cigar = n, o.reach_end = 0, o.cigar_off = (uint32_t)coff;
+				A.res[g_jid] = o;
+			}
+			__syncwarp();
 		}
-		if (i >= 0) PK_EMIT(2u, (uint32_t)(i + 1));
-		if (jj >= 0) PK_EMIT(1u, (uint32_t)(jj + 1));
-		if (run_len) { if (lane == 0) cig[n] = run_len << 4 | run_op; ++n; }
-		#undef PK_EMIT
-		__syncwarp();
-		n = __shfl_sync(full, n, 0);
-		unsigned long long coff = 0;
-		if (n > 0) {
-			if (lane == 0) coff = atomicAdd(A.cigar_used, (unsigned long long)n);
-			coff = __shfl_sync(full, coff, 0);
-			const bool rev_cigar = (jb.flag & MMB_KSW_REV_CIGAR) != 0;
-			if ((long long)(coff + n) <= A.cigar_cap)
-				for (int k = lane; k < n; k += 32) A.cigar[coff + k] = rev_cigar? cig[k] : cig[n - 1 - k];
-		}
-		if (lane == 0) {
-			mmb_ksw_res_t o;
-			o.max = 0, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1, o.mqe = o.mte = KSW_NEG_INF;
-			o.score = score, o.n_cigar = n, o.reach_end = 0, o.cigar_off = (uint32_t)coff;
-			A.res[jid] = o;
-		}
-		__syncwarp();
 	}
 	#undef PK_ENC
 	#undef PK2
@@ -525,15 +549,16 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 	const int amax = std::max(std::abs((int)A.mch), std::max(std::abs((int)A.mis), std::abs((int)A.scn)));
 	const bool pk_ok = !no_pk && 2 * std::max(q + e, q2 + e2) + amax + 8 <= 127 && A.mch > 0 && A.mis <= 0 && A.scn <= 0;
 	// column strips: the smallest C with 32*C >= tlen keeps the idle-lane fraction low (C is a template parameter)
-	static const int CW[] = { 2, 4, 6, 7, 8, 9, 10, 12, 14, 16,   2, 4, 6, 8, 10, 12, 14, 16 };
-	static const int CPW[] = { 4, 4, 8, 8, 8, 16, 16, 16, 16, 16,   2, 4, 8, 8, 16, 16, 16, 16 };
-	const int NS = 10, NC = 18; // [0,NS): scalar kernel widths, [NS,NC): packed kernel widths
+	static const int CW[] = { 2, 4, 6, 7, 8, 9, 10, 12, 14, 16,   4, 8, 12, 16,   10, 12, 14, 16 };
+	static const int CPW[] = { 4, 4, 8, 8, 8, 16, 16, 16, 16, 16,   4, 8, 16, 16,   16, 16, 16, 16 };
+	static const int LNW[] = { 32, 32, 32, 32, 32, 32, 32, 32, 32, 32,   16, 16, 16, 16,   32, 32, 32, 32 };
+	const int NS = 10, NC = 18; // [0,NS): scalar kernel widths, [NS,NC): packed kernel widths (16-lane classes, then 32-lane)
 	std::vector<int> v[NC];
 	for (int i : idx) {
 		const bool pk = pk_ok && !(h_jobs[i].flag & MMB_KSW_GENERIC_SC);
 		int k = pk? NS : 0;
 		const int last = pk? NC - 1 : NS - 1;
-		while (k < last && 32 * CW[k] < h_jobs[i].tlen) ++k;
+		while (k < last && LNW[k] * CW[k] < h_jobs[i].tlen) ++k;
 		v[k].push_back(i);
 	}
 	size_t order_off = 0;
@@ -542,16 +567,18 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 		mmb_order_by_cells(v[k], h_jobs);
 		int maxq = 1, maxsum = 2;
 		for (int i : v[k]) maxq = std::max(maxq, h_jobs[i].qlen), maxsum = std::max(maxsum, h_jobs[i].qlen + h_jobs[i].tlen);
-		const int C = CW[k], W = 32 * CPW[k];
-		A.qmax = (maxq + 15) / 16 * 16;
+		const int C = CW[k], W = LNW[k] * CPW[k], NJ = 32 / LNW[k];
+		A.qmax = (maxq + 1 + 15) / 16 * 16;
 		const int threads = 128, nwk = threads / 32;
-		const size_t smem = (size_t)(A.qmax + 1024) * nwk;
+		const size_t smem = k >= NS? (size_t)A.qmax * nwk * NJ : (size_t)(A.qmax + 1024) * nwk;
 		void (*kern)(FastArgs) = nullptr;
-		if (k >= NS) switch (C) {
-		case 2: kern = ksw_pk_kernel<1>; break;   case 4: kern = ksw_pk_kernel<2>; break;
-		case 6: kern = ksw_pk_kernel<3>; break;   case 8: kern = ksw_pk_kernel<4>; break;
-		case 10: kern = ksw_pk_kernel<5>; break;  case 12: kern = ksw_pk_kernel<6>; break;
-		case 14: kern = ksw_pk_kernel<7>; break;  default: kern = ksw_pk_kernel<8>; break;
+		if (k >= NS && NJ == 2) switch (C) {
+		case 4: kern = ksw_pk_kernel<2, 16>; break;   case 8: kern = ksw_pk_kernel<4, 16>; break;
+		case 12: kern = ksw_pk_kernel<6, 16>; break;  default: kern = ksw_pk_kernel<8, 16>; break;
+		}
+		else if (k >= NS) switch (C) {
+		case 10: kern = ksw_pk_kernel<5, 32>; break;  case 12: kern = ksw_pk_kernel<6, 32>; break;
+		case 14: kern = ksw_pk_kernel<7, 32>; break;  default: kern = ksw_pk_kernel<8, 32>; break;
 		}
 		else switch (C) {
 		case 2: kern = ksw_fast_kernel<2>; break;   case 4: kern = ksw_fast_kernel<4>; break;
@@ -564,7 +591,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 		MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, kern, threads, smem));
 		if (cta_per_sm < 1) { fprintf(stderr, "[ERROR] ksw_fast: no occupancy\n"); abort(); }
 		int grid = ctx->n_sm * cta_per_sm;
-		grid = std::max(1, std::min(grid, ((int)v[k].size() + nwk - 1) / nwk));
+		grid = std::max(1, std::min(grid, ((int)v[k].size() + nwk * NJ - 1) / (nwk * NJ)));
 		A.pws_stride = ((size_t)maxq * W + 255) & ~(size_t)255;
 		A.cigws_stride = (size_t)maxsum + 8;
 		int *d_order = d_order_all + order_off; order_off += v[k].size() + 1;
@@ -572,7 +599,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		A.counter = d_order, A.order = d_order + 1, A.n = (int)v[k].size();
 		KswPlan pl;
-		pl.pws_bytes = A.pws_stride * (size_t)grid * nwk, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nwk;
+		pl.pws_bytes = A.pws_stride * (size_t)grid * nwk * NJ, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nwk * NJ;
 		const FastArgs A0 = A;
 		pl.go = [=](uint8_t *pws, uint32_t *cigws) {
 			FastArgs B = A0;

@@ -99,16 +99,18 @@ void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t, in
 	g_pool->run(n, fn);
 }
 
-int g_gpu_slots = getenv("MM_B200_GPU_SLOTS")? std::max(1, atoi(getenv("MM_B200_GPU_SLOTS"))) : 2;
+int g_gpu_slots = getenv("MM_B200_GPU_SLOTS")? std::max(1, atoi(getenv("MM_B200_GPU_SLOTS"))) : 4;
 // FIFO gate bounding how many groups are in a device phase at once: with more groups than slots, the groups fall out of
 // lock-step and one group's host phase overlaps the others' kernels.
 class GpuGate {
 public:
-	void acquire() {
+	// cls 1 (alignment waves) is served before cls 0 (stage 1 of a new group): finishing a group early spreads the host
+	// replay work over the batch instead of piling it up at the end
+	void acquire(int cls) {
 		std::unique_lock<std::mutex> lk(mu_);
-		const uint64_t my = tail_++;
-		cv_.wait(lk, [&]() { return my == head_ && in_ < slots(); });
-		++head_, ++in_;
+		const uint64_t my = tail_[cls]++;
+		cv_.wait(lk, [&]() { return my == head_[cls] && in_ < slots() && (cls == 1 || head_[1] == tail_[1]); });
+		++head_[cls], ++in_;
 		cv_.notify_all();
 	}
 	void release() { std::lock_guard<std::mutex> lk(mu_); --in_; cv_.notify_all(); }
@@ -116,13 +118,13 @@ public:
 private:
 	std::mutex mu_;
 	std::condition_variable cv_;
-	uint64_t head_ = 0, tail_ = 0;
+	uint64_t head_[2] = {0, 0}, tail_[2] = {0, 0};
 	int in_ = 0;
 };
 GpuGate g_gate;
 struct GateHold {
 	bool on;
-	explicit GateHold(bool use) : on(use) { if (on) g_gate.acquire(); }
+	GateHold(bool use, int cls) : on(use) { if (on) g_gate.acquire(cls); }
 	void drop() { if (on) g_gate.release(), on = false; }
 	~GateHold() { drop(); }
 };
@@ -227,13 +229,14 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 
 } // namespace
 
+static double g_batch_t0 = 0;
 static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
 					 int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
 {
 	if (n_reads <= 0) return 0;
 	static const bool timing = getenv("MM_B200_TIMING") != nullptr;
 	double t_last = realtime();
-	auto lap = [&](const char *what) { if (timing) { cudaStreamSynchronize(G.ctx->stream); double t = realtime(); fprintf(stderr, "[timing g%d] %-28s %.1f ms\n", G.ctx->group_id, what, 1e3 * (t - t_last)); t_last = t; } };
+	auto lap = [&](const char *what) { if (timing) { cudaStreamSynchronize(G.ctx->stream); double t = realtime(); fprintf(stderr, "[timing g%d] %-28s %.1f ms  @ %.1f - %.1f\n", G.ctx->group_id, what, 1e3 * (t - t_last), 1e3 * (t_last - g_batch_t0), 1e3 * (t - g_batch_t0)); t_last = t; } };
 	mm_idx_bucket_s *B = mi->B;
 	mmb_ctx_t *ctx = G.ctx;
 	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -261,7 +264,8 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	uint8_t *h_seq = bb.h_seq.as<uint8_t>((size_t)total_bases + 16);
 	parallel_for(n, n_threads, [&](int64_t j, int) { memcpy(h_seq + off[j], rs[live[j]].seq, rs[live[j]].qlen); });
 	lap("host concat");
-	GateHold gate1(G.gated);
+	GateHold gate1(G.gated, 0);
+	lap("gate wait 1");
 	uint8_t *d_seq = bb.seq.as<uint8_t>((size_t)total_bases + 16);
 	int64_t *d_off = bb.off.as<int64_t>((size_t)n + 1);
 	int32_t *d_qlen = bb.qlen.as<int32_t>((size_t)n);
@@ -484,7 +488,8 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				int64_t cap_tot = 0;
 				for (int64_t i = 0; i < n_jobs; ++i) if (!(jobs[i].flag & MMB_JOB_LL)) cap_tot += (jobs[i].qlen + jobs[i].tlen) / 2 + 8;
 				uint32_t *h_cig = bb.h_cig[wave].as<uint32_t>((size_t)cap_tot + 64);
-				GateHold gatew(G.gated);
+				GateHold gatew(G.gated, 1);
+				lap("  gate wait w");
 				std::vector<int64_t> chunk_base; // offset of each chunk's CIGAR block inside h_cig
 				int64_t cig_fill = 0;
 				for (int64_t b = 0; b < n_jobs; b += CH) {
@@ -582,8 +587,9 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
 {
 	if (n_reads <= 0) return 0;
+	g_batch_t0 = realtime();
 	unsupported_check(mi, opt);
-	static int ng_env = getenv("MM_B200_GROUPS")? atoi(getenv("MM_B200_GROUPS")) : 3;
+	static int ng_env = getenv("MM_B200_GROUPS")? atoi(getenv("MM_B200_GROUPS")) : 12;
 	const bool sequential = g_groups_override < 0; // negative override: same groups, run one after another (clean per-kernel timing)
 	const int ng_req = g_groups_override > 0? g_groups_override : g_groups_override < 0? -g_groups_override : ng_env;
 	int NG = ng_req < 1? 1 : ng_req > MAX_GROUPS? MAX_GROUPS : ng_req;

@@ -354,28 +354,104 @@ __global__ void __launch_bounds__(64) sort_exact_kernel(const m128 *a_in, m128 *
 	if (n > 1) mmx_rs_sort(a_out + off, n, stk + stk_off[rd], KeyX128());
 }
 
-// Exact emulation for the reads whose anchors contain equal keys: the sequential American-flag walk is latency-bound, so
-// it runs on a shared-memory copy of (x, original index) -- one warp per read, lane 0 walks, all lanes copy in/out.
-struct KeyIdx { uint64_t x; uint32_t i; };
-struct KeyOfKeyIdx { MM_HD uint64_t operator()(const KeyIdx &v) const { return v.x; } };
-
+// Exact emulation for the reads whose anchors contain equal keys. The American-flag walk of one bucket is sequential, but
+// (1) buckets of one level are independent, so the 32 lanes of a warp each walk a different bucket, level by level;
+// (2) the walk only needs an element's digit and identity, so it permutes 32-bit words (index | digit << 16) in shared
+//     memory instead of 16-byte anchors, with the 64-bit keys kept in a read-only shared array;
+// (3) a bucket whose elements all share the digit is left untouched by the reference's walk, so it is skipped.
+// One warp (= one CTA) per read.
 __global__ void __launch_bounds__(32) sort_exact_smem_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
 															 int cap, int *over_cnt, int *over_list)
 {
 	extern __shared__ __align__(16) uint8_t sm_raw[];
-	KeyIdx *e = (KeyIdx*)sm_raw;
-	int32_t *stk = (int32_t*)(e + cap);
+	const int MAXT = 512;
+	uint64_t *X = (uint64_t*)sm_raw;
+	uint32_t *pd = (uint32_t*)(X + cap);
+	uint16_t *head = (uint16_t*)(pd + cap) + (size_t)threadIdx.x * 512, *tail = head + 256;
+	uint32_t *tasks0 = (uint32_t*)((uint16_t*)(pd + cap) + 32 * 512), *tasks1 = tasks0 + MAXT;
+	__shared__ int s_next;
+	const int lane = threadIdx.x;
 	const int n_list = *cnt_ptr;
 	for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
 		const int rd = list[li];
 		const int64_t off = a_off[rd];
 		const int n = (int)(a_off[rd + 1] - off);
-		if (n > cap) { if (threadIdx.x == 0) over_list[atomicAdd(over_cnt, 1)] = rd; continue; }
-		for (int i = threadIdx.x; i < n; i += 32) e[i].x = a_in[off + i].x, e[i].i = (uint32_t)i;
+		if (n > cap) { if (lane == 0) over_list[atomicAdd(over_cnt, 1)] = rd; continue; }
+		for (int i = lane; i < n; i += 32) X[i] = a_in[off + i].x, pd[i] = (uint32_t)i;
+		if (lane == 0) tasks0[0] = 0u | (uint32_t)n << 16, s_next = 0;
 		__syncwarp();
-		if (threadIdx.x == 0) mmx_rs_sort(e, (int64_t)n, stk, KeyOfKeyIdx());
+		uint32_t *cur = tasks0, *nxt = tasks1;
+		int n_task = 1;
+		if (n <= 64) { // ksort.h:147: plain insertion sort
+			if (lane == 0)
+				for (int i = 1; i < n; ++i)
+					if (X[pd[i]] < X[pd[i - 1]]) {
+						const uint32_t tmp = pd[i]; int j;
+						for (j = i; j > 0 && X[tmp] < X[pd[j - 1]]; --j) pd[j] = pd[j - 1];
+						pd[j] = tmp;
+					}
+			n_task = 0;
+		}
+		for (int shift = 56; n_task > 0; shift = shift > 8? shift - 8 : 0) {
+			for (int t = lane; t < n_task; t += 32) {
+				const int beg = cur[t] & 0xffff, end = cur[t] >> 16;
+				for (int b = 0; b < 256; b += 2) *(uint32_t*)(head + b) = 0;
+				for (int i = beg; i < end; ++i) { // count, and stamp each word with its digit at this level
+					const uint32_t idx = pd[i] & 0xffffu, d = (uint32_t)(X[idx] >> shift) & 0xffu;
+					pd[i] = idx | d << 16;
+					++head[d];
+				}
+				uint32_t run = (uint32_t)beg, mx = 0;
+				for (int b = 0; b < 256; ++b) { const uint32_t c = head[b]; mx = max(mx, c); head[b] = (uint16_t)run; run += c; tail[b] = (uint16_t)run; }
+				if (mx != (uint32_t)(end - beg)) { // permute (ksort.h:126-138)
+					for (int b = 0; b < 256;) {
+						const uint32_t hb = head[b];
+						if (hb != tail[b]) {
+							const uint32_t w = pd[hb];
+							uint32_t l = w >> 16;
+							if (l != (uint32_t)b) {
+								uint32_t tmp = w;
+								do {
+									const uint32_t sw = tmp, hl = head[l];
+									tmp = pd[hl]; pd[hl] = sw; head[l] = (uint16_t)(hl + 1);
+									l = tmp >> 16;
+								} while (l != (uint32_t)b);
+								pd[hb] = tmp;
+							}
+							head[b] = (uint16_t)(hb + 1);
+						} else ++b;
+					}
+				}
+				if (shift) {
+					uint32_t bb = (uint32_t)beg;
+					for (int b = 0; b < 256; ++b) {
+						const uint32_t be = tail[b];
+						if (be - bb > 64) nxt[atomicAdd(&s_next, 1)] = bb | be << 16;
+						else if (be - bb > 1) { // insertion sort on the full key (ksort.h:100-110)
+							for (uint32_t i = bb + 1; i < be; ++i) {
+								const uint32_t wi = pd[i];
+								const uint64_t ki = X[wi & 0xffffu];
+								if (ki < X[pd[i - 1] & 0xffffu]) {
+									uint32_t j;
+									for (j = i; j > bb && ki < X[pd[j - 1] & 0xffffu]; --j) pd[j] = pd[j - 1];
+									pd[j] = wi;
+								}
+							}
+						}
+						bb = be;
+					}
+				}
+			}
+			__syncwarp();
+			n_task = s_next;
+			__syncwarp();
+			if (lane == 0) s_next = 0;
+			uint32_t *sw = cur; cur = nxt; nxt = sw;
+			__syncwarp();
+			if (shift == 0) break;
+		}
 		__syncwarp();
-		for (int i = threadIdx.x; i < n; i += 32) a_out[off + i] = a_in[off + e[i].i];
+		for (int i = lane; i < n; i += 32) a_out[off + i] = a_in[off + (pd[i] & 0xffffu)];
 		__syncwarp();
 	}
 }
@@ -454,11 +530,11 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 																	 d_cls_cnt + N_CLS + 1, d_cls_list + (size_t)(N_CLS + 1) * A.n_reads);
 			++ctx->n_launch;
 		}
-		// exact emulation: reads with equal keys go through the shared-memory walker (cap 12288 anchors: 16 B/entry + stack);
+		// exact emulation: reads with equal keys go through the shared-memory walker (cap 15360 anchors: 12 B/entry + per-lane bucket tables);
 		// whatever does not fit, and the oversize class, falls back to the global-memory walker (one thread per read)
 		{
-			const int cap = 12288;
-			const size_t smem = (size_t)cap * sizeof(KeyIdx) + (size_t)mmx_rs_stack_len(cap) * 4;
+			const int cap = 15360;
+			const size_t smem = (size_t)cap * 12 + 32 * 512 * 2 + 2 * 512 * 4;
 			{ static std::once_flag once; std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(sort_exact_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024)); }); }
 			sort_exact_smem_kernel<<<ctx->n_sm, 32, smem, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)(N_CLS + 1) * A.n_reads, d_cls_cnt + N_CLS + 1,
 																		 cap, d_cls_cnt + N_CLS, d_cls_list + (size_t)N_CLS * A.n_reads);

@@ -12,6 +12,7 @@
 
 #include <stdint.h>
 #include <stddef.h>
+#include "minimap.h" /* mm_idx_t */
 
 #ifdef __cplusplus
 extern "C" {
@@ -107,13 +108,62 @@ typedef struct {
  * (n_v[i] of them). u_out capacity must be >= total anchors/ min_cnt... (pass total anchors to be safe). */
 int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
 						 int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy);
+/* Same layout, but every read goes through mg_lchain_rmq (lchain.c:251-357; the long-join rescue chainer of map.c:283-292).
+ * par: max_dist_x = max_dist, max_dist_inner, bw, max_skip, rmq_size_cap, min_cnt, min_sc, chn_pen_gap, chn_pen_skip. */
+int mmb_chain_rmq_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
+							 int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Index on device + whole-path batch mapping are driven through the minimap.h API (include/minimap.h):
- * mm_idx_* builds/loads the host index and mirrors it into HBM (side table keyed by mm_idx_t*), mm_map_file /
- * mmb_map_batch run the GPU batch scheduler that replaces worker_pipeline/kt_for (map.c:403-691).
+ * mm_idx_* builds/loads the index on the GPU (side table keyed by mm_idx_t*), mm_map_file / mm_map_batch run the GPU
+ * batch scheduler that replaces worker_pipeline/kt_for (map.c:403-691). The entries below are the knobs and hand-off
+ * points around it; none has a counterpart in the reference (single process, CPU threads).
  * --------------------------------------------------------------------------------------------------------- */
-struct mm_idx_s_fwd; /* see minimap.h */
+
+/* scheduler: the batch is cut into `n` groups that run the pipeline concurrently (n < 0: the same |n| groups one after
+ * another -- clean per-kernel timing); at most `slots` groups are inside a device phase at a time. 0 / defaults:
+ * MM_B200_GROUPS (12) and MM_B200_GPU_SLOTS (4). */
+void mmb_set_groups(int n);
+void mmb_set_gpu_slots(int slots);
+/* benchmark aid: when on, a batch whose first read pointer / count / bases equal the previous batch's of the same group
+ * reuses the reads already in HBM (no H2D, no re-encode): the "inputs resident" timing of bench.py. */
+void mmb_set_resident_reads(int on);
+
+/* process-wide variants of the per-context counters above (sum over the default context and every scheduler group) */
+void *mmb_default_ctx_c(void);
+void mmb_profile_enable_all(int on);
+double mmb_profile_ms_all(int which, int reset);
+uint64_t mmb_profile_units_all(int which, int reset);
+uint64_t mmb_profile_bytes_all(int which, int reset);   /* algorithmic bytes per kernel family */
+uint64_t mmb_profile_scopes_all(int which, int reset);  /* timed launch groups per family */
+uint64_t mmb_profile_bytes(mmb_ctx_t *ctx, int which, int reset);
+uint64_t mmb_profile_scopes(mmb_ctx_t *ctx, int which, int reset);
+uint64_t mmb_launch_count_all(int reset);
+uint64_t mmb_last_d2h_bytes(void);                      /* device->host bytes of the last mm_map_batch call */
+uint64_t mmb_last_d2h_bytes_all(void);
+void mmb_free(void *p);                                 /* free() for buffers handed out by this library */
+
+/* one-process-per-GPU replication of the device index (index.c has no counterpart): rank 0 exports the device
+ * arrays, the caller broadcasts them (NCCL) into its own device buffers and adopts them as an mm_idx_t on each rank.
+ * ptr/bytes order: hash table, positions, 4-bit sequence, sequence offsets, sequence lengths. */
+typedef struct {
+	void *ptr[5];
+	uint64_t bytes[5];
+	int64_t n_keys, n_pos;
+	int32_t tab_bits, w, k, b, flag;
+	uint32_t n_seq;
+	uint64_t sum_len;
+} mmb_idx_desc_t;
+void mmb_idx_export(const mm_idx_t *mi, mmb_idx_desc_t *d);
+mm_idx_t *mmb_idx_adopt(const mmb_idx_desc_t *d, const char **names, const uint32_t *lens, const uint32_t *cnt_sorted_dev);
+const void *mmb_idx_cnt_sorted(const mm_idx_t *mi, uint64_t *bytes); /* sorted occurrence counts (mm_idx_cal_max_occ, index.c:158) */
+
+/* synthetic workload for bench.py (BASELINE.json configs[1] shape; there is no network for real genomes): a random
+ * genome of total_len bases in n_contigs contigs indexed on the device, and reads sampled from it with the given
+ * error profile (err = per-base error rate, split into substitutions / insertions / deletions by sub, ins, 1-sub-ins). */
+mm_idx_t *mmb_synth_index(uint64_t total_len, int n_contigs, uint64_t seed, int w, int k, int bucket_bits);
+int mmb_synth_reads(const mm_idx_t *mi, int n_reads, int read_len, uint64_t seed, float err, float sub, float ins, char *out);
+int mmb_idx_write_fasta(const mm_idx_t *mi, const char *fn); /* dump the indexed sequences (to feed the reference arm) */
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,8 @@ def lib():
                                             C.c_void_p, C.c_int64, C.c_void_p]
         L.mmb_chain_batch_host.restype = C.c_int
         L.mmb_chain_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mmb_chain_rmq_batch_host.restype = C.c_int
+        L.mmb_chain_rmq_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 

@@ -409,3 +409,50 @@ void mmb_chain_rescue_device(mmb_ctx_t *ctx, const RescuePar *rp, int n_reads, c
 	MMB_CUDA_CHECK(cudaGetLastError());
 	++ctx->n_launch;
 }
+
+// Kernel-level entry for mg_lchain_rmq alone (lchain.c:251-357), HOST buffers: every read is re-chained by the rescue kernel
+// regardless of the mapper's rescue condition (map.c:283-292). Used by the parity tests against the reference function.
+// par: max_dist_x = max_dist, max_dist_inner, bw, max_skip, rmq_size_cap, min_cnt, min_sc, chn_pen_gap, chn_pen_skip.
+extern "C" int mmb_chain_rmq_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
+										int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy)
+{
+	if (n_reads <= 0) return 0;
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	const int64_t n_tot = a_off[n_reads];
+	m128 *d_a = ctx->d_a.as<m128>((size_t)n_tot + 1);
+	int64_t *d_off = ctx->d_b.as<int64_t>((size_t)n_reads * 2 + 2), *d_toff = d_off + n_reads + 1;
+	int32_t *d_nu = ctx->d_c.as<int32_t>((size_t)n_reads * 3 + 3), *d_nv = d_nu + n_reads, *d_qlen = d_nv + n_reads;
+	uint64_t *d_u = ctx->d_d.as<uint64_t>((size_t)n_tot + 1);
+	m128 *d_ao = ctx->d_e.as<m128>((size_t)n_tot + 1);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_a, anchors_xy, sizeof(m128) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_off, a_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
+	mmb_chain_par_t dp = *par;
+	dp.use_rmq = 0;
+	mmb_chain_device(ctx, &dp, n_reads, d_a, d_off, n_tot, d_nu, d_nv, d_u, d_ao, ctx->d_f, ctx->d_g); // sets up the scratch the rescue kernel reuses
+	// pretend every read came out of the DP as two chains over all of its anchors, so that the kernel re-chains it
+	std::vector<int32_t> h_nu(n_reads), h_nv(n_reads), h_q(n_reads, INT32_MAX);
+	std::vector<uint64_t> h_u((size_t)n_tot + 1, 0);
+	for (int i = 0; i < n_reads; ++i) {
+		const int64_t n = a_off[i + 1] - a_off[i];
+		h_nv[i] = (int32_t)n, h_nu[i] = n > 0? 2 : 0;
+		if (n > 0) h_u[a_off[i]] = 1;
+	}
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_nu, h_nu.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_nv, h_nv.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_qlen, h_q.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_u, h_u.data(), sizeof(uint64_t) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_ao, anchors_xy, sizeof(m128) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_toff, a_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
+	RescuePar rp;
+	rp.qlen = d_qlen, rp.rescue_size = 0, rp.rescue_ratio = 0.0f;
+	rp.max_dist = par->max_dist_x, rp.max_dist_inner = par->max_dist_inner, rp.bw = par->bw, rp.max_skip = par->max_skip;
+	rp.rmq_size_cap = par->rmq_size_cap, rp.min_cnt = par->min_cnt, rp.min_sc = par->min_sc;
+	rp.pen_gap = par->chn_pen_gap, rp.pen_skip = par->chn_pen_skip, rp.tree = nullptr, rp.tree_off = d_toff;
+	mmb_chain_rescue_device(ctx, &rp, n_reads, d_off, n_tot, d_nu, d_nv, d_u, d_ao, ctx->d_f, ctx->d_g, ctx->d_h, n_tot);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(n_u, d_nu, sizeof(int32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(n_v, d_nv, sizeof(int32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(u_out, d_u, sizeof(uint64_t) * n_tot, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(a_out_xy, d_ao, sizeof(m128) * n_tot, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}

@@ -657,14 +657,6 @@ extern "C" int64_t mm_idx_spsc_get(const mm_idx_t *, int32_t, int64_t st0, int64
 // Multi-GPU: the device index is replicated, not sharded (reads shard). Rank 0 exports the device arrays,
 // torch.distributed (NCCL over NVLink) broadcasts them into buffers on the other ranks, which adopt them here.
 // ---------------------------------------------------------------------------------------------------------
-struct mmb_idx_desc_t {           // plain C view of the device index (include/mm_b200.h)
-	void *ptr[5];                 // tab, pos, S, seq_off, seq_len, cnt_sorted is rebuilt on import
-	uint64_t bytes[5];
-	int64_t n_keys, n_pos;
-	int32_t tab_bits, w, k, b, flag;
-	uint32_t n_seq;
-	uint64_t sum_len;
-};
 
 extern "C" void mmb_idx_export(const mm_idx_t *mi, mmb_idx_desc_t *d)
 {

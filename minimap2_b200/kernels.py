@@ -81,3 +81,23 @@ def chain_batch(ctx, anchor_arrays, max_dist_x, max_dist_y, bw, max_skip, max_it
         o = int(off[i])
         out.append((u[o:o + n_u[i]].copy(), ao[o:o + n_v[i]].copy()))
     return out
+
+
+def chain_rmq_batch(ctx, anchor_arrays, max_dist, max_dist_inner, bw, max_skip, cap, min_cnt, min_sc, pen_gap, pen_skip=0.0):
+    """mg_lchain_rmq on every read (anchors sorted by x). Returns list of (u, a)."""
+    n = len(anchor_arrays)
+    off = np.zeros(n + 1, dtype=np.int64)
+    for i, a in enumerate(anchor_arrays):
+        off[i + 1] = off[i] + len(a)
+    tot = int(off[-1])
+    cat = np.concatenate([np.asarray(a, dtype=np.uint64).reshape(-1, 2) for a in anchor_arrays]) if tot else np.zeros((0, 2), dtype=np.uint64)
+    cat = np.ascontiguousarray(cat)
+    par = ChainPar(max_dist, max_dist, bw, max_skip, 5000, min_cnt, min_sc, pen_gap, pen_skip, 0, 1, 1, max_dist_inner, cap)
+    n_u = np.zeros(n, dtype=np.int32); n_v = np.zeros(n, dtype=np.int32)
+    u = np.zeros(tot + 1, dtype=np.uint64); ao = np.zeros((tot + 1, 2), dtype=np.uint64)
+    lib().mmb_chain_rmq_batch_host(ctx.h, C.byref(par), n, cat.ctypes.data, off.ctypes.data, n_u.ctypes.data, n_v.ctypes.data, u.ctypes.data, ao.ctypes.data)
+    out = []
+    for i in range(n):
+        o = int(off[i])
+        out.append((u[o:o + n_u[i]].copy(), ao[o:o + n_v[i]].copy()))
+    return out

@@ -1,0 +1,69 @@
+"""CPU: the plain-C oracle (oracle/mm2o_*.c) against the committed known-answer vectors that tests/golden/make_golden.py took
+from the unmodified reference (mm_sketch, radix_sort_128x, mg_lchain_dp, ksw_extd2_sse, ksw_ll_i16). This pins the oracle
+without needing /root/reference or oracle/_ref at test time."""
+import os
+import numpy as np
+import pytest
+import oracle_lib as O
+
+VEC = os.path.join(O.ROOT, "tests", "golden", "vectors.npz")
+pytestmark = pytest.mark.skipif(not os.path.exists(VEC), reason="golden vectors missing")
+
+
+@pytest.fixture(scope="module")
+def V():
+    return np.load(VEC)
+
+
+def test_oracle_sketch_matches_golden(V):
+    nc, ns = V["sk_n"]
+    for ci in range(nc):
+        for si in range(ns):
+            w, k, hpc, rid = [int(x) for x in V["sk%d_%d_par" % (ci, si)]]
+            got = O.oracle_sketch(V["sk%d_%d_seq" % (ci, si)].tobytes(), w, k, rid=rid, is_hpc=hpc)
+            exp = V["sk%d_%d_out" % (ci, si)]
+            assert got.shape == exp.shape and (got == exp).all(), (ci, si)
+
+
+def test_oracle_radix_sort_matches_golden(V):
+    for i in range(int(V["rs_n"][0])):
+        got = O.oracle_sort128(V["rs%d_in" % i])
+        assert (got == V["rs%d_out" % i]).all(), i
+
+
+def test_oracle_lchain_dp_matches_golden(V):
+    for i in range(int(V["ch_n"][0])):
+        par = [int(x) for x in V["ch%d_par" % i]]
+        pg, ps = [float(x) for x in V["ch%d_pen" % i]]
+        u, b = O.oracle_lchain_dp(V["ch%d_a" % i], *par, pg, ps)
+        assert len(u) == len(V["ch%d_u" % i]) and (u == V["ch%d_u" % i]).all(), i
+        assert b.shape == V["ch%d_b" % i].shape and (b == V["ch%d_b" % i]).all(), i
+
+
+KEYS = ["max", "zdropped", "max_q", "max_t", "mqe", "mqe_t", "mte", "mte_q", "score", "reach_end"]
+
+
+def test_oracle_extd2_matches_golden(V):
+    mat = V["kw_mat"]
+    for i in range(int(V["kw_n"][0])):
+        w, zdrop, end_bonus, flag = [int(x) for x in V["kw%d_par" % i]]
+        r = O.oracle_extd2(V["kw%d_q" % i], V["kw%d_t" % i], mat, 4, 2, 24, 1, w, zdrop, end_bonus, flag)
+        exp = V["kw%d_res" % i]
+        if flag & 0x08:   # KSW_EZ_APPROX_MAX: the reference leaves ez->max/max_q/max_t at their reset values
+            pass
+        for k, e in zip(KEYS, exp):
+            assert r[k] == int(e), (i, k, r[k], int(e), flag)
+        assert r["cigar"] == [int(x) for x in V["kw%d_cig" % i]], i
+
+
+def test_oracle_ll_i16_matches_golden(V):
+    mat = V["kw_mat"]
+    for i in range(int(V["ll_n"][0])):
+        sc, qe, te = O.oracle_ll_i16(V["ll%d_q" % i], V["ll%d_t" % i], mat, 4, 2)
+        assert [sc, qe, te] == [int(x) for x in V["ll%d_res" % i]], i
+
+
+def test_expected_outputs_present():
+    exp = os.path.join(O.ROOT, "tests", "golden", "expected")
+    names = sorted(os.listdir(exp))
+    assert "mt_sam.txt" in names and "ont_paf_cs.txt" in names and len(names) >= 10

@@ -50,6 +50,7 @@ uint64_t mmb_profile_units(mmb_ctx_t *ctx, int which, int reset); /* algorithmic
 /* job-level addressing flags (how the kernel walks the resident sequences) */
 #define MMB_JOB_Q_COMP       0x10000 /* complement query bases (3-c, N stays 4): reverse strand (align.c:1056-1061) */
 #define MMB_JOB_LL           0x20000 /* run ksw_ll_i16 (local score) instead of extd2 */
+#define MMB_JOB_ZDROP        0x40000 /* also run mm_test_zdrop's scan over the resulting CIGAR (align.c:61-89); see zd_* below */
 
 typedef struct {
 	int64_t q_start;   /* index of the first query base of this job in the query byte array (nt4 codes, 1 B/base) */
@@ -69,6 +70,10 @@ typedef struct {      /* ksw_extz_t (ksw2.h:34-43) without the pointer */
 	int32_t score;
 	int32_t n_cigar, reach_end;
 	uint32_t cigar_off; /* offset (in uint32 ops) of this job's CIGAR in the batch cigar buffer */
+	/* MMB_JOB_ZDROP: max_zdrop and pos[0][0], pos[0][1], pos[1][0], pos[1][1] of mm_test_zdrop (align.c:61-89), i.e. the
+	 * largest score drop along the alignment path and where it starts/ends on target and query. zd_max = -1: not evaluated
+	 * by the kernel that ran the job (the caller scans the CIGAR itself). */
+	int32_t zd_max, zd_t0, zd_t1, zd_q0, zd_q1;
 } mmb_ksw_res_t;
 
 typedef struct {      /* scoring: what align.c:655 ksw_gen_ts_mat + mm_mapopt_t a,b,q,e,q2,e2 give */

@@ -19,7 +19,8 @@ class KswJob(C.Structure):  # mmb_ksw_job_t (include/mm_b200.h)
 class KswRes(C.Structure):  # mmb_ksw_res_t
     _fields_ = [("max", C.c_int32), ("zdropped", C.c_int32), ("max_q", C.c_int32), ("max_t", C.c_int32),
                 ("mqe", C.c_int32), ("mqe_t", C.c_int32), ("mte", C.c_int32), ("mte_q", C.c_int32),
-                ("score", C.c_int32), ("n_cigar", C.c_int32), ("reach_end", C.c_int32), ("cigar_off", C.c_uint32)]
+                ("score", C.c_int32), ("n_cigar", C.c_int32), ("reach_end", C.c_int32), ("cigar_off", C.c_uint32),
+                ("zd_max", C.c_int32), ("zd_t0", C.c_int32), ("zd_t1", C.c_int32), ("zd_q0", C.c_int32), ("zd_q1", C.c_int32)]
 
 
 class KswScore(C.Structure):  # mmb_ksw_score_t

@@ -19,6 +19,7 @@ namespace {
 struct Ez {
 	int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end;
 	const uint32_t *cigar;
+	int zd_max, zd_pos[2][2]; // mm_test_zdrop's scan evaluated by the kernel (MMB_JOB_ZDROP); zd_max < 0: not available
 };
 
 inline void ez_reset(Ez *ez) // ksw2.h:164-169
@@ -26,6 +27,7 @@ inline void ez_reset(Ez *ez) // ksw2.h:164-169
 	ez->max_q = ez->max_t = ez->mqe_t = ez->mte_q = -1;
 	ez->max = 0, ez->score = ez->mqe = ez->mte = KSW_NEG_INF_H;
 	ez->n_cigar = 0, ez->zdropped = 0, ez->reach_end = 0, ez->cigar = 0;
+	ez->zd_max = -1;
 }
 
 struct Seg { // a piece of the query (on strand `rev`, strand coordinates) and of the target
@@ -80,6 +82,7 @@ struct Driver {
 
 	// cache lookup; on a miss the job is queued for the GPU and false is returned
 	bool fetch(const KswKey &k, Ez *ez) {
+		HpScope hp_(HP_FETCH);
 		int slot = ra.find(k);
 		if (slot >= 0 && ra.done_idx[slot] >= 0) {
 			const KswDone &d = ra.done[ra.done_idx[slot]];
@@ -87,6 +90,7 @@ struct Driver {
 			ez->mqe = d.r.mqe, ez->mqe_t = d.r.mqe_t, ez->mte = d.r.mte, ez->mte_q = d.r.mte_q;
 			ez->score = d.r.score, ez->n_cigar = d.r.n_cigar, ez->reach_end = d.r.reach_end;
 			ez->cigar = d.cig;
+			ez->zd_max = d.r.zd_max, ez->zd_pos[0][0] = d.r.zd_t0, ez->zd_pos[0][1] = d.r.zd_t1, ez->zd_pos[1][0] = d.r.zd_q0, ez->zd_pos[1][1] = d.r.zd_q1;
 			return true;
 		}
 		if (slot < 0) {
@@ -122,6 +126,7 @@ struct Driver {
 
 	const uint8_t *qptr(int rev, int qs) const { return ra.qseq[rev] + qs; }
 	void get_tseq(uint32_t rid, int st, int en, std::vector<uint8_t> &buf) const {
+		HpScope hp_(HP_TSEQ);
 		buf.resize(en > st? en - st : 0);
 		if (en > st) mm_idx_getseq(mi, rid, st, en, buf.data());
 	}
@@ -138,10 +143,15 @@ struct Driver {
 	}
 
 	// align.c:61-103. Returns 0/1/2, or -1 if the inversion probe (ksw_ll_i16) is still pending on the GPU.
-	int test_zdrop(const Seg &s, const uint8_t *qseq, const uint8_t *tseq, uint32_t n_cigar, const uint32_t *cigar) {
+	// zd: the scan's result when the kernel already evaluated it (max_zdrop, pos), else null and the CIGAR is scanned here
+	int test_zdrop(const Seg &s, const uint8_t *qseq, const uint8_t *tseq, uint32_t n_cigar, const uint32_t *cigar, const Ez *zd) {
+		HpScope hp_(HP_ZDROP);
 		int32_t score = 0, max = INT32_MIN, max_i = -1, max_j = -1, i = 0, j = 0, max_zdrop = 0;
 		int pos[2][2] = {{-1, -1}, {-1, -1}}, q_len, t_len;
-		for (uint32_t k = 0; k < n_cigar; ++k) {
+		if (zd) {
+			max_zdrop = zd->zd_max;
+			pos[0][0] = zd->zd_pos[0][0], pos[0][1] = zd->zd_pos[0][1], pos[1][0] = zd->zd_pos[1][0], pos[1][1] = zd->zd_pos[1][1];
+		} else for (uint32_t k = 0; k < n_cigar; ++k) {
 			uint32_t op = cigar[k] & 0xf, len = cigar[k] >> 4;
 			if (op == MM_CIGAR_MATCH) {
 				for (uint32_t l = 0; l < len; ++l) {
@@ -184,6 +194,7 @@ struct Driver {
 		}
 	}
 	static void append_cigar(mm_reg1_t *r, uint32_t n_cigar, const uint32_t *cigar) {
+		HpScope hp_(HP_APPEND);
 		if (n_cigar == 0) return;
 		enlarge_cigar(r, n_cigar);
 		mm_extra_t *p = r->p;
@@ -306,38 +317,61 @@ struct Driver {
 	}
 
 	void update_extra(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, int8_t q, int8_t e, int is_eqx, int log_gap) { // align.c:254-303
+		HpScope hp_(HP_EXTRA);
 		int32_t qshift, tshift, toff = 0, qoff = 0;
 		double s = 0.0, max = 0.0;
 		mm_extra_t *p = r->p;
 		if (p == 0) return;
 		fix_cigar(r, qseq, tseq, &qshift, &tshift);
 		qseq += qshift, tseq += tshift;
-		r->blen = r->mlen = 0, r->is_spliced = 0;
-		for (uint32_t k = 0; k < p->n_cigar; ++k) {
-			uint32_t op = p->cigar[k] & 0xf, len = p->cigar[k] >> 4;
-			if (op == MM_CIGAR_MATCH) {
-				int n_ambi = 0, n_diff = 0;
-				for (uint32_t l = 0; l < len; ++l) {
-					int cq = qseq[qoff + l], ct = tseq[toff + l];
-					if (ct > 3 || cq > 3) ++n_ambi;
-					else if (ct != cq) ++n_diff;
-					s += mat[ct * 5 + cq];
-					if (s < 0) s = 0;
-					else max = max > s? max : s;
-				}
-				r->blen += len - n_ambi, r->mlen += len - (n_ambi + n_diff), p->n_ambi += n_ambi;
-				toff += len, qoff += len;
-			} else if (op == MM_CIGAR_INS || op == MM_CIGAR_DEL) {
-				int n_ambi = 0;
-				const uint8_t *sq = op == MM_CIGAR_INS? qseq + qoff : tseq + toff;
-				for (uint32_t l = 0; l < len; ++l) if (sq[l] > 3) ++n_ambi;
-				r->blen += len - n_ambi, p->n_ambi += n_ambi;
-				if (log_gap) s -= q + (double)e * mmx_log2(1.0 + len);
-				else s -= q + e;
-				if (s < 0) s = 0;
-				if (op == MM_CIGAR_INS) qoff += len; else toff += len;
-			} else if (op == MM_CIGAR_N_SKIP) r->is_spliced = 1, toff += len;
+		// The running score s of align.c:266-297 is a sum of integers (matrix entries, q) and of e * mg_log2(1+len) terms whose
+		// float mantissa keeps them multiples of 2^-32 in any realistic range, so the reference's double arithmetic is exact
+		// and a 2^-32 fixed-point integer reproduces it; the double loop below remains as the fallback when a gap penalty is
+		// not representable.
+		bool fixed_ok = true;
+		{
+			int64_t matfx[25];
+			for (int i = 0; i < 25; ++i) matfx[i] = (int64_t)mat[i] << 32;
+			int64_t sfx = 0, maxfx = 0;
+			int32_t blen = 0, mlen = 0, n_ambi_tot = 0, is_spliced = 0;
+			toff = qoff = 0;
+			for (uint32_t k = 0; k < p->n_cigar && fixed_ok; ++k) {
+				uint32_t op = p->cigar[k] & 0xf, len = p->cigar[k] >> 4;
+				if (op == MM_CIGAR_MATCH) {
+					int n_ambi = 0, n_diff = 0;
+					const uint8_t *pq = qseq + qoff, *pt = tseq + toff;
+					for (uint32_t l = 0; l < len; ++l) {
+						const int cq = pq[l], ct = pt[l];
+						const int amb = (ct | cq) > 3;
+						n_ambi += amb, n_diff += (ct != cq) & !amb;
+						sfx += matfx[ct * 5 + cq];
+						if (sfx < 0) sfx = 0;
+						else maxfx = maxfx > sfx? maxfx : sfx;
+					}
+					blen += len - n_ambi, mlen += len - (n_ambi + n_diff), n_ambi_tot += n_ambi;
+					toff += len, qoff += len;
+				} else if (op == MM_CIGAR_INS || op == MM_CIGAR_DEL) {
+					int n_ambi = 0;
+					const uint8_t *sq = op == MM_CIGAR_INS? qseq + qoff : tseq + toff;
+					for (uint32_t l = 0; l < len; ++l) if (sq[l] > 3) ++n_ambi;
+					blen += len - n_ambi, n_ambi_tot += n_ambi;
+					const double pen = log_gap? q + (double)e * mmx_log2(1.0 + len) : (double)(q + e);
+					const double scaled = pen * 4294967296.0;
+					const int64_t pfx = (int64_t)scaled;
+					if ((double)pfx != scaled || pen > 1e6 || pen < -1e6) { fixed_ok = false; break; }
+					sfx -= pfx;
+					if (sfx < 0) sfx = 0;
+					if (op == MM_CIGAR_INS) qoff += len; else toff += len;
+				} else if (op == MM_CIGAR_N_SKIP) is_spliced = 1, toff += len;
+			}
+			if (fixed_ok) {
+				r->blen = blen, r->mlen = mlen, r->is_spliced = is_spliced, p->n_ambi += n_ambi_tot;
+				max = (double)maxfx / 4294967296.0;
+			}
 		}
+		if (!fixed_ok) {
+		toff = qoff = 0, s = 0.0, max = 0.0;
+		r->blen = r->mlen = 0, r->is_spliced = 0;		}
 		p->dp_max = p->dp_max0 = (int32_t)(max + .499);
 		assert(qoff == r->qe - r->qs && toff == r->re - r->rs);
 		if (is_eqx) update_cigar_eqx(r, qseq, tseq);
@@ -565,11 +599,12 @@ struct Driver {
 				int j, bw1 = bw_long, zdrop_code;
 				if (a[as1 + i].y & MMX_SEED_LONG_JOIN) bw1 = qe - qs > re - rs? qe - qs : re - rs;
 				Seg s; s.rev = rev, s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0;
-				bool ok = align_pair(s, bw1, -1, opt->zdrop, MMB_KSW_APPROX_MAX, &ez); // first pass
+				bool ok = align_pair(s, bw1, -1, opt->zdrop, MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez); // first pass
 				if (ok) { // results that are available are consumed even if an earlier call is pending: this surfaces second-pass jobs one wave earlier
 					const uint8_t *qseq = qptr(rev, qs);
-					get_tseq(rid, rs, re, tseq);
-					zdrop_code = test_zdrop(s, qseq, tseq.data(), ez.n_cigar, ez.cigar);
+					const bool have_zd = ez.zd_max >= 0 && !ez.zdropped;
+					if (!have_zd) get_tseq(rid, rs, re, tseq);
+					zdrop_code = test_zdrop(s, qseq, tseq.data(), ez.n_cigar, ez.cigar, have_zd? &ez : nullptr);
 					if (zdrop_code > 0) ok = align_pair(s, bw1, -1, zdrop_code == 2? opt->zdrop_inv : opt->zdrop, 0, &ez); // second pass
 					else if (zdrop_code < 0) ok = false;
 					if (ok) {
@@ -680,8 +715,26 @@ inline mm_reg1_t *insert_reg(const mm_reg1_t *r, int i, int *n_regs, mm_reg1_t *
 
 } // namespace
 
+uint64_t g_hp[HP_N] = {0};
+thread_local uint64_t tl_hp[HP_N] = {0};
+void hl_hp_flush()
+{
+	if (!g_hp_on) return;
+	for (int i = 0; i < HP_N; ++i) if (tl_hp[i]) { __atomic_fetch_add(&g_hp[i], tl_hp[i], __ATOMIC_RELAXED); tl_hp[i] = 0; }
+}
+bool g_hp_on = getenv("MM_B200_TIMING") != nullptr;
+void hl_hp_dump(const char *tag)
+{
+	if (!g_hp_on) return;
+	static const char *nm[HP_N] = { "skeleton", "tseq", "zdrop", "extra", "fetch", "append", "pre", "post", "hits" };
+	fprintf(stderr, "[hostprof %s]", tag);
+	for (int i = 0; i < HP_N; ++i) fprintf(stderr, " %s=%.1fms", nm[i], (double)__atomic_exchange_n(&g_hp[i], 0, __ATOMIC_RELAXED) / 2.0e6); // ~2 GHz TSC
+	fprintf(stderr, "\n");
+}
+
 mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAlign &ra, int *n_regs_, mm_reg1_t *regs, int n_a_in, m128 *a)
 {
+	HpScope hp_(HP_SKEL);
 	int32_t n_regs = *n_regs_, n_a;
 	Driver D(opt, mi, ra);
 	ra.incomplete = false;

@@ -120,16 +120,38 @@ __global__ void __launch_bounds__(128) chain_fill_kernel(ChainArgs A)
 	const float pen_gap = P.chn_pen_gap, pen_skip = P.chn_pen_skip;
 	if (max_dist_x < bw) max_dist_x = bw;
 	if (max_dist_y < bw && !is_cdna) max_dist_y = bw;
-	for (int32_t i = lane; i < n; i += 32) t[i] = 0;
-	__syncwarp();
-	int32_t st = 0, best_prev = -1;
-	for (int32_t i = 0; i < n; ++i) {
-		const m128 ai = a[i];
-		while (st < i) { // advance st (warp-uniform scalar loop; short)
-			const m128 as = a[st];
-			if (ai.x >> 32 != as.x >> 32 || ai.x > as.x + (uint64_t)(int64_t)max_dist_x) ++st; else break;
+	// Pass 1 (all lanes, one anchor each): the start of anchor i's predecessor window has a closed form -- st is monotone
+	// in i in the reference (lchain.c:170-172), so st_i = max(lower_bound(x_i - max_dist_x within the same strand/contig),
+	// i - max_iter) -- found by binary search. An anchor with an empty window (st_i == i: the bulk of the seed hits, which
+	// are isolated) gets f = span, p = -1 and leaves max_ii = i behind, whatever came before; only the others need the
+	// sequential DP below. Their indices are compacted in order into `lst`.
+	int32_t *stv = (int32_t*)(A.z + off), *lst = (int32_t*)(A.b + off);
+	int32_t n_lst = 0;
+	for (int32_t i0 = 0; i0 < n; i0 += 32) {
+		const int32_t i = i0 + lane;
+		bool nontriv = false;
+		if (i < n) {
+			const m128 ai = a[i];
+			const uint64_t base = ai.x >> 32 << 32;
+			const uint64_t lo = ai.x - base > (uint64_t)(int64_t)max_dist_x? ai.x - (uint64_t)(int64_t)max_dist_x : base;
+			int32_t l = 0, h = i; // first j in [0, i] with a[j].x >= lo
+			while (l < h) { const int32_t m = (l + h) >> 1; if (a[m].x < lo) l = m + 1; else h = m; }
+			if (i - l > max_iter) l = i - max_iter;
+			stv[i] = l, t[i] = 0;
+			nontriv = l < i;
+			if (!nontriv) { const int32_t sp = (int32_t)(ai.y >> 32 & 0xff); f[i] = sp, p[i] = -1, v[i] = sp; }
 		}
-		if (i - st > max_iter) st = i - max_iter;
+		const unsigned m = __ballot_sync(full, nontriv);
+		if (nontriv) lst[n_lst + __popc(m & ((1u << lane) - 1))] = i;
+		n_lst += __popc(m);
+	}
+	__syncwarp();
+	int32_t best_prev = -1;
+	for (int32_t li = 0; li < n_lst; ++li) {
+		const int32_t i = lst[li];
+		const m128 ai = a[i];
+		const int32_t st = stv[i];
+		if (stv[i - 1] == i - 1) best_prev = i - 1; // the previous anchor was skipped: it reset max_ii to itself
 		int32_t max_f = (int32_t)(ai.y >> 32 & 0xff), max_j = -1, n_skip = 0, end_j = st - 1;
 		bool brk = false;
 		for (int32_t j_hi = i - 1; j_hi >= st && !brk; j_hi -= 32) {

@@ -71,6 +71,19 @@ struct ReadAlign {          // per-read alignment working set (lives across wave
 // a[] must have its IGNORE/LONG_JOIN marks cleared by the caller before every replay.
 mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAlign &ra, int *n_regs_, mm_reg1_t *regs, int n_a, m128 *a);
 
+// ---- host section profiler (MM_B200_TIMING only): cycles per section, summed over threads ----
+enum { HP_SKEL, HP_TSEQ, HP_ZDROP, HP_EXTRA, HP_FETCH, HP_APPEND, HP_PRE, HP_POST, HP_HITS, HP_N };
+extern uint64_t g_hp[HP_N];
+extern bool g_hp_on;
+extern thread_local uint64_t tl_hp[HP_N];
+struct HpScope { // accumulates in thread-local counters; hl_hp_flush() adds them to the global sums (once per read)
+	int k; uint64_t t0;
+	explicit HpScope(int k_) : k(k_), t0(g_hp_on? __builtin_ia32_rdtsc() : 0) {}
+	~HpScope() { if (g_hp_on) tl_hp[k] += __builtin_ia32_rdtsc() - t0; }
+};
+void hl_hp_flush();
+void hl_hp_dump(const char *tag);
+
 // ---- format.cc ----
 struct hl_str { std::string s; };
 void hl_set_seq_for_tags(const char *seq);

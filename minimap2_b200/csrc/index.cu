@@ -7,6 +7,7 @@
 // open-addressing table is filled with atomicCAS. Occurrence lists come out ordered by position inside a key, the
 // order the reference establishes with radix_sort_64 (index.c:264-266), so mm_idx_get-dependent results are identical.
 #include "index.h"
+#include <emmintrin.h>
 #include "mm_algo.cuh"
 #include "fastx.h"
 #include "scan.cuh"
@@ -356,6 +357,14 @@ extern "C" int mm_idx_getseq(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint
 	const uint64_t st1 = mi->seq[rid].offset + st, en1 = mi->seq[rid].offset + en;
 	uint64_t i = st1;
 	for (; i < en1 && (i & 7); ++i) seq[i - st1] = (uint8_t)mmx_seq4_get(mi->S, i);
+	const __m128i m0f = _mm_set1_epi8(0x0f);
+	for (; i + 16 <= en1; i += 16) { // two 32-bit words = 16 bases: split the nibbles and interleave them back in order
+		uint64_t w;
+		memcpy(&w, &mi->S[i >> 3], 8);
+		const __m128i v = _mm_cvtsi64_si128((long long)w);
+		const __m128i lo = _mm_and_si128(v, m0f), hi = _mm_and_si128(_mm_srli_epi16(v, 4), m0f);
+		_mm_storeu_si128((__m128i*)(seq + (i - st1)), _mm_unpacklo_epi8(lo, hi));
+	}
 	for (; i + 8 <= en1; i += 8) { // one 32-bit word = 8 bases
 		uint32_t w = mi->S[i >> 3];
 		uint8_t *o = seq + (i - st1);

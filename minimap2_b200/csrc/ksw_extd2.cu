@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 		if (qlen <= 0 || tlen <= 0 || A.skip) {
 			if (g == 0) {
 				mmb_ksw_res_t o;
+				o.zd_max = -1, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
 				o.max = ez.max, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1;
 				o.mqe = o.mte = o.score = KSW_NEG_INF, o.n_cigar = 0, o.reach_end = 0, o.cigar_off = 0;
 				A.res[jid] = o;
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 		}
 		if (g == 0) {
 			mmb_ksw_res_t o;
+			o.zd_max = -1, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
 			o.max = ez.max, o.zdropped = ez.zdropped, o.max_q = ez.max_q, o.max_t = ez.max_t;
 			o.mqe = ez.mqe, o.mqe_t = ez.mqe_t, o.mte = ez.mte, o.mte_q = ez.mte_q;
 			o.score = ez.score, o.n_cigar = n_cig, o.reach_end = ez.reach_end, o.cigar_off = (uint32_t)coff;
@@ -546,6 +548,7 @@ __global__ void __launch_bounds__(128) ksw_ll_kernel(LLArgs A)
 		if (best >= 0) qe = best / 8 + best % 8 * slen;
 		if (k == 0) {
 			mmb_ksw_res_t o;
+			o.zd_max = -1, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
 			o.max = 0, o.zdropped = 0, o.max_q = qe, o.max_t = te, o.mqe = o.mte = KSW_NEG_INF, o.mqe_t = o.mte_q = -1;
 			o.score = gmax, o.n_cigar = 0, o.reach_end = 0, o.cigar_off = 0;
 			A.res[jid] = o;

@@ -42,6 +42,7 @@ struct FastArgs {
 	int qmax;                             // shared-memory query staging capacity per warp
 	int8_t mch, mis, scn;
 	int8_t q, e, q2, e2;
+	int8_t zd_q, zd_e;                    // gap open/extension as mm_test_zdrop uses them (opt->q, opt->e: not reordered)
 	int long_thres, long_diff;
 	int8_t mat[25];
 };
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(128) ksw_fast_kernel(FastArgs A)
 		}
 		if (lane == 0) {
 			mmb_ksw_res_t o;
+			o.zd_max = -1, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
 			o.max = 0, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1, o.mqe = o.mte = KSW_NEG_INF;
 			o.score = score, o.n_cigar = n, o.reach_end = 0, o.cigar_off = (uint32_t)coff;
 			A.res[jid] = o;
@@ -474,6 +476,70 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			if (run_len) { if (lane == 0) cig[n] = run_len << 4 | run_op; ++n; }
 			#undef PK_EMIT
 			__syncwarp();
+			// ---- mm_test_zdrop's scan (align.c:61-89) over the path just traced, 32 bases per step: prefix sums give the score at
+			// every base, an exclusive prefix maximum the running maximum it is compared with, a max-scan of the updating
+			// lanes the position of that maximum, and the first lane holding the largest drop wins (strict '>' in the reference).
+			int zd_max = -1, zd_t0 = -1, zd_t1 = -1, zd_q0 = -1, zd_q1 = -1;
+			if (g_flag & MMB_JOB_ZDROP) {
+				const uint8_t *gq = smem + (size_t)(wk * NJ + g) * A.qmax;
+				const long long g_ts = (long long)__shfl_sync(full, (int)(jb.t_start >> 32), src) << 32 | (unsigned)__shfl_sync(full, (int)jb.t_start, src);
+				const int g_tstep = __shfl_sync(full, jb.t_step, src);
+				const int zq = A.zd_q, ze = A.zd_e, mch = A.mch, mis = A.mis, scn = A.scn;
+				int sco = 0, mx = INT32_MIN, mi = -1, mj = -1, ti0 = 0, qj0 = 0;
+				zd_max = 0;
+				for (int k = n - 1; k >= 0; --k) {
+					const uint32_t op = cig[k] & 0xf; const int len = (int)(cig[k] >> 4);
+					if (op == 0) {
+						for (int base = 0; base < len; base += 32) {
+							const bool valid = base + lane < len;
+							const int ti = ti0 + base + lane, qj = qj0 + base + lane;
+							int sc = 0;
+							if (valid) {
+								const uint32_t oh = gq[qj];
+								const int tb = fetch_t(A.target, A.t_packed, g_ts + (long long)ti * g_tstep);
+								sc = (oh == 0x80 || tb == 4)? scn : (oh >> tb & 1)? mch : mis;
+							}
+							int S = sc;
+							#pragma unroll
+							for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, S, o); if (lane >= o) S += y; }
+							S += sco;
+							int pm = valid? S : INT32_MIN;
+							#pragma unroll
+							for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, pm, o); if (lane >= o) pm = max(pm, y); }
+							int ex = __shfl_up_sync(full, pm, 1);
+							if (lane == 0) ex = INT32_MIN;
+							const int M = max(mx, ex);               // running maximum this base is compared with
+							const bool upd = valid && S >= M;        // '!(score < max)': ties move the maximum forward
+							int lu = upd? lane : -1;
+							#pragma unroll
+							for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, lu, o); if (lane >= o) lu = max(lu, y); }
+							int exl = __shfl_up_sync(full, lu, 1);
+							if (lane == 0) exl = -1;
+							const int cmi = exl >= 0? ti0 + base + exl : mi, cmj = exl >= 0? qj0 + base + exl : mj;
+							int z = INT32_MIN;
+							if (valid && !upd) { const int li = ti - cmi, lj = qj - cmj, diff = li > lj? li - lj : lj - li; z = M - S - diff * ze; }
+							int zm = z;
+							#pragma unroll
+							for (int o = 16; o > 0; o >>= 1) zm = max(zm, __shfl_xor_sync(full, zm, o));
+							if (zm > zd_max) {
+								const int wl = __ffs(__ballot_sync(full, z == zm)) - 1;
+								zd_max = zm, zd_t0 = __shfl_sync(full, cmi, wl), zd_t1 = __shfl_sync(full, ti, wl), zd_q0 = __shfl_sync(full, cmj, wl), zd_q1 = __shfl_sync(full, qj, wl);
+							}
+							const int L = __shfl_sync(full, lu, 31);
+							if (L >= 0) mx = __shfl_sync(full, S, L), mi = ti0 + base + L, mj = qj0 + base + L;
+							sco = __shfl_sync(full, S, min(32, len - base) - 1);
+						}
+						ti0 += len, qj0 += len;
+					} else if (op == 1 || op == 2) {
+						sco -= zq + ze * len;
+						if (op == 1) qj0 += len; else ti0 += len;
+						if (sco < mx) {
+							const int li = ti0 - mi, lj = qj0 - mj, diff = li > lj? li - lj : lj - li, z = mx - sco - diff * ze;
+							if (z > zd_max) zd_max = z, zd_t0 = mi, zd_t1 = ti0, zd_q0 = mj, zd_q1 = qj0;
+						} else mx = sco, mi = ti0, mj = qj0;
+					}
+				}
+			}
 			unsigned long long coff = 0;
 			if (n > 0) {
 				if (lane == 0) coff = atomicAdd(A.cigar_used, (unsigned long long)n);
@@ -484,7 +550,9 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			}
 			if (lane == 0) {
 				mmb_ksw_res_t o;
+				o.zd_max = -1, o.zd_t0 = o.zd_t1 = o.zd_q0 = o.zd_q1 = -1;
 				o.max = 0, o.zdropped = 0, o.max_q = o.max_t = o.mqe_t = o.mte_q = -1, o.mqe = o.mte = KSW_NEG_INF;
+				o.zd_max = zd_max, o.zd_t0 = zd_t0, o.zd_t1 = zd_t1, o.zd_q0 = zd_q0, o.zd_q1 = zd_q1;
 				o.score = g_score, o.n_cigar = n, o.reach_end = 0, o.cigar_off = (uint32_t)coff;
 				A.res[g_jid] = o;
 			}
@@ -538,6 +606,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 	int8_t q = sc->q, e = sc->e, q2 = sc->q2, e2 = sc->e2;
 	if (q2 + e2 < q + e) std::swap(q, q2), std::swap(e, e2);
 	A.q = q, A.e = e, A.q2 = q2, A.e2 = e2;
+	A.zd_q = sc->q, A.zd_e = sc->e;
 	A.mch = sc->mat[0], A.mis = sc->mat[1], A.scn = sc->mat[24] == 0? (int8_t)(-e2) : sc->mat[24];
 	for (int i = 0; i < 25; ++i) A.mat[i] = sc->mat[i];
 	int lt = e != e2? (q2 - q) / (e - e2) - 1 : 0;

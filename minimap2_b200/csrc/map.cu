@@ -13,6 +13,7 @@
 #include "scan.cuh"
 #include "fastx.h"
 #include <thread>
+#include <unistd.h>
 #include <atomic>
 #include <functional>
 #include <cstring>
@@ -95,7 +96,15 @@ void parallel_for(int64_t n, int n_threads, const std::function<void(int64_t, in
 {
 	if (n <= 0) return;
 	if (n_threads <= 1 || n == 1) { for (int64_t i = 0; i < n; ++i) fn(i, 0); return; }
-	std::call_once(g_pool_once, [&]() { g_pool = new HostPool(n_threads - 1); }); // sized by the first caller; never torn down
+	std::call_once(g_pool_once, [&]() { // sized by the first caller; never torn down
+		// The group threads that feed the GPU must never wait for a core: with one worker per logical CPU the launches of
+		// the next kernels queue behind replay work and the GPU idles (measured: 128 workers 1.42 s/step, 64 workers 1.05 s on
+		// a 128-thread host). Default cap: half of the online CPUs; MM_B200_HOST_THREADS overrides.
+		int cap = (int)sysconf(_SC_NPROCESSORS_ONLN) / 2;
+		if (getenv("MM_B200_HOST_THREADS")) cap = atoi(getenv("MM_B200_HOST_THREADS"));
+		if (cap < 2) cap = 2;
+		g_pool = new HostPool(std::min(n_threads, cap) - 1);
+	});
 	g_pool->run(n, fn);
 }
 
@@ -104,28 +113,34 @@ int g_gpu_slots = getenv("MM_B200_GPU_SLOTS")? std::max(1, atoi(getenv("MM_B200_
 // lock-step and one group's host phase overlaps the others' kernels.
 class GpuGate {
 public:
-	// cls 1 (alignment waves) is served before cls 0 (stage 1 of a new group): finishing a group early spreads the host
-	// replay work over the batch instead of piling it up at the end
+	// Two request classes: 0 = stage 1 of a group (sketch..chain), 1 = an alignment wave. Each class is FIFO. While both have
+	// requests waiting, waves get all slots but one: finishing groups early spreads the host replay work over the batch,
+	// and the reserved slot keeps new groups entering so that the end of the batch is not a single group's serial chain.
 	void acquire(int cls) {
 		std::unique_lock<std::mutex> lk(mu_);
 		const uint64_t my = tail_[cls]++;
-		cv_.wait(lk, [&]() { return my == head_[cls] && in_ < slots() && (cls == 1 || head_[1] == tail_[1]); });
-		++head_[cls], ++in_;
+		cv_.wait(lk, [&]() {
+			if (my != head_[cls] || in_[0] + in_[1] >= slots()) return false;
+			const bool other_waiting = head_[1 - cls] != tail_[1 - cls];
+			if (!other_waiting) return true;
+			return cls == 1? in_[1] < std::max(1, slots() - 1) : in_[0] < 1;
+		});
+		++head_[cls], ++in_[cls];
 		cv_.notify_all();
 	}
-	void release() { std::lock_guard<std::mutex> lk(mu_); --in_; cv_.notify_all(); }
+	void release(int cls) { std::lock_guard<std::mutex> lk(mu_); --in_[cls]; cv_.notify_all(); }
 	static int slots() { return g_gpu_slots; }
 private:
 	std::mutex mu_;
 	std::condition_variable cv_;
 	uint64_t head_[2] = {0, 0}, tail_[2] = {0, 0};
-	int in_ = 0;
+	int in_[2] = {0, 0};
 };
 GpuGate g_gate;
 struct GateHold {
-	bool on;
-	GateHold(bool use, int cls) : on(use) { if (on) g_gate.acquire(cls); }
-	void drop() { if (on) g_gate.release(), on = false; }
+	bool on; int cls;
+	GateHold(bool use, int cls_) : on(use), cls(cls_) { if (on) g_gate.acquire(cls); }
+	void drop() { if (on) g_gate.release(cls), on = false; }
 	~GateHold() { drop(); }
 };
 
@@ -381,6 +396,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	const bool with_cigar = (opt->flag & MM_F_CIGAR) != 0;
 	if (with_cigar && bb.qseq_pool.size() < (size_t)total_bases * 2 + 16) bb.qseq_pool.resize((size_t)total_bases * 2 + 16);
 	parallel_for(n, n_threads, [&](int64_t j, int) {
+		HpScope hp_(HP_HITS);
 		ReadState &r = rs[live[j]];
 		r.rep_len = h_rep[j];
 		r.n_u = (int)(h_uo[j + 1] - h_uo[j]), r.u = h_du + h_uo[j];
@@ -445,18 +461,24 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		while (!active.empty()) {
 			// replay every active read; collect the jobs they miss
 			parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
+				hl_hp_flush();
 				ReadState &r = rs[active[t]];
 				ReadAlign &ra = *r.ra;
 				ra.want.clear(); ra.want_slot.clear();
-				r.a.assign(r.a_src, r.a_src + r.n_a); // pristine anchors (IGNORE/LONG_JOIN marks cleared)
 				int n_regs = r.n_regs0;
-				mm_reg1_t *regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
-				memcpy(regs, r.regs0, sizeof(mm_reg1_t) * n_regs);
+				mm_reg1_t *regs;
+				{
+					HpScope hp_(HP_PRE);
+					r.a.assign(r.a_src, r.a_src + r.n_a); // pristine anchors (IGNORE/LONG_JOIN marks cleared)
+					regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
+					memcpy(regs, r.regs0, sizeof(mm_reg1_t) * n_regs);
+				}
 				regs = hl_align_skeleton(opt, mi, ra, &n_regs, regs, r.n_a, r.a.data());
 				if (ra.incomplete) {
 					for (int i = 0; i < n_regs; ++i) free(regs[i].p);
 					free(regs);
 				} else {
+					HpScope hp_(HP_POST);
 					if (!(opt->flag & MM_F_ALL_CHAINS)) { // align_regs (map.c:215-225)
 						hl_set_parent(opt->mask_level, opt->mask_len, n_regs, regs, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
 						hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 0, (int)(opt->max_gap * 0.8), &n_regs, regs);
@@ -546,6 +568,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	lap("waves end");
 	// ---------------- stage 4: finalize (map.c:338-343) ----------------
 	parallel_for(n, n_threads, [&](int64_t j, int) {
+		hl_hp_flush();
 		ReadState &r = rs[live[j]];
 		if (r.regs0) free(r.regs0);
 		r.regs0 = nullptr, r.ra = nullptr;
@@ -556,6 +579,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		if (rep_len_out) rep_len_out[live[j]] = r.rep_len;
 	});
 	lap("finalize");
+	if (timing) hl_hp_dump("group");
 	return 0;
 }
 
@@ -601,10 +625,14 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	if (NG == 1) return map_group(get_group(0, device), mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads);
 	std::vector<int> cut(NG + 1, 0);
 	{
+		// equal shares, except that the last three groups shrink (3/4, 1/2, 1/4 of a share): the end of the batch is then
+		// the short serial chain of a small group instead of a full-size one
+		std::vector<double> wsum(NG + 1, 0.0);
+		for (int g2 = 0; g2 < NG; ++g2) wsum[g2 + 1] = wsum[g2] + (NG >= 8 && g2 >= NG - 3? 0.25 * (NG - g2) : 1.0);
 		int64_t acc = 0; int g = 1;
 		for (int i = 0; i < n_reads && g < NG; ++i) {
 			acc += qlens[i] > 0? qlens[i] : 0;
-			if (acc >= total * g / NG) cut[g++] = i + 1;
+			if ((double)acc >= (double)total * wsum[g] / wsum[NG]) cut[g++] = i + 1;
 		}
 		for (; g < NG; ++g) cut[g] = n_reads;
 		cut[NG] = n_reads;

@@ -14,7 +14,8 @@ idx = L.mmb_synth_index(int(mbp * 1e6), 24, 11, 10, 15, 14)
 t1 = time.time()
 print("index: %.2fs for %.0f Mbp" % (t1 - t0, mbp), flush=True)
 al = api.Aligner(preset="map-ont", _idx=idx, n_threads=nthr)
-al.map_opt.flag |= api.MM_F_CIGAR | api.MM_F_OUT_CG
+if not os.environ.get('NO_CIGAR'):
+    al.map_opt.flag |= api.MM_F_CIGAR | api.MM_F_OUT_CG
 print("mid_occ", al.map_opt.mid_occ, flush=True)
 buf = np.zeros(n_reads * rl, dtype=np.uint8)
 L.mmb_synth_reads(idx, n_reads, rl, 12, 0.10, 0.40, 0.25, buf.ctypes.data)

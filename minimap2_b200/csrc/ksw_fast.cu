@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(128) ksw_fast_kernel(FastArgs A)
 //
 // The kernel above is issue-bound (~40 integer instructions per cell). Every quantity of the difference recurrence fits
 // in 8 bits, so two cells are packed as 16-bit halves of one register and updated with VIMNMX(3).S16x2 and plain 32-bit
-// adds. Layout of a half: ((value + 128) << 7) | low bits. Biasing keeps both halves non-negative, hence a 32-bit
-// add/subtract of packed words never carries between halves; the 7 low bits are scratch: a candidate carries the tag
+// adds. Layout of a half: ((value + 128) << 8) | low byte (unsigned 16-bit compares). Biasing keeps both halves non-negative, hence a 32-bit
+// add/subtract of packed words never carries between halves; the low byte is scratch: a candidate carries the tag
 // 7-k of the state k it stands for, so one 3-input maximum returns both max(z) and the reference's tie rule (the earlier
 // state wins, ksw2_extd2_sse.c:235-243), and the gap-open floor carries one "not extended" bit per gap state, so the
 // four continuation flags (:244-273) drop out of the maxima as well. ~28 instructions per PAIR of cells.
@@ -287,15 +287,15 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 	uint8_t *p = A.pws + A.pws_stride * (size_t)(worker0 + grp);
 	const int q = A.q, e = A.e, q2 = A.q2, e2 = A.e2, qe = q + e, qe2 = q2 + e2;
 	const unsigned full = 0xffffffffu;
-	#define PK_ENC(v) ((uint32_t)((v) + 128) << 7)
+	#define PK_ENC(v) ((uint32_t)((v) + 128) << 8)
 	#define PK2(v) (PK_ENC(v) * 0x10001u)
-	const uint32_t BB2 = 0x40004000u, CLEAN = 0xff80ff80u, FLAGM = 0x00780078u, TAGM = 0x00070007u;
+	const uint32_t BB2 = 0x80008000u, CLEAN = 0xff00ff00u;
 	const uint32_t K_A = 0x00060006u - BB2, K_B = 0x00050005u - BB2, K_A2 = 0x00040004u - BB2, K_B2 = 0x00030003u - BB2;
-	const uint32_t KX = BB2 - ((uint32_t)e << 7) * 0x10001u - 0x00060006u, KY = BB2 - ((uint32_t)e << 7) * 0x10001u - 0x00050005u;
-	const uint32_t KX2 = BB2 - ((uint32_t)e2 << 7) * 0x10001u - 0x00040004u, KY2 = BB2 - ((uint32_t)e2 << 7) * 0x10001u - 0x00030003u;
+	const uint32_t KX = BB2 - ((uint32_t)e << 8) * 0x10001u - 0x00060006u, KY = BB2 - ((uint32_t)e << 8) * 0x10001u - 0x00050005u;
+	const uint32_t KX2 = BB2 - ((uint32_t)e2 << 8) * 0x10001u - 0x00040004u, KY2 = BB2 - ((uint32_t)e2 << 8) * 0x10001u - 0x00030003u;
 	const uint32_t NQX = PK2(-qe) | 0x00080008u, NQY = PK2(-qe) | 0x00100010u, NQX2 = PK2(-qe2) | 0x00200020u, NQY2 = PK2(-qe2) | 0x00400040u;
-	const uint32_t MCH8 = PK2((int)A.mch), SCN_T = PK2((int)A.scn) + 0x00070007u;
-	const uint32_t KMM = (uint32_t)((int)A.mch - (int)A.mis) << 7;
+	const uint32_t SCN_T = PK2((int)A.scn) + 0x00070007u;
+	const uint32_t KMM = (uint32_t)((int)A.mch - (int)A.mis) << 8;
 	const uint32_t E_QE = PK_ENC(-q - e), E_E = PK_ENC(-e), E_E2 = PK_ENC(-e2), E_LD = PK_ENC(A.long_diff), E_QE2 = PK_ENC(-q2 - e2);
 	const int lt = A.long_thres;
 
@@ -373,13 +373,13 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 					sc = (sc & ~mN) | (SCN_T & mN);
 					const uint32_t uc = U[c];
 					const uint32_t a = xl + vl + K_A, a2 = x2l + vl + K_A2, b = Y[c] + uc + K_B, b2 = Y2[c] + uc + K_B2;
-					uint32_t zt = __vimax3_s16x2(sc, a, b);
-					zt = __vimax3_s16x2(zt, a2, b2);
-					const uint32_t z8 = __vmins2(zt & CLEAN, MCH8);
+					uint32_t zt = __vimax3_u16x2(sc, a, b);
+					zt = __vimax3_u16x2(zt, a2, b2);
+					const uint32_t z8 = zt & CLEAN; // no clip to the match score (:243) needed: H(i,j) - H(i-1,j-1) <= match holds in every cell when the band does not clip
 					const uint32_t un = z8 - vl + BB2, vn = z8 - uc + BB2;
-					const uint32_t xt = __vmaxs2(a - z8 + KX, NQX), yt = __vmaxs2(b - z8 + KY, NQY);
-					const uint32_t x2t = __vmaxs2(a2 - z8 + KX2, NQX2), y2t = __vmaxs2(b2 - z8 + KY2, NQY2);
-					wd[c] = (zt & TAGM) | ((xt | yt | x2t | y2t) & FLAGM);
+					const uint32_t xt = __vmaxu2(a - z8 + KX, NQX), yt = __vmaxu2(b - z8 + KY, NQY);
+					const uint32_t x2t = __vmaxu2(a2 - z8 + KX2, NQX2), y2t = __vmaxu2(b2 - z8 + KY2, NQY2);
+					wd[c] = (xt | yt | x2t) | y2t | zt; // low byte of each half = tag | flags (the value sits in the high byte)
 					xl = xt & CLEAN, Y[c] = yt & CLEAN, x2l = x2t & CLEAN, Y2[c] = y2t & CLEAN;
 					U[c] = un, vl = vn;
 					if (c == 0) v_first = vn;
@@ -397,11 +397,11 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 				// score pieces: H(t, qlen-1) = H(t-1, qlen-1) + u(t, qlen-1) along the last row
 				if (jA == qlen - 1) {
 					#pragma unroll
-					for (int c = 0; c < H; ++c) if (t0 + c >= 1 && t0 + c < tlen) hrow += (int)((U[c] & 0xffffu) >> 7) - 128;
+					for (int c = 0; c < H; ++c) if (t0 + c >= 1 && t0 + c < tlen) hrow += (int)((U[c] & 0xffffu) >> 8) - 128;
 				}
 				if (jA == qlen) {
 					#pragma unroll
-					for (int c = 0; c < H; ++c) if (t0 + H + c < tlen) hrow += (int)(U[c] >> 23) - 128;
+					for (int c = 0; c < H; ++c) if (t0 + H + c < tlen) hrow += (int)(U[c] >> 24) - 128;
 				}
 				// traceback bytes: lo bytes of the words -> row jA (block A), byte 2 of the words -> row jA-1 (block B)
 				uint32_t lo[NW], hi[NW];
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 		int score = hrow;
 		#pragma unroll
 		for (int o = LN / 2; o > 0; o >>= 1) score += __shfl_xor_sync(full, score, o);
-		score += (int)(hcol_acc >> 7) - 128 * qlen - qe;
+		score += (int)(hcol_acc >> 8) - 128 * qlen - qe;
 		score = __shfl_sync(full, score, lead);
 		__syncwarp();
 		// ---- traceback from (tlen-1, qlen-1) (ksw2.h:130-162; no forced states: the band is never clipped) ----

@@ -67,3 +67,13 @@ def test_expected_outputs_present():
     exp = os.path.join(O.ROOT, "tests", "golden", "expected")
     names = sorted(os.listdir(exp))
     assert "mt_sam.txt" in names and "ont_paf_cs.txt" in names and len(names) >= 10
+
+
+def test_oracle_lchain_rmq_matches_golden(V):
+    """mg_lchain_rmq incl. the krmq.h tree-shape dependent ties"""
+    for i in range(int(V["ch_n"][0])):
+        par = [int(x) for x in V["rq%d_par" % i]]
+        pg, ps = [float(x) for x in V["ch%d_pen" % i]]
+        u, b = O.oracle_lchain_rmq(V["ch%d_a" % i], *par, pg, ps)
+        assert len(u) == len(V["rq%d_u" % i]) and (u == V["rq%d_u" % i]).all(), i
+        assert b.shape == V["rq%d_b" % i].shape and (b == V["rq%d_b" % i]).all(), i

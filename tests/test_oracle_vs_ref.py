@@ -136,3 +136,18 @@ def test_lchain_dp(seed):
             x = O.oracle_lchain_dp(a, mdx, mdy, bw, skip, iters, mincnt, minsc, float(pg), 0.0, is_cdna)
             y = O.ref_lchain_dp(a, mdx, mdy, bw, skip, iters, mincnt, minsc, float(pg), 0.0, is_cdna)
             assert (x[0] == y[0]).all() and x[1].shape == y[1].shape and (x[1] == y[1]).all(), (it, mdx)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_lchain_rmq(seed):
+    """mg_lchain_rmq: the answer on equal priorities depends on the AVL shape of krmq.h -- checked against the reference
+    over window sizes that force erasures, a tiny tree cap, with and without the inner tree"""
+    rng = np.random.default_rng(900 + seed)
+    for it in range(20):
+        a = make_anchors(rng, n_chain=int(rng.integers(1, 5)), n_noise=int(rng.integers(0, 500)))
+        for (md, mdi, bw, skip, cap, mincnt, minsc) in [(5000, 1000, 20000, 25, 100000, 3, 40), (800, 0, 500, 25, 100000, 3, 40),
+                                                         (5000, 1000, 2000, 5, 12, 2, 20), (300, 300, 100, 25, 100000, 3, 40)]:
+            pg = np.float32(np.float32(0.8) * 0.01 * 15)
+            x = O.oracle_lchain_rmq(a, md, mdi, bw, skip, cap, mincnt, minsc, float(pg), 0.0)
+            y = O.ref_lchain_rmq(a, md, mdi, bw, skip, cap, mincnt, minsc, float(pg), 0.0)
+            assert len(x[0]) == len(y[0]) and (x[0] == y[0]).all() and x[1].shape == y[1].shape and (x[1] == y[1]).all(), (it, md, cap)

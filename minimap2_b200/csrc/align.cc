@@ -106,7 +106,9 @@ struct Driver {
 		return false;
 	}
 
-	// mm_align_pair (align.c:336-368) for the dual-affine case
+	// mm_align_pair (align.c:336-368). Single-affine scoring (q == q2, e == e2: ksw_extz2_sse, align.c:360-361) runs the same
+	// dual-affine kernels with both gap terms equal: on every flag combination align.c uses, ksw_extz2_sse(q,e) and
+	// ksw_extd2_sse(q,e,q,e) return identical ksw_extz_t and CIGARs (tests/test_oracle_vs_ref.py::test_extz2_is_extd2_with_equal_gaps).
 	bool align_pair(const Seg &s, int w, int end_bonus, int zdrop, int ksw_flag, Ez *ez) {
 		if (opt->transition != 0 && opt->b != opt->transition) ksw_flag |= MMB_KSW_GENERIC_SC;
 		if (opt->max_sw_mat > 0 && (int64_t)s.tlen * s.qlen > opt->max_sw_mat) {

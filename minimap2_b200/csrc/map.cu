@@ -233,7 +233,6 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 	else if (opt->flag & MM_F_SR) what = "short-read mode (-x sr)";
 	else if (opt->flag & MM_F_RMQ) what = "RMQ chaining as the primary chainer (--rmq / asm presets)";
 	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
-	else if (opt->q == opt->q2 && opt->e == opt->e2) what = "single-affine gap cost (ksw_extz2)";
 	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
 	else if (mi->n_alt) what = "ALT contigs";
 	if (what) {

@@ -42,6 +42,8 @@ CASES = {
     "ont_sam_md": ["-x", "map-ont", "-a", "--MD", "synth-ref.fa", "synth-ont.fa"],
     "ont_paf_nocigar_allchains": ["-x", "map-ont", "-P", "synth-ref.fa", "synth-ont.fa"],
     "hifi_paf_cigar": ["-x", "map-hifi", "-c", "synth-ref.fa", "synth-hifi.fa"],
+    "mt_paf_single_affine": ["-c", "-O4", "-E2", "MT-human.fa", "MT-orang.fa"],          # q == q2, e == e2: ksw_extz2 in the reference
+    "ont_paf_single_affine": ["-x", "map-ont", "-c", "-O6", "-E2", "synth-ref.fa", "synth-ont.fa"],
 }
 
 

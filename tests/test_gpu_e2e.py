@@ -64,3 +64,16 @@ def test_synthetic_map_ont(tmp_path, cfg):
     synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
     n = compare(["-x", "map-ont", "-c", "--cs", rf, qf])
     assert n >= cfg["n"] * 0.9
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("gap", [["-O4", "-E2"], ["-O6", "-E3"]])
+def test_single_affine_gap_cost(tmp_path, gap):
+    """q == q2 and e == e2 select ksw_extz2 in the reference (align.c:360); here the dual-affine kernels run with equal terms"""
+    compare(["-c"] + gap + [os.path.join(DATA, "MT-human.fa"), os.path.join(DATA, "MT-orang.fa")])
+    contigs = synth.random_genome(400_000, 21, n_contigs=2, repeat_frac=0.1)
+    reads = synth.make_reads(contigs, 150, 4000, 0.10, 121, chimeric_frac=0.05)
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    compare(["-x", "map-ont", "-c"] + gap + [rf, qf])

@@ -1,5 +1,6 @@
 """Pins the oracle (oracle/*.c) against the UNMODIFIED reference build (oracle/_ref, compiled from /root/reference).
 CPU only. Skipped when oracle/_ref has not been built (it is built by __graft_entry__.build() in the dev container)."""
+import ctypes as C
 import numpy as np
 import pytest
 import oracle_lib as O
@@ -151,3 +152,35 @@ def test_lchain_rmq(seed):
             x = O.oracle_lchain_rmq(a, md, mdi, bw, skip, cap, mincnt, minsc, float(pg), 0.0)
             y = O.ref_lchain_rmq(a, md, mdi, bw, skip, cap, mincnt, minsc, float(pg), 0.0)
             assert len(x[0]) == len(y[0]) and (x[0] == y[0]).all() and x[1].shape == y[1].shape and (x[1] == y[1]).all(), (it, md, cap)
+
+
+def _ref_extz2(q, t, mat, go, ge, w, zdrop, eb, flag):
+    ez = O.RefEz()
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8); mat = np.ascontiguousarray(mat, dtype=np.int8)
+    O.ref().refshim_extz2(C.c_int(len(q)), q.ctypes.data_as(C.c_void_p), C.c_int(len(t)), t.ctypes.data_as(C.c_void_p), C.c_int8(5),
+                          mat.ctypes.data_as(C.c_void_p), C.c_int8(go), C.c_int8(ge), C.c_int(w), C.c_int(zdrop), C.c_int(eb), C.c_int(flag), C.byref(ez))
+    d = O.ez_dict(ez, True)
+    O.ref().refshim_free(ez.cigar)
+    return d
+
+
+def test_extz2_is_extd2_with_equal_gaps():
+    """The single-affine kernel of the reference (ksw2_extz2_sse.c:26) is not rebuilt: for every flag combination align.c
+    passes (KSW_EZ_APPROX_DROP is never set, align.c:336-368,779-890), it equals ksw_extd2 with q2 = q, e2 = e -- shown
+    here on the reference itself and on the oracle, band-clipped calls included."""
+    rng = np.random.default_rng(77)
+    flags = [0, 0x08, 0x40, 0x40 | 0x02 | 0x80, 0x02, 0x40 | 0x02, 0x08 | 0x02, 0x01, 0x80]
+    for it in range(1500):
+        tl = int(rng.integers(1, 400)); t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = O.mutate(t, rng, err=float(rng.choice([0.0, 0.05, 0.15, 0.4])))
+        if len(q) == 0:
+            q = np.array([0], dtype=np.uint8)
+        if rng.random() < 0.2:
+            q[rng.integers(0, len(q))] = 4
+        a, b, go, ge = [(2, 4, 4, 2), (1, 4, 6, 2), (2, 8, 12, 2), (1, 1, 1, 1), (2, 4, 24, 1)][it % 5]
+        mat = O.simple_mat(a, b, 1)
+        w = int(rng.choice([-1, 5, 17, 40, 100, 751])); zd = int(rng.choice([-1, 50, 200, 400])); eb = int(rng.choice([-1, 0, 10]))
+        fl = int(rng.choice(flags))
+        x = _ref_extz2(q, t, mat, go, ge, w, zd, eb, fl)
+        assert x == O.ref_extd2(q, t, mat, go, ge, go, ge, w, zd, eb, fl), (it, fl)
+        assert x == O.oracle_extd2(q, t, mat, go, ge, go, ge, w, zd, eb, fl), (it, fl)

@@ -290,7 +290,7 @@ extern "C" void mm_idx_destroy(mm_idx_t *mi) // index.c:62-91
 	if (mi->B) {
 		mm_idx_bucket_s *B = mi->B;
 		if (B->ctx) cudaSetDevice(B->ctx->device);
-		if (!B->external) { cudaFree(B->d_tab); cudaFree(B->d_pos); cudaFree(B->d_S); cudaFree(B->d_seq_off); cudaFree(B->d_seq_len); cudaFree(B->d_cnt_sorted); } cudaFree(B->d_ukeys); cudaFree(B->d_ucnt); cudaFree(B->d_uoff);
+		if (!B->external) { cudaFree(B->d_tab); cudaFree(B->d_pos); cudaFree(B->d_S); cudaFree(B->d_seq_off); cudaFree(B->d_seq_len); cudaFree(B->d_cnt_sorted); } cudaFree(B->d_name_rank); cudaFree(B->d_ukeys); cudaFree(B->d_ucnt); cudaFree(B->d_uoff);
 		delete B->h_map;
 		delete B;
 	}

@@ -41,6 +41,8 @@ struct mm_idx_bucket_s {  // the opaque "B" of mm_idx_t
 	uint64_t *d_seq_off = nullptr;
 	uint32_t *d_seq_len = nullptr;
 	uint32_t *d_cnt_sorted = nullptr;   // ascending occurrence counts (for mm_idx_cal_max_occ)
+	uint32_t *d_name_rank = nullptr;    // rank of every sequence name in the sorted name list (skip_seed, map.c:78-100); lazy
+	std::vector<uint32_t> name_order;   // sequence ids in name order (host side of the same)
 	uint64_t *d_ukeys = nullptr; uint32_t *d_ucnt = nullptr; int64_t *d_uoff = nullptr; // key list kept for the lazy host mirror
 	// host (lazy)
 	std::mutex mu;

@@ -215,6 +215,7 @@ struct BatchBufs { // device arenas reused across batches (per context)
 	DevBuf a2, seq, off, mz, mz_off, n_mz, qlen, s_n, s_off, k_idx, k_aoff, flt, mini_pos, n_keep, rep_len, n_a, a_off, a, stk;
 	DevBuf n_u, n_v, u, a_out, ch1, ch2, t1, t2, doff, dense_u, dense_a, dense_mp;
 	DevBuf jobs, res, cig;
+	DevBuf qlo, qhi, k_cnt;                // skip_seed inputs (ava / strand-restricted modes only)
 	PinBuf h_seq, h_misc, h_jobs, h_res, h_cig[16];
 	std::vector<ReadState> rs_pool;        // persistent per-read objects: their vectors keep capacity => no allocation in steady state
 	std::vector<ReadAlign> ra_pool;
@@ -312,6 +313,36 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	S.n_keep = bb.n_keep.as<int32_t>((size_t)n), S.rep_len = bb.rep_len.as<int32_t>((size_t)n), S.n_a = bb.n_a.as<int64_t>((size_t)n + 1);
 	init_nmz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_mz_off, n, S.n_mz);
 	++ctx->n_launch;
+	if (opt->flag & (MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_FOR_ONLY | MM_F_REV_ONLY)) { // skip_seed (map.c:78-100) runs on the device
+		S.k_cnt = bb.k_cnt.as<uint32_t>(nm);
+		if (names && (opt->flag & (MM_F_NO_DIAG | MM_F_NO_DUAL))) {
+			{ // rank of every reference name in sorted order, built once per index
+				std::lock_guard<std::mutex> lk(B->mu);
+				if (!B->d_name_rank) {
+					B->name_order.resize(mi->n_seq);
+					for (uint32_t i = 0; i < mi->n_seq; ++i) B->name_order[i] = i;
+					std::stable_sort(B->name_order.begin(), B->name_order.end(), [&](uint32_t x, uint32_t y) { return strcmp(mi->seq[x].name, mi->seq[y].name) < 0; });
+					std::vector<uint32_t> rank(mi->n_seq);
+					for (uint32_t i = 0; i < mi->n_seq; ++i) rank[B->name_order[i]] = i;
+					MMB_CUDA_CHECK(cudaMalloc(&B->d_name_rank, sizeof(uint32_t) * (mi->n_seq + 1)));
+					MMB_CUDA_CHECK(cudaMemcpy(B->d_name_rank, rank.data(), sizeof(uint32_t) * mi->n_seq, cudaMemcpyHostToDevice));
+				}
+			}
+			std::vector<uint32_t> qlo(n), qhi(n);
+			const std::vector<uint32_t> &ord = B->name_order;
+			parallel_for(n, n_threads, [&](int64_t j, int) {
+				const char *qn = rs[live[j]].name;
+				if (!qn) { qlo[j] = qhi[j] = 0; return; } // no name: no name test (map.c:81)
+				qlo[j] = (uint32_t)(std::lower_bound(ord.begin(), ord.end(), qn, [&](uint32_t id, const char *q) { return strcmp(mi->seq[id].name, q) < 0; }) - ord.begin());
+				qhi[j] = (uint32_t)(std::upper_bound(ord.begin(), ord.end(), qn, [&](const char *q, uint32_t id) { return strcmp(q, mi->seq[id].name) < 0; }) - ord.begin());
+			});
+			uint32_t *d_qlo = bb.qlo.as<uint32_t>((size_t)n), *d_qhi = bb.qhi.as<uint32_t>((size_t)n);
+			MMB_CUDA_CHECK(cudaMemcpyAsync(d_qlo, qlo.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+			MMB_CUDA_CHECK(cudaMemcpyAsync(d_qhi, qhi.data(), sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+			MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope
+			S.name_rank = B->d_name_rank, S.q_name_lo = d_qlo, S.q_name_hi = d_qhi;
+		}
+	}
 	mmb_seed_select_device(ctx, S, total_mz);
 	int64_t *d_a_off = bb.a_off.as<int64_t>((size_t)n + 1);
 	copy_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(S.n_a, n, d_a_off);

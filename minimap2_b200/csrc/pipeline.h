@@ -21,6 +21,11 @@ struct SeedArgs {
 	// anchors
 	m128 *a; const int64_t *a_off;
 	m128 *a_sorted;           // output of the anchor sort (a stays in expansion order for the exact-sort fallback)
+	// skip_seed (map.c:78-100), only when MM_F_NO_DIAG/NO_DUAL/FOR_ONLY/REV_ONLY is set: names are compared through their
+	// rank in the sorted list of reference names; a query name equals the references ranked [q_name_lo, q_name_hi)
+	const uint32_t *name_rank = nullptr;  // per reference sequence (null: no query names => no name tests, as in the reference)
+	const uint32_t *q_name_lo = nullptr, *q_name_hi = nullptr; // per read
+	uint32_t *k_cnt = nullptr;            // per kept seed: occurrences that survive skip_seed
 };
 
 void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz);

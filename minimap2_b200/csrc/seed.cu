@@ -238,6 +238,57 @@ __global__ void __launch_bounds__(128) select_kernel(SeedArgs A)
 #undef QPOS
 }
 
+#define MMB_SKIP_FLAGS (MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_FOR_ONLY | MM_F_REV_ONLY)
+
+// skip_seed (map.c:78-100). strcmp(qname, name[rid]) is evaluated on name ranks: >0 below q_name_lo, 0 inside [lo,hi), <0 above.
+__device__ __forceinline__ bool skip_seed_dev(const SeedArgs &A, int rd, uint64_t r, uint32_t q_pos, int qlen, bool *is_self)
+{
+	*is_self = false;
+	if (A.name_rank && (A.flag & (MM_F_NO_DIAG | MM_F_NO_DUAL))) {
+		const uint32_t rid = (uint32_t)(r >> 32), rk = A.name_rank[rid];
+		const int cmp = rk < A.q_name_lo[rd]? 1 : rk < A.q_name_hi[rd]? 0 : -1;
+		if ((A.flag & MM_F_NO_DIAG) && cmp == 0 && (int)A.ix.seq_len[rid] == qlen) {
+			if ((uint32_t)r >> 1 == (q_pos >> 1)) return true;      // the diagonal itself
+			if ((r & 1) == (q_pos & 1)) *is_self = true;
+		}
+		if ((A.flag & MM_F_NO_DUAL) && cmp > 0) return true;        // all-vs-all: map each pair once
+	}
+	if (A.flag & (MM_F_FOR_ONLY | MM_F_REV_ONLY)) {
+		if ((r & 1) == (q_pos & 1)) { if (A.flag & MM_F_REV_ONLY) return true; }
+		else if (A.flag & MM_F_FOR_ONLY) return true;
+	}
+	return false;
+}
+
+// With skip_seed active the anchor count of a seed is no longer its occurrence count: count the survivors per kept seed,
+// then rebuild the per-read offsets (the reference simply appends the survivors, map.c:181-199).
+__global__ void __launch_bounds__(256) skip_count_kernel(SeedArgs A, int64_t total)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= total) return;
+	const int rd = find_read(A.mz_off, A.n_reads, t);
+	const int64_t base = A.mz_off[rd];
+	if ((int)(t - base) >= A.n_keep[rd]) return;
+	const uint32_t mi = A.k_idx[t] & 0x7fffffffu;
+	const uint32_t q_pos = (uint32_t)A.mz[base + mi].y, n = A.s_n[base + mi];
+	const uint64_t *cr = A.ix.pos + A.s_off[base + mi];
+	const int qlen = A.qlen[rd];
+	uint32_t c = 0;
+	for (uint32_t j = 0; j < n; ++j) { bool self; if (!skip_seed_dev(A, rd, cr[j], q_pos, qlen, &self)) ++c; }
+	A.k_cnt[t] = c;
+}
+
+__global__ void __launch_bounds__(128) skip_offsets_kernel(SeedArgs A)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= A.n_reads) return;
+	const int64_t base = A.mz_off[rd];
+	const int n_keep = A.n_keep[rd];
+	int64_t run = 0;
+	for (int k = 0; k < n_keep; ++k) { A.k_aoff[base + k] = (uint32_t)run; run += A.k_cnt[base + k]; }
+	A.n_a[rd] = run;
+}
+
 __global__ void __launch_bounds__(256) expand_kernel(SeedArgs A, int64_t total) // map.c:176-199
 {
 	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -253,9 +304,12 @@ __global__ void __launch_bounds__(256) expand_kernel(SeedArgs A, int64_t total) 
 	const uint64_t *cr = A.ix.pos + A.s_off[base + mi];
 	m128 *a = A.a + A.a_off[rd] + A.k_aoff[t];
 	const int qlen = A.qlen[rd];
-	const bool qstrand = (A.flag & MM_F_QSTRAND) != 0;
+	const bool qstrand = (A.flag & MM_F_QSTRAND) != 0, filtered = (A.flag & MMB_SKIP_FLAGS) != 0;
+	uint32_t w = 0;
 	for (uint32_t j = 0; j < n; ++j) {
 		const uint64_t r = cr[j];
+		bool is_self = false;
+		if (filtered && skip_seed_dev(A, rd, r, q_pos, qlen, &is_self)) continue;
 		const int32_t rpos = (int32_t)((uint32_t)r >> 1);
 		m128 p;
 		if ((r & 1) == (q_pos & 1)) {
@@ -271,7 +325,8 @@ __global__ void __launch_bounds__(256) expand_kernel(SeedArgs A, int64_t total) 
 		}
 		p.y |= (uint64_t)seg_id << MMX_SEED_SEG_SHIFT;
 		if (e >> 31) p.y |= MMX_SEED_TANDEM;
-		a[j] = p;
+		if (is_self) p.y |= MMX_SEED_SELF;
+		a[w++] = p;
 	}
 }
 
@@ -477,8 +532,8 @@ void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz)
 	if (A.n_reads <= 0) return;
 	const int rb = (A.n_reads + 127) / 128;
 	ProfScope prof(ctx, MMB_PROF_SEED, (uint64_t)total_mz);
-	if (A.flag & (MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_FOR_ONLY | MM_F_REV_ONLY | MM_F_HEAP_SORT)) {
-		fprintf(stderr, "[ERROR] minimap2_b200: --for-only/--rev-only/ava (-X) /sr heap-sort seeding are not supported by this build yet\n");
+	if (A.flag & MM_F_HEAP_SORT) {
+		fprintf(stderr, "[ERROR] minimap2_b200: heap-sort seeding (-x sr) is not supported by this build\n");
 		abort();
 	}
 	{
@@ -491,8 +546,13 @@ void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz)
 	++ctx->n_launch;
 	if (total_mz > 0) lookup_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
 	select_kernel<<<rb, 128, 0, ctx->stream>>>(A);
-	MMB_CUDA_CHECK(cudaGetLastError());
 	ctx->n_launch += 3;
+	if ((A.flag & MMB_SKIP_FLAGS) && total_mz > 0) { // skip_seed changes the anchor counts (map.c:78-100)
+		skip_count_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
+		skip_offsets_kernel<<<rb, 128, 0, ctx->stream>>>(A);
+		ctx->n_launch += 2;
+	}
+	MMB_CUDA_CHECK(cudaGetLastError());
 }
 
 void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, int64_t total_a, DevBuf &stkbuf)

@@ -77,3 +77,37 @@ def test_single_affine_gap_cost(tmp_path, gap):
     synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
     synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
     compare(["-x", "map-ont", "-c"] + gap + [rf, qf])
+
+
+def _overlap_set(tmp_path, seed, glen=300_000, n=240, rlen=5000):
+    contigs = synth.random_genome(glen, seed, n_contigs=1, repeat_frac=0.05)
+    reads = synth.make_reads(contigs, n, rlen, 0.08, seed + 7, chimeric_frac=0.0)
+    qf = str(tmp_path / "reads.fa")
+    synth.write_fasta(qf, ["rd%03d" % i for i in range(len(reads))], reads)
+    return qf
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_ava_ont_overlaps(tmp_path):
+    """BASELINE config 4 shape: all-vs-all overlap, skip_seed's name tests (NO_DIAG, NO_DUAL) evaluated on the device"""
+    qf = _overlap_set(tmp_path, 31)
+    assert compare(["-x", "ava-ont", qf, qf]) > 100
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_ava_with_cigar(tmp_path):
+    """-X with base-level alignment: self-chain anchors carry MM_SEED_SELF into mm_align1 (align.c:760)"""
+    qf = _overlap_set(tmp_path, 32, glen=150_000, n=100, rlen=4000)
+    compare(["-x", "map-ont", "-X", "-c", qf, qf])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("strand", ["--for-only", "--rev-only"])
+def test_strand_restricted(tmp_path, strand):
+    compare(["-c", strand, os.path.join(DATA, "MT-human.fa"), os.path.join(DATA, "MT-orang.fa")])
+    contigs = synth.random_genome(300_000, 41, n_contigs=2, repeat_frac=0.1)
+    reads = synth.make_reads(contigs, 120, 4000, 0.10, 141, chimeric_frac=0.05)
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    compare(["-x", "map-ont", "-c", strand, rf, qf])

@@ -330,8 +330,9 @@ struct Driver {
 		// float mantissa keeps them multiples of 2^-32 in any realistic range, so the reference's double arithmetic is exact
 		// and a 2^-32 fixed-point integer reproduces it; the double loop below remains as the fallback when a gap penalty is
 		// not representable.
-		bool fixed_ok = true;
-		{
+		static const bool no_fixed = getenv("MM_B200_NO_FIXED_EXTRA") != nullptr; // debugging aid: force the double loop
+		bool fixed_ok = !no_fixed;
+		if (fixed_ok) {
 			int64_t matfx[25];
 			for (int i = 0; i < 25; ++i) matfx[i] = (int64_t)mat[i] << 32;
 			int64_t sfx = 0, maxfx = 0;
@@ -371,9 +372,35 @@ struct Driver {
 				max = (double)maxfx / 4294967296.0;
 			}
 		}
-		if (!fixed_ok) {
-		toff = qoff = 0, s = 0.0, max = 0.0;
-		r->blen = r->mlen = 0, r->is_spliced = 0;		}
+		if (!fixed_ok) { // the reference's loop as written (align.c:266-297)
+			toff = qoff = 0, s = 0.0, max = 0.0;
+			r->blen = r->mlen = 0, r->is_spliced = 0;
+			for (uint32_t k = 0; k < p->n_cigar; ++k) {
+				uint32_t op = p->cigar[k] & 0xf, len = p->cigar[k] >> 4;
+				if (op == MM_CIGAR_MATCH) {
+					int n_ambi = 0, n_diff = 0;
+					for (uint32_t l = 0; l < len; ++l) {
+						int cq = qseq[qoff + l], ct = tseq[toff + l];
+						if (ct > 3 || cq > 3) ++n_ambi;
+						else if (ct != cq) ++n_diff;
+						s += mat[ct * 5 + cq];
+						if (s < 0) s = 0;
+						else max = max > s? max : s;
+					}
+					r->blen += len - n_ambi, r->mlen += len - (n_ambi + n_diff), p->n_ambi += n_ambi;
+					toff += len, qoff += len;
+				} else if (op == MM_CIGAR_INS || op == MM_CIGAR_DEL) {
+					int n_ambi = 0;
+					const uint8_t *sq = op == MM_CIGAR_INS? qseq + qoff : tseq + toff;
+					for (uint32_t l = 0; l < len; ++l) if (sq[l] > 3) ++n_ambi;
+					r->blen += len - n_ambi, p->n_ambi += n_ambi;
+					if (log_gap) s -= q + (double)e * mmx_log2(1.0 + len);
+					else s -= q + e;
+					if (s < 0) s = 0;
+					if (op == MM_CIGAR_INS) qoff += len; else toff += len;
+				} else if (op == MM_CIGAR_N_SKIP) r->is_spliced = 1, toff += len;
+			}
+		}
 		p->dp_max = p->dp_max0 = (int32_t)(max + .499);
 		assert(qoff == r->qe - r->qs && toff == r->re - r->rs);
 		if (is_eqx) update_cigar_eqx(r, qseq, tseq);

@@ -89,17 +89,7 @@ __global__ void tab_insert_kernel(IdxSlot *tab, int bits, const uint64_t *keys, 
 	}
 }
 
-__global__ void seqoff_kernel(const uint32_t *len, uint32_t n, int64_t *off) // off[i] = len[i] (to be scanned)
-{
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) off[i] = len[i];
-}
 
-__global__ void copy_i64_u64(const int64_t *a, uint64_t *b, int64_t n)
-{
-	int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) b[i] = (uint64_t)a[i];
-}
 
 void finish_table(mm_idx_t *mi, mmb_ctx_t *ctx, const uint64_t *d_keys, const uint32_t *d_cnt, const int64_t *d_off, int64_t n_keys)
 {

@@ -46,7 +46,6 @@ public:
 	explicit HostPool(int n_workers) {
 		for (int t = 0; t < n_workers; ++t) th_.emplace_back([this, t]() { worker(t + 1); });
 	}
-	int size() const { return (int)th_.size(); }
 	void run(int64_t n, const std::function<void(int64_t, int)> &fn) {
 		if (n <= 0) return;
 		auto task = std::make_shared<Task>();

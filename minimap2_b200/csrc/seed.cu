@@ -5,12 +5,14 @@
 // collect_seed_hits (map.c:168-204) and its radix_sort_128x (ksort.h:98-151, exact tie order).
 //
 // Stage kernels over a whole read batch (SoA arrays in HBM, per-read slices given by offset arrays):
-//   mzflt_kernel   1 thread / read      query-side high-multiplicity minimizer filter
-//   lookup_kernel  1 thread / minimizer hash-table probe: one 16 B slot load per probe (random HBM sector access)
-//   select_kernel  1 thread / read      tandem flags, high-occurrence streak selection (<=128-entry heap), rep_len,
-//                                       mini_pos, per-seed anchor offsets
-//   expand_kernel  1 thread / seed      occurrence list -> anchors (strand-normalised coordinates)
-//   sort_kernel    1 thread / read      exact emulation of the reference's unstable in-place MSD radix sort
+//   mzflt_smem_kernel  1 CTA / read         query-side high-multiplicity minimizer filter (shared-memory hash; mzflt_kernel for >2048)
+//   lookup_kernel      1 thread / minimizer hash-table probe: one 16 B slot load per probe (random HBM sector access)
+//   select_kernel      1 thread / read      tandem flags, high-occurrence streak selection (<=128-entry heap), rep_len,
+//                                           mini_pos, per-seed anchor offsets
+//   skip_count/offsets 1 thread / seed,read skip_seed (map.c:78-100) survivors per seed; only for ava / strand-restricted modes
+//   expand_kernel      1 thread / seed      occurrence list -> anchors (strand-normalised coordinates)
+//   sort_block_kernel  1 CTA / read         bitonic sort of (x, index) in shared memory, tie detection
+//   sort_exact_smem    1 warp / read        exact emulation of the reference's unstable in-place MSD radix sort for tie reads
 #include "index.h"
 #include "mm_algo.cuh"
 #include "scan.cuh"
@@ -517,11 +519,6 @@ __global__ void stk_len_kernel2(const int64_t *a_off, int n_reads, int64_t *stk_
 	if (i < n_reads) stk_off[i] = mmx_rs_stack_len(a_off[i + 1] - a_off[i]);
 }
 
-__global__ void copy_na_kernel(const int64_t *n_a, int n, int64_t *a_off)
-{
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) a_off[i] = n_a[i];
-}
 
 } // namespace
 

@@ -78,6 +78,12 @@ void refshim_extz2(int qlen, const uint8_t *q, int tlen, const uint8_t *t, int8_
 	memset(ez, 0, sizeof(*ez));
 	ksw_extz2_sse(0, qlen, q, tlen, t, m, mat, gapo, gape, w, zdrop, end_bonus, flag, ez);
 }
+void refshim_exts2(int qlen, const uint8_t *q, int tlen, const uint8_t *t, int8_t m, const int8_t *mat, int8_t gapo, int8_t gape, int8_t gapo2,
+				   int8_t noncan, int zdrop, int end_bonus, int8_t junc_bonus, int8_t junc_pen, int flag, const uint8_t *junc, ksw_extz_t *ez)
+{
+	memset(ez, 0, sizeof(*ez));
+	ksw_exts2_sse(0, qlen, q, tlen, t, m, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus, junc_pen, flag, junc, ez);
+}
 int refshim_ll_i16(int qlen, const uint8_t *q, int tlen, const uint8_t *t, int m, const int8_t *mat, int gapo, int gape, int *qe, int *te)
 {
 	void *qp = ksw_ll_qinit(0, 2, qlen, q, m, mat);

@@ -167,6 +167,21 @@ def make_vectors():
         v["ll%d_q" % i] = q; v["ll%d_t" % i] = t
         v["ll%d_res" % i] = np.array([sc, qe, te], dtype=np.int32)
     v["ll_n"] = np.array([12], dtype=np.int32)
+    # ---- ksw_exts2_sse (spliced alignment; checker for the next hot-path row) ----
+    from test_oracle_vs_ref import _spliced_pair
+    smat = O.simple_mat(1, 2, 1)
+    sflags = [0x100, 0x200 | 0x400, 0x100 | 0x08, 0x100 | 0x40, 0x200 | 0x40 | 0x02 | 0x80, 0x100 | 0x800, 0x100 | 0x02, 0x200 | 0x01]
+    for i in range(24):
+        q, t = _spliced_pair(rng, int(rng.integers(1, 5)), float(rng.choice([0.0, 0.03, 0.1])))
+        fl = sflags[i % len(sflags)]
+        zdrop = int(rng.choice([-1, 200])); end_bonus = int(rng.choice([-1, 10]))
+        r = O.ref_exts2(q, t, smat, 2, 1, 32, 9, zdrop, end_bonus, 9, 5, fl)
+        v["sp%d_q" % i] = q; v["sp%d_t" % i] = t
+        v["sp%d_par" % i] = np.array([zdrop, end_bonus, fl], dtype=np.int32)
+        v["sp%d_res" % i] = np.array([r["max"], r["zdropped"], r["max_q"], r["max_t"], r["mqe"], r["mqe_t"], r["mte"], r["mte_q"], r["score"], r["reach_end"]], dtype=np.int64)
+        v["sp%d_cig" % i] = np.array(r["cigar"], dtype=np.uint32)
+    v["sp_n"] = np.array([24], dtype=np.int32)
+    v["sp_mat"] = np.asarray(smat, dtype=np.int8)
     np.savez_compressed(os.path.join(HERE, "vectors.npz"), **v)
     print("vectors.npz: %d arrays" % len(v))
 

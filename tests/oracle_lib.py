@@ -233,3 +233,33 @@ def mutate(seq: np.ndarray, rng, err=0.1, sub=0.4, ins=0.25, dele=0.35):
         else:
             out.append(int(seq[i]))
     return np.array(out, dtype=np.uint8)
+
+
+# ---------------- ksw_exts2 (splice): oracle restatement and reference ----------------
+def _exts2_args(q, t, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus, junc_pen, flag, junc, i8):
+    q = np.ascontiguousarray(q, dtype=np.uint8); t = np.ascontiguousarray(t, dtype=np.uint8)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    T = C.c_int8 if i8 else C.c_int
+    jp = None if junc is None else np.ascontiguousarray(junc, dtype=np.uint8)
+    args = [C.c_int(len(q)), q.ctypes.data_as(C.c_void_p), C.c_int(len(t)), t.ctypes.data_as(C.c_void_p), T(5), mat.ctypes.data_as(C.c_void_p),
+            T(gapo), T(gape), T(gapo2), T(noncan), C.c_int(zdrop), C.c_int(end_bonus), T(junc_bonus), T(junc_pen), C.c_int(flag),
+            C.c_void_p(0) if jp is None else jp.ctypes.data_as(C.c_void_p)]
+    return args, (q, t, mat, jp)
+
+
+def oracle_exts2(q, t, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus, junc_pen, flag, junc=None):
+    ez = OracleEz()
+    args, keep = _exts2_args(q, t, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus, junc_pen, flag, junc, False)
+    oracle().mm2o_exts2(*args, C.byref(ez))
+    d = ez_dict(ez, False)
+    oracle().mm2o_free(ez.cigar)
+    return d
+
+
+def ref_exts2(q, t, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus, junc_pen, flag, junc=None):
+    ez = RefEz()
+    args, keep = _exts2_args(q, t, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus, junc_pen, flag, junc, True)
+    ref().refshim_exts2(*args, C.byref(ez))
+    d = ez_dict(ez, True)
+    ref().refshim_free(ez.cigar)
+    return d

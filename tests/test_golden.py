@@ -77,3 +77,14 @@ def test_oracle_lchain_rmq_matches_golden(V):
         u, b = O.oracle_lchain_rmq(V["ch%d_a" % i], *par, pg, ps)
         assert len(u) == len(V["rq%d_u" % i]) and (u == V["rq%d_u" % i]).all(), i
         assert b.shape == V["rq%d_b" % i].shape and (b == V["rq%d_b" % i]).all(), i
+
+
+def test_oracle_exts2_matches_golden(V):
+    """ksw_exts2_sse (splice) restatement vs recorded reference outputs: gap open 2, ext 1, intron open 32, non-canonical 9"""
+    mat = V["sp_mat"]
+    for i in range(int(V["sp_n"][0])):
+        zdrop, end_bonus, flag = [int(x) for x in V["sp%d_par" % i]]
+        r = O.oracle_exts2(V["sp%d_q" % i], V["sp%d_t" % i], mat, 2, 1, 32, 9, zdrop, end_bonus, 9, 5, flag)
+        for k, e in zip(KEYS, V["sp%d_res" % i]):
+            assert r[k] == int(e), (i, k, r[k], int(e), hex(flag))
+        assert r["cigar"] == [int(x) for x in V["sp%d_cig" % i]], i

@@ -184,3 +184,50 @@ def test_extz2_is_extd2_with_equal_gaps():
         x = _ref_extz2(q, t, mat, go, ge, w, zd, eb, fl)
         assert x == O.ref_extd2(q, t, mat, go, ge, go, ge, w, zd, eb, fl), (it, fl)
         assert x == O.oracle_extd2(q, t, mat, go, ge, go, ge, w, zd, eb, fl), (it, fl)
+
+
+def _spliced_pair(rng, n_exon, err):
+    """target = exons separated by introns with (mostly) canonical GT..AG ends; query = the exons with errors"""
+    ex = [rng.integers(0, 4, int(rng.integers(20, 120))).astype(np.uint8) for _ in range(n_exon)]
+    t_parts = [ex[0]]
+    for k in range(1, n_exon):
+        il = int(rng.integers(30, 400))
+        intron = rng.integers(0, 4, il).astype(np.uint8)
+        sig = int(rng.integers(0, 5))
+        if sig < 3: intron[:2] = [2, 3]; intron[-2:] = [0, 2]      # GT..AG
+        elif sig == 3: intron[:2] = [2, 1]; intron[-2:] = [0, 2]    # GC..AG
+        t_parts += [intron, ex[k]]
+    t = np.concatenate(t_parts)
+    q = O.mutate(np.concatenate(ex), rng, err=err)
+    if len(q) == 0:
+        q = np.array([0], dtype=np.uint8)
+    return q, t
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_exts2_splice(seed):
+    """ksw_exts2_sse (spliced alignment) restatement vs the reference: splice models, strands, reversed (left-extension)
+    inputs, gap left/right alignment, extension mode, approximate max, annotated junctions and junction scores"""
+    rng = np.random.default_rng(300 + seed)
+    SPF, SPR, FLANK, CMPLX, SPSC = 0x100, 0x200, 0x400, 0x800, 0x1000
+    base_flags = [0, 0x08, 0x40, 0x40 | 0x02 | 0x80, 0x02, 0x01, 0x80, 0x40 | 0x80]
+    for it in range(220):
+        q, t = _spliced_pair(rng, int(rng.integers(1, 5)), float(rng.choice([0.0, 0.03, 0.1])))
+        if rng.random() < 0.15:
+            q[rng.integers(0, len(q))] = 4
+        if rng.random() < 0.3:  # reverse-complement both: the signals of the other transcript strand
+            q = (3 - q[::-1]) % 4 if (q < 4).all() else q
+            t = 3 - t[::-1]
+        fl = int(rng.choice(base_flags)) | int(rng.choice([0, SPF, SPR])) | (FLANK if rng.random() < 0.5 else 0) | (CMPLX if rng.random() < 0.3 else 0)
+        a, b, go, ge, go2, noncan = [(1, 2, 2, 1, 32, 9), (2, 4, 4, 2, 24, 5), (1, 2, 2, 1, 16, 0)][it % 3]
+        mat = O.simple_mat(a, b, 1)
+        zd = int(rng.choice([-1, 100, 200])); eb = int(rng.choice([-1, 0, 10]))
+        junc = None; jb = 9; jp = 5
+        if rng.random() < 0.4:
+            junc = (rng.random(len(t)) < 0.03).astype(np.uint8) * rng.integers(1, 16, len(t)).astype(np.uint8)
+            if rng.random() < 0.5:
+                fl |= SPSC
+                junc = np.where(rng.random(len(t)) < 0.05, rng.integers(0, 200, len(t)), 0xff).astype(np.uint8)
+        x = O.oracle_exts2(q, t, mat, go, ge, go2, noncan, zd, eb, jb, jp, fl, junc)
+        y = O.ref_exts2(q, t, mat, go, ge, go2, noncan, zd, eb, jb, jp, fl, junc)
+        assert x == y, (it, hex(fl), len(q), len(t), {k: (x[k], y[k]) for k in x if x[k] != y[k] and k != "cigar"}, x["cigar"][:8], y["cigar"][:8])

@@ -263,3 +263,36 @@ def ref_exts2(q, t, mat, gapo, gape, gapo2, noncan, zdrop, end_bonus, junc_bonus
     d = ez_dict(ez, True)
     ref().refshim_free(ez.cigar)
     return d
+
+
+# ---------------- seeding stage (oracle index + anchors) ----------------
+class OracleIndex:
+    def __init__(self, seqs, names, w, k, is_hpc=0):
+        L = oracle()
+        L.mm2o_idx_build.restype = C.c_void_p
+        n = len(seqs)
+        self._seqs = [s if isinstance(s, bytes) else bytes(s) for s in seqs]
+        arr = (C.c_char_p * n)(*self._seqs)
+        lens = (C.c_int * n)(*[len(s) for s in self._seqs])
+        nm = (C.c_char_p * n)(*[x.encode() for x in names])
+        self.names = list(names)
+        self.h = C.c_void_p(L.mm2o_idx_build(n, arr, lens, nm, w, k, is_hpc))
+
+    def anchors(self, seq, qname=None, flag=0, mid_occ=10, q_occ_frac=0.01, max_max_occ=4095, occ_dist=500):
+        L = oracle()
+        L.mm2o_collect_seed_hits.restype = C.c_int64
+        a = C.POINTER(M128)(); mp = C.POINTER(C.c_uint64)(); rep = C.c_int(0); nmp = C.c_int(0)
+        s = seq if isinstance(seq, bytes) else bytes(seq)
+        n = L.mm2o_collect_seed_hits(self.h, None if qname is None else qname.encode(), s, C.c_int(len(s)), C.c_int64(flag), C.c_int(mid_occ),
+                                     C.c_float(q_occ_frac), C.c_int(max_max_occ), C.c_int(occ_dist), C.byref(a), C.byref(rep), C.byref(nmp), C.byref(mp))
+        out = np.zeros((n, 2), dtype=np.uint64)
+        if n:
+            C.memmove(out.ctypes.data, a, n * 16)
+        mini = np.array([mp[i] for i in range(nmp.value)], dtype=np.uint64)
+        L.mm2o_free(a); L.mm2o_free(mp)
+        return out, rep.value, mini
+
+    def close(self):
+        if self.h:
+            oracle().mm2o_idx_destroy(self.h)
+            self.h = None

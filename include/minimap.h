@@ -277,7 +277,9 @@ int mm_map_file(const mm_idx_t *idx, const char *fn, const mm_mapopt_t *opt, int
 int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads); /* minimap.h:395 */
 
 /* B200 extension (not in the reference): map a whole in-memory batch through the GPU scheduler. seqs[i]/names[i]
- * are NUL-terminated; regs_out[i] / n_regs_out[i] follow mm_map()'s ownership rules; rep_len_out may be NULL. */
+ * are NUL-terminated; regs_out[i] / n_regs_out[i] follow mm_map()'s ownership rules; rep_len_out may be NULL.
+ * Thread-safe: concurrent callers are served one batch at a time (the scheduler's streams and arenas are process-wide);
+ * mm_map()/mm_map_frag() are batches of one and share that queue. */
 int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
 				 int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads);
 

@@ -640,6 +640,8 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
 {
 	if (n_reads <= 0) return 0;
+	static std::mutex batch_mu; // the scheduler groups (streams, arenas) are process-wide: concurrent callers take turns
+	std::lock_guard<std::mutex> batch_lk(batch_mu);
 	g_batch_t0 = realtime();
 	unsupported_check(mi, opt);
 	static int ng_env = getenv("MM_B200_GROUPS")? atoi(getenv("MM_B200_GROUPS")) : 12;

@@ -332,6 +332,13 @@ def main():
                 "note": "ALU-bound by construction: ~%.0f DP cells per read base at 1 B/cell traceback; HBM fraction is expected to be small (SURVEY 8d)" % (k["units"] / max(1.0, tot_bases_a / max(1, world) * n_prof)),
                 "stage_ms_per_step": {nm: prof[nm]["ms"] / n_prof for nm in prof},
                 "timing": "CUDA events on the launch stream, %d profiled steps with the scheduler's read groups serialised" % n_prof}
+    try:  # per-stage algorithmic bandwidth (DESIGN.md section 3 definitions); informational, never allowed to break the line
+        roofline["stages"] = {nm: {"ms_per_step": prof[nm]["ms"] / n_prof, "algorithmic_gb_per_step": prof[nm]["bytes"] / n_prof / 1e9,
+                                   "gb_per_s": (prof[nm]["bytes"] / 1e9) / (prof[nm]["ms"] / 1e3) if prof[nm]["ms"] > 0 else 0.0,
+                                   "frac_of_hbm_peak": ((prof[nm]["bytes"] / 1e9) / (prof[nm]["ms"] / 1e3) / peak) if prof[nm]["ms"] > 0 and peak else 0.0}
+                              for nm in ("sketch", "seed", "sort", "chain", "ksw")}
+    except Exception:
+        pass
     tp = os.path.join(ROOT, "profiles", "ksw_traffic.json")
     if os.path.exists(tp):
         try:

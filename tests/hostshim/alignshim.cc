@@ -1,0 +1,105 @@
+// tests/hostshim/alignshim.cc -- TEST INFRASTRUCTURE: runs the product's replayable alignment driver (minimap2_b200/csrc/align.cc,
+// the restatement of mm_align_skeleton / mm_align1 / mm_align1_inv, align.c:645-1120) on the CPU, with the oracle's ksw2
+// (oracle/mm2o_ksw2.c) standing in for the GPU as the executor of the ksw jobs the driver requests -- the same wave/replay
+// protocol as csrc/map.cu. tests/test_aligndriver_vs_ref.py compares the result with the reference's mm_align_skeleton on the
+// same chains, so the driver logic is checked without a GPU and independently of the CUDA kernels.
+#include "hostlogic.h"
+#include "../../oracle/mm2o.h"
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+extern "C" {
+extern int mm_verbose;
+
+// mm_idx_getseq on the public part of mm_idx_t (index.c:164-175): the product's own lives in csrc/index.cu (CUDA file)
+int mm_idx_getseq(const mm_idx_t *mi, uint32_t rid, uint32_t st, uint32_t en, uint8_t *seq)
+{
+	if (rid >= mi->n_seq || st >= mi->seq[rid].len) return -1;
+	if (en > mi->seq[rid].len) en = mi->seq[rid].len;
+	const uint64_t st1 = mi->seq[rid].offset + st, en1 = mi->seq[rid].offset + en;
+	for (uint64_t i = st1; i < en1; ++i) seq[i - st1] = (uint8_t)mmx_seq4_get(mi->S, i);
+	return (int)(en - st);
+}
+
+static uint8_t nt4_of(uint8_t c) { return mmx_nt4(c); }
+
+// Executes one requested job with the oracle; the CIGAR is kept alive in `store`.
+static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t *mat, const uint8_t *q_fwd, int64_t q_dev_off, const mmb_ksw_job_t &j,
+					   std::vector<uint32_t*> &store)
+{
+	std::vector<uint8_t> q(j.qlen > 0? j.qlen : 0), t(j.tlen > 0? j.tlen : 0);
+	for (int i = 0; i < j.qlen; ++i) {
+		uint8_t c = q_fwd[j.q_start - q_dev_off + (int64_t)i * j.q_step];
+		if ((j.flag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
+		q[i] = c;
+	}
+	for (int i = 0; i < j.tlen; ++i) t[i] = (uint8_t)mmx_seq4_get(mi->S, (uint64_t)(j.t_start + (int64_t)i * j.t_step));
+	KswDone d;
+	memset(&d, 0, sizeof(d));
+	d.r.zd_max = -1; // the scan of mm_test_zdrop is left to the driver (host path)
+	if (j.flag & MMB_JOB_LL) {
+		int qe = -1, te = -1;
+		d.r.score = mm2o_ll_i16(j.qlen, q.data(), j.tlen, t.data(), 5, mat, j.w, j.zdrop, &qe, &te);
+		d.r.max_q = qe, d.r.max_t = te;
+		d.cig = nullptr;
+		return d;
+	}
+	mm2o_ez_t ez;
+	memset(&ez, 0, sizeof(ez));
+	mm2o_extd2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->e2, j.w, j.zdrop, j.end_bonus, j.flag & 0xff, &ez);
+	d.r.max = ez.max, d.r.zdropped = ez.zdropped, d.r.max_q = ez.max_q, d.r.max_t = ez.max_t, d.r.mqe = ez.mqe, d.r.mqe_t = ez.mqe_t;
+	d.r.mte = ez.mte, d.r.mte_q = ez.mte_q, d.r.score = ez.score, d.r.n_cigar = ez.n_cigar, d.r.reach_end = ez.reach_end;
+	d.cig = ez.cigar;
+	store.push_back(ez.cigar);
+	return d;
+}
+
+// regs: libc-malloc'd array of n_regs hits (after chain post-processing), a: their anchors. Returns the aligned hits.
+mm_reg1_t *hs_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, int qlen, const char *qstr, int *n_regs_, const mm_reg1_t *regs0, int n_a, const m128 *a0,
+							 int *n_waves)
+{
+	int8_t mat[25];
+	{ // align.c:11-38 for m = 5
+		const int8_t a = (int8_t)(opt->a < 0? -opt->a : opt->a), b = (int8_t)(opt->b > 0? -opt->b : opt->b), sa = (int8_t)(opt->sc_ambi > 0? -opt->sc_ambi : opt->sc_ambi);
+		for (int i = 0; i < 4; ++i) { for (int k = 0; k < 4; ++k) mat[i * 5 + k] = i == k? a : b; mat[i * 5 + 4] = sa; }
+		for (int k = 0; k < 5; ++k) mat[20 + k] = sa;
+		if (!(opt->transition == 0 || opt->transition == opt->b)) {
+			const int8_t t = (int8_t)(opt->transition > 0? -opt->transition : opt->transition);
+			mat[0 * 5 + 2] = t, mat[1 * 5 + 3] = t, mat[2 * 5 + 0] = t, mat[3 * 5 + 1] = t;
+		}
+	}
+	std::vector<uint8_t> qf(qlen), qr(qlen);
+	for (int i = 0; i < qlen; ++i) { const uint8_t c = nt4_of((uint8_t)qstr[i]); qf[i] = c, qr[qlen - 1 - i] = c < 4? 3 - c : 4; }
+	ReadAlign ra;
+	ra.reset();
+	ra.qlen = qlen, ra.q_dev_off = 1000, ra.qseq[0] = qf.data(), ra.qseq[1] = qr.data(); // any offset: jobs address the query through it
+	std::vector<uint32_t*> store;
+	std::vector<m128> a(n_a);
+	mm_reg1_t *out = nullptr;
+	int n_out = 0;
+	for (int wave = 0;; ++wave) {
+		if (wave > 16) abort();
+		ra.want.clear(); ra.want_slot.clear();
+		ra.incomplete = false;
+		memcpy(a.data(), a0, sizeof(m128) * n_a);
+		int n_regs = *n_regs_;
+		mm_reg1_t *regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
+		memcpy(regs, regs0, sizeof(mm_reg1_t) * n_regs);
+		regs = hl_align_skeleton(opt, mi, ra, &n_regs, regs, n_a, a.data());
+		if (!ra.incomplete) { out = regs, n_out = n_regs; if (n_waves) *n_waves = wave; break; }
+		for (int i = 0; i < n_regs; ++i) free(regs[i].p);
+		free(regs);
+		if (ra.want.empty()) abort(); // no progress
+		for (size_t i = 0; i < ra.want.size(); ++i) {
+			KswDone d = run_job(opt, mi, mat, qf.data(), ra.q_dev_off, ra.want[i], store);
+			ra.done_idx[ra.want_slot[i]] = (int)ra.done.size();
+			ra.done.push_back(d);
+		}
+	}
+	for (uint32_t *c : store) free(c);
+	*n_regs_ = n_out;
+	return out;
+}
+void hs_free_regs(int n, mm_reg1_t *r) { for (int i = 0; i < n; ++i) free(r[i].p); free(r); }
+}

@@ -1,0 +1,156 @@
+"""CPU: the product's alignment driver (minimap2_b200/csrc/align.cc: mm_align_skeleton / mm_align1 / mm_align1_inv restated as a
+replayable routine) against the reference's mm_align_skeleton on identical chains. The ksw2 jobs the driver requests are
+executed by the oracle's ksw2 (tests/hostshim/alignshim.cc plays the GPU's role), so this checks the driver logic -- window
+selection, gap-fill two-pass rule, z-drop splits, inversion probes, CIGAR assembly, statistics, filters -- without a GPU and
+independently of the CUDA kernels. Compared: every field of every mm_reg1_t and of its mm_extra_t, CIGAR included."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+import pytest
+import oracle_lib as O
+import synth
+from test_hostlogic_vs_ref import Idx, REG_SIZE
+
+ROOT = O.ROOT
+SHIM = os.path.join(ROOT, "tests", "hostshim", "_build", "libalignshim.so")
+pytestmark = pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref not built")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    from minimap2_b200 import api
+    O.build_oracle() if hasattr(O, "build_oracle") else None
+    os.makedirs(os.path.dirname(SHIM), exist_ok=True)
+    csrc = os.path.join(ROOT, "minimap2_b200", "csrc")
+    src = [os.path.join(csrc, "align.cc"), os.path.join(csrc, "hits.cc"), os.path.join(ROOT, "tests", "hostshim", "hostshim.cc"),
+           os.path.join(ROOT, "tests", "hostshim", "alignshim.cc")]
+    if not os.path.exists(SHIM) or any(os.path.getmtime(s) > os.path.getmtime(SHIM) for s in src):
+        inc = ["-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-I/usr/local/cuda/include"]
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared"] + inc + src +
+                              ["-L" + O.ORACLE_DIR, "-lmm2oracle", "-Wl,-rpath," + O.ORACLE_DIR, "-o", SHIM])
+    H = C.CDLL(SHIM)
+    R = O.ref()
+    H.hs_align_skeleton.restype = C.c_void_p
+    R.mm_align_skeleton.restype = C.c_void_p
+    R.mm_gen_regs.restype = C.c_void_p
+    R.mm_idx_str.restype = C.POINTER(Idx)
+    return H, R, api
+
+
+def build_ref_index(R, contigs, names, w=10, k=15):
+    n = len(contigs)
+    seqs = (C.c_char_p * n)(*[bytes(c) for c in contigs])
+    nms = (C.c_char_p * n)(*[x.encode() for x in names])
+    return R.mm_idx_str(w, k, 0, 14, n, seqs, nms), (seqs, nms)
+
+
+def extra_of(reg_ptr, i):
+    """(header ints, cigar list) of regs[i].p, or None"""
+    p = C.cast(C.c_void_p(reg_ptr + i * REG_SIZE + 72), C.POINTER(C.c_void_p))[0]
+    if not p:
+        return None
+    hdr = (C.c_uint32 * 7).from_address(p)
+    n_cigar = hdr[6]
+    cig = (C.c_uint32 * n_cigar).from_address(p + 28)
+    return (tuple(hdr[1:7]), list(cig))
+
+
+def run_case(H, R, api, contigs, names, reads, preset="map-ont"):
+    mi, keep = build_ref_index(R, contigs, names)
+    io, mo = api.IdxOpt(), api.MapOpt()
+    R.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
+    R.mm_set_opt(None, C.byref(io), C.byref(mo)); R.mm_set_opt(preset.encode(), C.byref(io), C.byref(mo))
+    mo.flag |= api.MM_F_CIGAR
+    mo.mid_occ = 50
+    R.mm_mapopt_update(C.byref(mo), mi)
+    oidx = O.OracleIndex([bytes(c) for c in contigs], names, 10, 15)
+    pg = float(np.float32(mo.chain_gap_scale * 0.01 * 15))
+    n_checked = n_split = 0
+    for qi, rd in enumerate(reads):
+        qstr = bytes(rd); qlen = len(qstr)
+        a, rep, mini = oidx.anchors(qstr, mid_occ=mo.mid_occ, q_occ_frac=mo.q_occ_frac, max_max_occ=mo.max_max_occ, occ_dist=mo.occ_dist)
+        if len(a) == 0:
+            continue
+        u, b = O.ref_lchain_dp(a, mo.max_gap, mo.max_gap, mo.bw, mo.max_chain_skip, mo.max_chain_iter, mo.min_cnt, mo.min_chain_score, pg, 0.0)
+        if len(u) == 0:
+            continue
+        n = len(u)
+        uu = u.copy(); bb = np.ascontiguousarray(b.copy())
+        hash_ = 12345 + qi
+        regs0 = R.mm_gen_regs(None, C.c_uint32(hash_), qlen, n, uu.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p), 0)
+        R.mm_set_parent(None, C.c_float(mo.mask_level), mo.mask_len, n, C.c_void_p(regs0), mo.a * 2 + mo.b, 0, C.c_float(mo.alt_drop))
+        nn = C.c_int(n)
+        R.mm_select_sub(None, C.c_float(mo.pri_ratio), 30, mo.best_n, 1, int(mo.max_gap * 0.8), C.byref(nn), C.c_void_p(regs0))
+        n0 = R.mm_filter_strand_retained(nn.value, C.c_void_p(regs0))
+        snap = C.string_at(regs0, n0 * REG_SIZE)
+        # mine first (inputs are const), then the reference (consumes regs0 and rewrites the anchors)
+        nm = C.c_int(n0); waves = C.c_int(0)
+        a_mine = np.ascontiguousarray(bb.copy())
+        pm = H.hs_align_skeleton(C.byref(mo), mi, qlen, qstr, C.byref(nm), snap, len(a_mine), a_mine.ctypes.data_as(C.c_void_p), C.byref(waves))
+        nr = C.c_int(n0)
+        a_ref = np.ascontiguousarray(bb.copy())
+        pr = R.mm_align_skeleton(None, C.byref(mo), mi, qlen, qstr, C.byref(nr), C.c_void_p(regs0), a_ref.ctypes.data_as(C.c_void_p))
+        assert nm.value == nr.value, (qi, nm.value, nr.value)
+        for i in range(nr.value):
+            x = C.string_at(pm + i * REG_SIZE, 72); y = C.string_at(pr + i * REG_SIZE, 72)
+            assert x == y, (qi, i, np.frombuffer(x, dtype=np.int32), np.frombuffer(y, dtype=np.int32))
+            assert extra_of(pm, i) == extra_of(pr, i), (qi, i)
+        n_checked += 1
+        n_split += nr.value > n0
+        H.hs_free_regs(nm.value, C.c_void_p(pm))
+    oidx.close()
+    return n_checked, n_split
+
+
+def test_driver_on_synthetic_ont(libs):
+    H, R, api = libs
+    contigs = synth.random_genome(250_000, 17, n_contigs=2, repeat_frac=0.15)
+    reads = synth.make_reads(contigs, 50, 3000, 0.10, 117, chimeric_frac=0.15)
+    n, _ = run_case(H, R, api, contigs, ["chr0", "chr1"], reads)
+    assert n >= 40
+
+
+def test_driver_on_inversion_pair(libs):
+    """test/t-inv.fa + q-inv.fa of the reference: z-drop split and mm_align1_inv (the ksw_ll_i16 probe)"""
+    H, R, api = libs
+
+    def fa(path):
+        seqs, names = [], []
+        for l in open(path):
+            if l.startswith(">"):
+                names.append(l[1:].split()[0]); seqs.append([])
+            else:
+                seqs[-1].append(l.strip())
+        return names, [("".join(s)).encode() for s in seqs]
+    data = os.path.join(ROOT, "tests", "golden", "data")
+    tn, ts = fa(os.path.join(data, "t-inv.fa")); qn, qs = fa(os.path.join(data, "q-inv.fa"))
+    n, _ = run_case(H, R, api, ts, tn, qs)
+    assert n == len(qs)
+
+
+def test_driver_on_structural_variants(libs):
+    """reads with junk insertions, long deletions and inverted segments: z-drop splits (mm_test_zdrop, second exact pass), region
+    splitting and the inversion probe on synthetic data"""
+    H, R, api = libs
+    rng = np.random.default_rng(5)
+    contigs = synth.random_genome(200_000, 23, n_contigs=1, repeat_frac=0.05)
+    g = np.frombuffer(bytes(contigs[0]), dtype=np.uint8)
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for i in range(40):
+        s = int(rng.integers(1000, len(g) - 12000))
+        left = g[s:s + 2500]
+        kind = i % 4
+        if kind == 0:    # junk insertion
+            mid = synth.ALPHA[rng.integers(0, 4, int(rng.integers(300, 900)))]; right = g[s + 2500:s + 5000]
+        elif kind == 1:  # long deletion in the read (reference has extra sequence)
+            mid = np.zeros(0, dtype=np.uint8); right = g[s + 2500 + int(rng.integers(1500, 6000)):][:2500]
+        elif kind == 2:  # inverted segment
+            seg = g[s + 2500:s + 2500 + int(rng.integers(300, 1200))]; mid = comp[seg[::-1]]; right = g[s + 2500 + len(seg):][:2500]
+        else:            # plain
+            mid = np.zeros(0, dtype=np.uint8); right = g[s + 2500:s + 5000]
+        rd = np.concatenate([left, mid, right])
+        reads.append(synth.mutate_ascii(rd, rng, 0.06))
+    n, n_split = run_case(H, R, api, contigs, ["chr0"], reads)
+    assert n >= 35 and n_split >= 3, (n, n_split)

@@ -103,3 +103,26 @@ mm_reg1_t *hs_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, int qle
 }
 void hs_free_regs(int n, mm_reg1_t *r) { for (int i = 0; i < n; ++i) free(r[i].p); free(r); }
 }
+
+// ---- formatting (csrc/format.cc) next to the reference's format.c ----
+extern "C" {
+// writes the PAF line of regs[j] (or the SAM record) into buf (capacity cap); returns the length
+int hs_write_paf(char *buf, int cap, const mm_idx_t *mi, const char *qname, const char *seq, int qlen, const mm_reg1_t *r, int64_t opt_flag, int rep_len)
+{
+	std::string s;
+	hl_set_seq_for_tags(seq);
+	hl_write_paf(s, mi, qname, qlen, r, opt_flag, rep_len);
+	if ((int)s.size() >= cap) return -1;
+	memcpy(buf, s.data(), s.size()); buf[s.size()] = 0;
+	return (int)s.size();
+}
+int hs_write_sam(char *buf, int cap, const mm_idx_t *mi, const char *qname, const char *seq, const char *qual, int qlen, int reg_idx, int n_regs,
+				 const mm_reg1_t *regs, int64_t opt_flag, int rep_len)
+{
+	std::string s;
+	hl_write_sam(s, mi, qname, seq, qual, qlen, reg_idx, n_regs, regs, opt_flag, rep_len);
+	if ((int)s.size() >= cap) return -1;
+	memcpy(buf, s.data(), s.size()); buf[s.size()] = 0;
+	return (int)s.size();
+}
+}

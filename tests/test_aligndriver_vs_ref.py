@@ -23,7 +23,7 @@ def libs():
     O.build_oracle() if hasattr(O, "build_oracle") else None
     os.makedirs(os.path.dirname(SHIM), exist_ok=True)
     csrc = os.path.join(ROOT, "minimap2_b200", "csrc")
-    src = [os.path.join(csrc, "align.cc"), os.path.join(csrc, "hits.cc"), os.path.join(ROOT, "tests", "hostshim", "hostshim.cc"),
+    src = [os.path.join(csrc, "align.cc"), os.path.join(csrc, "hits.cc"), os.path.join(csrc, "format.cc"), os.path.join(ROOT, "tests", "hostshim", "hostshim.cc"),
            os.path.join(ROOT, "tests", "hostshim", "alignshim.cc")]
     if not os.path.exists(SHIM) or any(os.path.getmtime(s) > os.path.getmtime(SHIM) for s in src):
         inc = ["-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-I/usr/local/cuda/include"]
@@ -54,6 +54,41 @@ def extra_of(reg_ptr, i):
     n_cigar = hdr[6]
     cig = (C.c_uint32 * n_cigar).from_address(p + 28)
     return (tuple(hdr[1:7]), list(cig))
+
+
+class KString(C.Structure):
+    _fields_ = [("l", C.c_size_t), ("m", C.c_size_t), ("s", C.c_void_p)]
+
+
+class BSeq1(C.Structure):  # mm_bseq1_t (bseq.h:13-17)
+    _fields_ = [("l_seq", C.c_int), ("rid", C.c_int), ("name", C.c_char_p), ("seq", C.c_char_p), ("qual", C.c_char_p), ("comment", C.c_char_p)]
+
+
+F_OUT_SAM, F_OUT_CG, F_OUT_CS, F_OUT_MD, F_OUT_CS_LONG = 0x008, 0x020, 0x040, 0x1000000, 0x800  # minimap.h:26-47
+
+
+def compare_formats(H, R, api, mi, qname, qstr, n, pm, pr, rep_len, flag):
+    """format.cc vs format.c on the aligned hits: PAF with cg/cs/MD tags and SAM records (incl. SA tags, clipping)"""
+    t = BSeq1(len(qstr), 0, qname.encode(), qstr, None, None)
+    buf = C.create_string_buffer(1 << 20)
+    for extra in (0, F_OUT_CG, F_OUT_CG | F_OUT_CS | F_OUT_MD, F_OUT_CS | F_OUT_CS_LONG):
+        fl = (flag | extra)
+        for j in range(n):
+            ks = KString(0, 0, None)
+            R.mm_write_paf3(C.byref(ks), mi, C.byref(t), C.c_void_p(pr + j * REG_SIZE), None, C.c_int64(fl), C.c_int(rep_len))
+            ref_line = C.string_at(ks.s, ks.l)
+            R.refshim_free(C.c_void_p(ks.s))
+            ln = H.hs_write_paf(buf, len(buf), mi, qname.encode(), qstr, len(qstr), C.c_void_p(pm + j * REG_SIZE), C.c_int64(fl), C.c_int(rep_len))
+            assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, hex(extra), ref_line[:300], buf.raw[:min(ln, 300)])
+    fl = flag | F_OUT_SAM | F_OUT_MD
+    n_arr = (C.c_int * 1)(n); regs_arr = (C.c_void_p * 1)(pr)
+    for j in range(n):
+        ks = KString(0, 0, None)
+        R.mm_write_sam3(C.byref(ks), mi, C.byref(t), 0, j, 1, n_arr, regs_arr, None, C.c_int64(fl), C.c_int(rep_len))
+        ref_line = C.string_at(ks.s, ks.l)
+        R.refshim_free(C.c_void_p(ks.s))
+        ln = H.hs_write_sam(buf, len(buf), mi, qname.encode(), qstr, None, len(qstr), j, n, C.c_void_p(pm), C.c_int64(fl), C.c_int(rep_len))
+        assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, ref_line[:300], buf.raw[:min(ln, 300)])
 
 
 def run_case(H, R, api, contigs, names, reads, preset="map-ont"):
@@ -96,6 +131,7 @@ def run_case(H, R, api, contigs, names, reads, preset="map-ont"):
             x = C.string_at(pm + i * REG_SIZE, 72); y = C.string_at(pr + i * REG_SIZE, 72)
             assert x == y, (qi, i, np.frombuffer(x, dtype=np.int32), np.frombuffer(y, dtype=np.int32))
             assert extra_of(pm, i) == extra_of(pr, i), (qi, i)
+        compare_formats(H, R, api, mi, "read%d" % qi, qstr, nr.value, pm, pr, rep, mo.flag)
         n_checked += 1
         n_split += nr.value > n0
         H.hs_free_regs(nm.value, C.c_void_p(pm))

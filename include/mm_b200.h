@@ -47,9 +47,15 @@ uint64_t mmb_profile_units(mmb_ctx_t *ctx, int which, int reset); /* algorithmic
 #define MMB_KSW_APPROX_DROP  0x10
 #define MMB_KSW_EXTZ_ONLY    0x40
 #define MMB_KSW_REV_CIGAR    0x80
+#define MMB_KSW_SPLICE_FOR   0x100  /* spliced alignment (ksw_exts2_sse, ksw2_exts2_sse.c:26): KSW_EZ_SPLICE_* of ksw2.h:15-19 */
+#define MMB_KSW_SPLICE_REV   0x200
+#define MMB_KSW_SPLICE_FLANK 0x400
+#define MMB_KSW_SPLICE_CMPLX 0x800
+#define MMB_KSW_SPLICE_SCORE 0x1000
 /* job-level addressing flags (how the kernel walks the resident sequences) */
 #define MMB_JOB_Q_COMP       0x10000 /* complement query bases (3-c, N stays 4): reverse strand (align.c:1056-1061) */
 #define MMB_JOB_LL           0x20000 /* run ksw_ll_i16 (local score) instead of extd2 */
+#define MMB_JOB_SPLICE       0x80000 /* the job is a ksw_exts2 call (align.c:352-355). No CUDA kernel runs it yet: mm_map* refuses -x splice */
 #define MMB_JOB_ZDROP        0x40000 /* also run mm_test_zdrop's scan over the resulting CIGAR (align.c:61-89); see zd_* below */
 
 typedef struct {

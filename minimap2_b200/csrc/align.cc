@@ -111,6 +111,10 @@ struct Driver {
 	// ksw_extd2_sse(q,e,q,e) return identical ksw_extz_t and CIGARs (tests/test_oracle_vs_ref.py::test_extz2_is_extd2_with_equal_gaps).
 	bool align_pair(const Seg &s, int w, int end_bonus, int zdrop, int ksw_flag, Ez *ez) {
 		if (opt->transition != 0 && opt->b != opt->transition) ksw_flag |= MMB_KSW_GENERIC_SC;
+		if (opt->flag & MM_F_SPLICE) { // ksw_exts2 (align.c:352-355): the splice-model bits travel in the job flag
+			ksw_flag |= MMB_JOB_SPLICE;
+			if (!(opt->flag & MM_F_SPLICE_OLD)) ksw_flag |= MMB_KSW_SPLICE_CMPLX;
+		}
 		if (opt->max_sw_mat > 0 && (int64_t)s.tlen * s.qlen > opt->max_sw_mat) {
 			ez_reset(ez);
 			ez->zdropped = 1;
@@ -523,8 +527,39 @@ struct Driver {
 		}
 	}
 
-	// ---- mm_align1 (align.c:645-914), genomic long-read path. Returns false if some ksw result is still pending. ----
-	bool align1(mm_reg1_t *r, mm_reg1_t *r2, int n_a, m128 *a) {
+	// mm_seed_ext_score (align.c:592-616): local score of the anchor extended by anchor_ext_len on both sides. False while pending.
+	bool seed_ext_score(const m128 *a, int *score) {
+		const int q_span = (int)(a->y >> 32 & 0xff), ext_len = opt->anchor_ext_len, rid = (int)(a->x << 1 >> 33);
+		int re = (int)(uint32_t)a->x + 1, rs = re - q_span, qe = (int)(uint32_t)a->y + 1, qs = qe - q_span, q_off, t_off;
+		rs = rs - ext_len > 0? rs - ext_len : 0;
+		qs = qs - ext_len > 0? qs - ext_len : 0;
+		re = re + ext_len < (int32_t)mi->seq[rid].len? re + ext_len : (int)mi->seq[rid].len;
+		qe = qe + ext_len < qlen? qe + ext_len : qlen;
+		Seg s; s.rev = (int)(a->x >> 63), s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0;
+		return ll_i16(s, score, &q_off, &t_off);
+	}
+	// mm_fix_bad_ends_splice (align.c:618-637): drop a boundary anchor that sits far from its neighbour and extends poorly
+	bool fix_bad_ends_splice(const mm_reg1_t *r, const m128 *a, int32_t *as1, int32_t *cnt1) {
+		int score;
+		double log_gap;
+		*as1 = r->as, *cnt1 = r->cnt;
+		if (r->cnt < 3) return true;
+		log_gap = log((int32_t)a[r->as + 1].x - (int32_t)a[r->as].x);
+		if ((double)(a[r->as].y >> 32 & 0xff) < log_gap + opt->anchor_ext_shift) {
+			if (!seed_ext_score(&a[r->as], &score)) return false;
+			if ((double)score / mat[0] < log_gap + opt->anchor_ext_shift) ++(*as1), --(*cnt1);
+		}
+		log_gap = log((int32_t)a[r->as + r->cnt - 1].x - (int32_t)a[r->as + r->cnt - 2].x);
+		if ((double)(a[r->as + r->cnt - 1].y >> 32 & 0xff) < log_gap + opt->anchor_ext_shift) {
+			if (!seed_ext_score(&a[r->as + r->cnt - 1], &score)) return false;
+			if ((double)score / mat[0] < log_gap + opt->anchor_ext_shift) --(*cnt1);
+		}
+		return true;
+	}
+
+	// ---- mm_align1 (align.c:645-914), long-read path (genomic or spliced). Returns false if some ksw result is still pending. ----
+	// splice_flag: which transcript strand(s) to assume (MM_F_SPLICE_FOR / MM_F_SPLICE_REV), as in align.c:684-689.
+	bool align1(mm_reg1_t *r, mm_reg1_t *r2, int n_a, m128 *a, int64_t splice_flag) {
 		const int32_t rid = (int32_t)(a[r->as].x << 1 >> 33), rev = (int32_t)(a[r->as].x >> 63);
 		int32_t as1, cnt1, i, l, bw, bw_long, dropped = 0, rs0, re0, qs0, qe0, rs, re, qs, qe, rs1, qs1, re1, qe1;
 		const int32_t ref_len = (int32_t)mi->seq[rid].len;
@@ -536,8 +571,17 @@ struct Driver {
 		bw = (int)(opt->bw * 1.5 + 1.);
 		bw_long = (int)(opt->bw_long * 1.5 + 1.);
 		if (bw_long < bw) bw_long = bw;
-		if (!(opt->flag & MM_F_NO_END_FLT)) fix_bad_ends(r, a, opt->bw, opt->min_chain_score * 2, &as1, &cnt1);
-		else as1 = r->as, cnt1 = r->cnt;
+		const bool is_splice = (opt->flag & MM_F_SPLICE) != 0;
+		int sflag = 0; // KSW_EZ_SPLICE_* for every ksw call of this region
+		if (!(opt->flag & MM_F_NO_END_FLT)) {
+			if (is_splice) { if (!fix_bad_ends_splice(r, a, &as1, &cnt1)) return false; } // the probe is pending: nothing below can be planned yet
+			else fix_bad_ends(r, a, opt->bw, opt->min_chain_score * 2, &as1, &cnt1);
+		} else as1 = r->as, cnt1 = r->cnt;
+		if (is_splice) {
+			if (splice_flag & MM_F_SPLICE_FOR) sflag |= rev? MMB_KSW_SPLICE_REV : MMB_KSW_SPLICE_FOR;
+			if (splice_flag & MM_F_SPLICE_REV) sflag |= rev? MMB_KSW_SPLICE_FOR : MMB_KSW_SPLICE_REV;
+			if (opt->flag & MM_F_SPLICE_FLANK) sflag |= MMB_KSW_SPLICE_FLANK;
+		}
 		filter_bad_seeds(as1, cnt1, a, 10, 40, opt->max_gap >> 1, 10);
 		filter_bad_seeds_alt(as1, cnt1, a, 30, opt->max_gap >> 1);
 		adjust_minier(&a[as1], &rs, &qs);
@@ -609,7 +653,7 @@ struct Driver {
 		// left extension (align.c:779-799)
 		if (qs > 0 && rs > 0) {
 			Seg s; s.rev = rev, s.qs = qs0, s.qlen = qs - qs0, s.q_reversed = 1, s.rid = rid, s.rs = rs0, s.tlen = rs - rs0, s.t_reversed = 1;
-			bool ok = align_pair(s, bw, opt->end_bonus, r->split_inv? opt->zdrop_inv : opt->zdrop, MMB_KSW_EXTZ_ONLY | MMB_KSW_RIGHT | MMB_KSW_REV_CIGAR, &ez);
+			bool ok = align_pair(s, bw, opt->end_bonus, r->split_inv? opt->zdrop_inv : opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY | MMB_KSW_RIGHT | MMB_KSW_REV_CIGAR, &ez);
 			if (ok) {
 				if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
 				rs1 = rs - (ez.reach_end? ez.mqe_t + 1 : ez.max_t + 1);
@@ -628,13 +672,13 @@ struct Driver {
 				int j, bw1 = bw_long, zdrop_code;
 				if (a[as1 + i].y & MMX_SEED_LONG_JOIN) bw1 = qe - qs > re - rs? qe - qs : re - rs;
 				Seg s; s.rev = rev, s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0;
-				bool ok = align_pair(s, bw1, -1, opt->zdrop, MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez); // first pass
+				bool ok = align_pair(s, bw1, -1, opt->zdrop, sflag | MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez); // first pass
 				if (ok) { // results that are available are consumed even if an earlier call is pending: this surfaces second-pass jobs one wave earlier
 					const uint8_t *qseq = qptr(rev, qs);
 					const bool have_zd = ez.zd_max >= 0 && !ez.zdropped;
 					if (!have_zd) get_tseq(rid, rs, re, tseq);
 					zdrop_code = test_zdrop(s, qseq, tseq.data(), ez.n_cigar, ez.cigar, have_zd? &ez : nullptr);
-					if (zdrop_code > 0) ok = align_pair(s, bw1, -1, zdrop_code == 2? opt->zdrop_inv : opt->zdrop, 0, &ez); // second pass
+					if (zdrop_code > 0) ok = align_pair(s, bw1, -1, zdrop_code == 2? opt->zdrop_inv : opt->zdrop, sflag, &ez); // second pass
 					else if (zdrop_code < 0) ok = false;
 					if (ok) {
 						if (ez.n_cigar > 0) append_cigar(r, ez.n_cigar, ez.cigar);
@@ -665,7 +709,7 @@ struct Driver {
 		// right extension (align.c:874-890)
 		if (!dropped && qe < qe0 && re < re0) {
 			Seg s; s.rev = rev, s.qs = qe, s.qlen = qe0 - qe, s.q_reversed = 0, s.rid = rid, s.rs = re, s.tlen = re0 - re, s.t_reversed = 0;
-			bool ok = align_pair(s, bw, opt->end_bonus, opt->zdrop, MMB_KSW_EXTZ_ONLY, &ez);
+			bool ok = align_pair(s, bw, opt->end_bonus, opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY, &ez);
 			if (ok) {
 				if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
 				re1 = re + (ez.reach_end? ez.mqe_t + 1 : ez.max_t + 1);
@@ -771,7 +815,28 @@ mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAli
 	n_a = hl_squeeze_a(n_regs, regs, a); // idempotent across replays: after the first call regions are already packed in order
 	for (int i = 0; i < n_regs; ++i) {
 		mm_reg1_t r2;
-		if (!D.align1(&regs[i], &r2, n_a, a)) continue; // results pending: other regions are still walked to collect their jobs
+		if ((opt->flag & MM_F_SPLICE) && (opt->flag & MM_F_SPLICE_FOR) && (opt->flag & MM_F_SPLICE_REV)) { // both transcript strands (align.c:1068-1098)
+			mm_reg1_t s[2], s2[2];
+			s[0] = s[1] = regs[i];
+			const bool ok0 = D.align1(&s[0], &s2[0], n_a, a, MM_F_SPLICE_FOR);
+			const bool ok1 = D.align1(&s[1], &s2[1], n_a, a, MM_F_SPLICE_REV); // walked even if the first is pending: its jobs join the same wave
+			if (!ok0 || !ok1) { free(s[0].p); free(s[1].p); continue; }
+			int which, trans_strand;
+			if (s[0].p->dp_score > s[1].p->dp_score) which = 0, trans_strand = 1;
+			else if (s[0].p->dp_score < s[1].p->dp_score) which = 1, trans_strand = 2;
+			else trans_strand = 3, which = (ra.qlen + s[0].p->dp_score) & 1;
+			regs[i] = s[which], r2 = s2[which];
+			free(s[1 - which].p);
+			mm_reg1_t *r = &regs[i];
+			r->p->trans_strand = trans_strand;
+			if (r->is_spliced) {
+				if (trans_strand == 1 || trans_strand == 2) r->p->dp_max += (opt->a + opt->b) + ((opt->a + opt->b) >> 1);
+				else if (trans_strand == 3) r->p->dp_max -= opt->a + opt->b;
+			}
+		} else {
+			if (!D.align1(&regs[i], &r2, n_a, a, opt->flag)) continue; // results pending: other regions are still walked to collect their jobs
+			if (opt->flag & MM_F_SPLICE) regs[i].p->trans_strand = opt->flag & MM_F_SPLICE_FOR? 1 : 2;
+		}
 		if (r2.cnt > 0) regs = insert_reg(&r2, i, &n_regs, regs);
 		if (i > 0 && regs[i].split_inv && !(opt->flag & MM_F_NO_INV)) {
 			int ret = D.align1_inv(&regs[i-1], &regs[i], &r2);

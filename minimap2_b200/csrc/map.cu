@@ -363,7 +363,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	cp.max_dist_x = max_chain_gap_ref, cp.max_dist_y = max_chain_gap_qry, cp.bw = opt->bw, cp.max_skip = opt->max_chain_skip;
 	cp.max_iter = opt->max_chain_iter, cp.min_cnt = opt->min_cnt, cp.min_sc = opt->min_chain_score;
 	cp.chn_pen_gap = (float)(opt->chain_gap_scale * 0.01 * mi->k), cp.chn_pen_skip = (float)(opt->chain_skip_scale * 0.01 * mi->k);
-	cp.is_cdna = 0, cp.n_seg = 1;
+	cp.is_cdna = (opt->flag & MM_F_SPLICE) != 0, cp.n_seg = 1; // map.c:277 (is_splice selects the cDNA gap model of comput_sc)
 	int32_t *d_n_u = bb.n_u.as<int32_t>((size_t)n), *d_n_v = bb.n_v.as<int32_t>((size_t)n);
 	uint64_t *d_u = bb.u.as<uint64_t>((size_t)total_a + 4);
 	m128 *d_a_out = bb.a_out.as<m128>((size_t)total_a + 4);
@@ -602,7 +602,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		if (r.regs0) free(r.regs0);
 		r.regs0 = nullptr, r.ra = nullptr;
 		r.regs = (mm_reg1_t*)realloc(r.regs, sizeof(mm_reg1_t) * (r.n_regs > 0? r.n_regs : 1));
-		hl_set_mapq(r.n_regs, r.regs, opt->min_chain_score, opt->a, r.rep_len, 0, 0);
+		hl_set_mapq(r.n_regs, r.regs, opt->min_chain_score, opt->a, r.rep_len, 0, (opt->flag & MM_F_SPLICE) != 0); // map.c:342
 		if (r.n_regs == 0) { free(r.regs); r.regs = nullptr; }
 		n_regs_out[live[j]] = r.n_regs, regs_out[live[j]] = r.regs;
 		if (rep_len_out) rep_len_out[live[j]] = r.rep_len;

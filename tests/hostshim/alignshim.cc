@@ -47,7 +47,10 @@ static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t 
 	}
 	mm2o_ez_t ez;
 	memset(&ez, 0, sizeof(ez));
-	mm2o_extd2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->e2, j.w, j.zdrop, j.end_bonus, j.flag & 0xff, &ez);
+	if (j.flag & MMB_JOB_SPLICE) // ksw_exts2 as mm_align_pair calls it (align.c:352-355); no junction annotation: junc[] is all zero there
+		mm2o_exts2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->noncan, j.zdrop, j.end_bonus, opt->junc_bonus, opt->junc_pen,
+				   j.flag & 0x1fff, nullptr, &ez);
+	else mm2o_extd2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->e2, j.w, j.zdrop, j.end_bonus, j.flag & 0xff, &ez);
 	d.r.max = ez.max, d.r.zdropped = ez.zdropped, d.r.max_q = ez.max_q, d.r.max_t = ez.max_t, d.r.mqe = ez.mqe, d.r.mqe_t = ez.mqe_t;
 	d.r.mte = ez.mte, d.r.mte_q = ez.mte_q, d.r.score = ez.score, d.r.n_cigar = ez.n_cigar, d.r.reach_end = ez.reach_end;
 	d.cig = ez.cigar;

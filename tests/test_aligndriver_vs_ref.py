@@ -91,15 +91,15 @@ def compare_formats(H, R, api, mi, qname, qstr, n, pm, pr, rep_len, flag):
         assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, ref_line[:300], buf.raw[:min(ln, 300)])
 
 
-def run_case(H, R, api, contigs, names, reads, preset="map-ont"):
-    mi, keep = build_ref_index(R, contigs, names)
+def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0):
+    mi, keep = build_ref_index(R, contigs, names, w=w)
     io, mo = api.IdxOpt(), api.MapOpt()
     R.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
     R.mm_set_opt(None, C.byref(io), C.byref(mo)); R.mm_set_opt(preset.encode(), C.byref(io), C.byref(mo))
     mo.flag |= api.MM_F_CIGAR
     mo.mid_occ = 50
     R.mm_mapopt_update(C.byref(mo), mi)
-    oidx = O.OracleIndex([bytes(c) for c in contigs], names, 10, 15)
+    oidx = O.OracleIndex([bytes(c) for c in contigs], names, w, 15)
     pg = float(np.float32(mo.chain_gap_scale * 0.01 * 15))
     n_checked = n_split = 0
     for qi, rd in enumerate(reads):
@@ -107,7 +107,9 @@ def run_case(H, R, api, contigs, names, reads, preset="map-ont"):
         a, rep, mini = oidx.anchors(qstr, mid_occ=mo.mid_occ, q_occ_frac=mo.q_occ_frac, max_max_occ=mo.max_max_occ, occ_dist=mo.occ_dist)
         if len(a) == 0:
             continue
-        u, b = O.ref_lchain_dp(a, mo.max_gap, mo.max_gap, mo.bw, mo.max_chain_skip, mo.max_chain_iter, mo.min_cnt, mo.min_chain_score, pg, 0.0)
+        gap_ref = mo.max_gap_ref if mo.max_gap_ref > 0 else mo.max_gap  # map.c:262-269
+        ps = float(np.float32(mo.chain_skip_scale * 0.01 * 15))
+        u, b = O.ref_lchain_dp(a, gap_ref, mo.max_gap, mo.bw, mo.max_chain_skip, mo.max_chain_iter, mo.min_cnt, mo.min_chain_score, pg, ps, is_cdna)
         if len(u) == 0:
             continue
         n = len(u)
@@ -190,3 +192,34 @@ def test_driver_on_structural_variants(libs):
         reads.append(synth.mutate_ascii(rd, rng, 0.06))
     n, n_split = run_case(H, R, api, contigs, ["chr0"], reads)
     assert n >= 35 and n_split >= 3, (n, n_split)
+
+
+def test_driver_on_spliced_reads(libs):
+    """-x splice host logic (boundary-anchor probe, splice-model flags, both transcript strands, trans_strand, N operations in the
+    statistics and in PAF/SAM) with the oracle's ksw_exts2 as the job executor. The CUDA kernel for these jobs does not exist yet
+    (the product refuses -x splice); this pins the driver half of that row."""
+    H, R, api = libs
+    rng = np.random.default_rng(11)
+    contigs = synth.random_genome(300_000, 29, n_contigs=1, repeat_frac=0.0)
+    g = np.frombuffer(bytes(contigs[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for i in range(36):
+        pos = int(rng.integers(2000, len(g) - 60000))
+        exons = []
+        strand_rev = i % 2 == 1
+        for k in range(int(rng.integers(2, 6))):
+            el = int(rng.integers(90, 400))
+            exons.append((pos, pos + el))
+            il = int(rng.integers(150, 6000))
+            if i % 3 != 2:  # plant canonical splice signals on the transcript strand: GT..AG (or CT..AC on the minus strand)
+                d, a_ = (b"GT", b"AG") if not strand_rev else (b"CT", b"AC")
+                g[pos + el:pos + el + 2] = list(d); g[pos + el + il - 2:pos + el + il] = list(a_)
+            pos += el + il
+        tr = np.concatenate([g[s:e] for s, e in exons])
+        if strand_rev:
+            tr = comp[tr[::-1]]
+        reads.append(synth.mutate_ascii(tr, rng, 0.03))
+    contigs = [g.tobytes()]
+    n, _ = run_case(H, R, api, contigs, ["chr0"], reads, preset="splice", w=5, is_cdna=1)
+    assert n >= 30

@@ -91,16 +91,18 @@ def compare_formats(H, R, api, mi, qname, qstr, n, pm, pr, rep_len, flag):
         assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, ref_line[:300], buf.raw[:min(ln, 300)])
 
 
-def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0):
-    mi, keep = build_ref_index(R, contigs, names, w=w)
+def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0, k=15, tweak=None):
+    mi, keep = build_ref_index(R, contigs, names, w=w, k=k)
     io, mo = api.IdxOpt(), api.MapOpt()
     R.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
     R.mm_set_opt(None, C.byref(io), C.byref(mo)); R.mm_set_opt(preset.encode(), C.byref(io), C.byref(mo))
     mo.flag |= api.MM_F_CIGAR
     mo.mid_occ = 50
+    if tweak:
+        tweak(mo)
     R.mm_mapopt_update(C.byref(mo), mi)
-    oidx = O.OracleIndex([bytes(c) for c in contigs], names, w, 15)
-    pg = float(np.float32(mo.chain_gap_scale * 0.01 * 15))
+    oidx = O.OracleIndex([bytes(c) for c in contigs], names, w, k)
+    pg = float(np.float32(mo.chain_gap_scale * 0.01 * k))
     n_checked = n_split = 0
     for qi, rd in enumerate(reads):
         qstr = bytes(rd); qlen = len(qstr)
@@ -108,7 +110,7 @@ def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0
         if len(a) == 0:
             continue
         gap_ref = mo.max_gap_ref if mo.max_gap_ref > 0 else mo.max_gap  # map.c:262-269
-        ps = float(np.float32(mo.chain_skip_scale * 0.01 * 15))
+        ps = float(np.float32(mo.chain_skip_scale * 0.01 * k))
         u, b = O.ref_lchain_dp(a, gap_ref, mo.max_gap, mo.bw, mo.max_chain_skip, mo.max_chain_iter, mo.min_cnt, mo.min_chain_score, pg, ps, is_cdna)
         if len(u) == 0:
             continue
@@ -118,7 +120,7 @@ def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0
         regs0 = R.mm_gen_regs(None, C.c_uint32(hash_), qlen, n, uu.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p), 0)
         R.mm_set_parent(None, C.c_float(mo.mask_level), mo.mask_len, n, C.c_void_p(regs0), mo.a * 2 + mo.b, 0, C.c_float(mo.alt_drop))
         nn = C.c_int(n)
-        R.mm_select_sub(None, C.c_float(mo.pri_ratio), 30, mo.best_n, 1, int(mo.max_gap * 0.8), C.byref(nn), C.c_void_p(regs0))
+        R.mm_select_sub(None, C.c_float(mo.pri_ratio), k * 2, mo.best_n, 1, int(mo.max_gap * 0.8), C.byref(nn), C.c_void_p(regs0))
         n0 = R.mm_filter_strand_retained(nn.value, C.c_void_p(regs0))
         snap = C.string_at(regs0, n0 * REG_SIZE)
         # mine first (inputs are const), then the reference (consumes regs0 and rewrites the anchors)
@@ -223,3 +225,19 @@ def test_driver_on_spliced_reads(libs):
     contigs = [g.tobytes()]
     n, _ = run_case(H, R, api, contigs, ["chr0"], reads, preset="splice", w=5, is_cdna=1)
     assert n >= 30
+
+
+def test_driver_on_hifi_and_single_affine(libs):
+    """other scoring regimes through the same driver: map-hifi (k19/w19, a1 b4 q6,26) and a single-affine setting (q == q2:
+    the reference switches to ksw_extz2 there, align.c:360; the product keeps the dual-affine jobs with equal terms)"""
+    H, R, api = libs
+    contigs = synth.random_genome(250_000, 37, n_contigs=2, repeat_frac=0.1)
+    reads = synth.make_reads(contigs, 25, 6000, 0.01, 137, chimeric_frac=0.1)
+    n, _ = run_case(H, R, api, contigs, ["chr0", "chr1"], reads, preset="map-hifi", w=19, k=19)
+    assert n >= 20
+
+    def single_affine(mo):
+        mo.q = mo.q2 = 6; mo.e = mo.e2 = 2
+    reads = synth.make_reads(contigs, 25, 3000, 0.10, 138, chimeric_frac=0.1)
+    n, _ = run_case(H, R, api, contigs, ["chr0", "chr1"], reads, preset="map-ont", tweak=single_affine)
+    assert n >= 20

@@ -1,0 +1,118 @@
+"""CPU: the product's K3 CUDA kernels (ksw_pk_kernel, ksw_fast_kernel, ksw_extd2_kernel, ksw_ll_kernel -- the unmodified sources of
+minimap2_b200/csrc/ksw_fast.cu and ksw_extd2.cu) executed by the SIMT emulator of tests/cuda_emu (one OS thread per CUDA thread)
+and compared with the oracle, job for job. This checks kernel LOGIC in the CPU suite; the -m gpu tests remain the parity proof on
+the real device."""
+import ctypes as C
+import os
+import sys
+import numpy as np
+import pytest
+import oracle_lib as O
+
+sys.path.insert(0, os.path.join(O.ROOT, "tests", "cuda_emu"))
+EXT, RIGHT, REVC, APPROX, SCORE_ONLY = 0x40, 0x02, 0x80, 0x08, 0x01
+JOB_LL, JOB_ZDROP = 0x20000, 0x40000
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build_emu
+    from minimap2_b200._lib import KswJob, KswRes, KswScore
+    L = C.CDLL(build_emu.build("mmb_emu_k3", ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu"]))
+    L.mmb_ctx_create.restype = C.c_void_p
+    L.mmb_ksw_batch_host.restype = C.c_int64
+    L.mmb_ksw_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64]
+    ctx = C.c_void_p(L.mmb_ctx_create(0))
+    assert ctx.value
+    return L, ctx, KswJob, KswRes, KswScore
+
+
+def run_jobs(emu, mat, q, e, q2, e2, pairs, params):
+    L, ctx, KswJob, KswRes, KswScore = emu
+    n = len(pairs)
+    qcat = np.concatenate([np.asarray(p[0], dtype=np.uint8) for p in pairs]); tcat = np.concatenate([np.asarray(p[1], dtype=np.uint8) for p in pairs])
+    jobs = (KswJob * n)(); qo = to = tot = 0
+    for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
+        j = jobs[i]
+        j.q_start, j.t_start, j.q_step, j.t_step, j.qlen, j.tlen = qo, to, 1, 1, len(qq), len(tt)
+        j.w, j.zdrop, j.end_bonus, j.flag = pr["w"], pr["zdrop"], pr["end_bonus"], pr["flag"]
+        qo += len(qq); to += len(tt); tot += len(qq) + len(tt) + 2
+    sc = KswScore()
+    for i in range(25):
+        sc.mat[i] = int(mat[i])
+    sc.q, sc.e, sc.q2, sc.e2 = q, e, q2, e2
+    res = (KswRes * n)(); cig = np.zeros(tot, dtype=np.uint32)
+    used = L.mmb_ksw_batch_host(ctx, C.byref(sc), n, jobs, qcat.ctypes.data, len(qcat), tcat.ctypes.data, len(tcat), res, cig.ctypes.data, len(cig))
+    assert used >= 0
+    out = []
+    for i in range(n):
+        r = res[i]
+        out.append((dict(max=r.max, zdropped=r.zdropped, max_q=r.max_q, max_t=r.max_t, mqe=r.mqe, mqe_t=r.mqe_t, mte=r.mte, mte_q=r.mte_q, score=r.score,
+                         n_cigar=r.n_cigar, reach_end=r.reach_end, cigar=[int(x) for x in cig[r.cigar_off:r.cigar_off + r.n_cigar]]),
+                    (r.zd_max, r.zd_t0, r.zd_t1, r.zd_q0, r.zd_q1)))
+    return out
+
+
+def zdrop_scan(q, t, mat, cigar, gq, ge):
+    """mm_test_zdrop's scan (align.c:61-89) in plain Python: max_zdrop and pos"""
+    score, mx, mi, mj, i, j, zd, pos = 0, -(1 << 31), -1, -1, 0, 0, 0, [-1, -1, -1, -1]
+
+    def upd(sc, ii, jj):
+        nonlocal mx, mi, mj, zd, pos
+        if sc < mx:
+            li, lj = ii - mi, jj - mj
+            z = mx - sc - abs(li - lj) * ge
+            if z > zd:
+                zd, pos = z, [mi, ii, mj, jj]
+        else:
+            mx, mi, mj = sc, ii, jj
+    for c in cigar:
+        op, ln = c & 0xf, c >> 4
+        if op == 0:
+            for l in range(ln):
+                score += int(mat[int(t[i + l]) * 5 + int(q[j + l])]); upd(score, i + l, j + l)
+            i += ln; j += ln
+        else:
+            score -= gq + ge * ln
+            if op == 1: j += ln
+            else: i += ln
+            upd(score, i, j)
+    return (zd, *pos)
+
+
+def test_emulated_kernels_match_oracle(emu):
+    rng = np.random.default_rng(2024)
+    mat = O.simple_mat(2, 4, 1)
+    pairs, params = [], []
+    for it in range(90):
+        tl = int(rng.integers(1, 330)) if it % 5 else int(rng.integers(260, 520))
+        t = rng.integers(0, 4, tl).astype(np.uint8)
+        q = O.mutate(t, rng, err=float(rng.choice([0.0, 0.05, 0.15, 0.35])))
+        if len(q) == 0:
+            q = np.array([0], dtype=np.uint8)
+        if rng.random() < 0.2:
+            q[rng.integers(0, len(q))] = 4; t[rng.integers(0, len(t))] = 4
+        kind = it % 6
+        if kind in (0, 1, 2):   # gap fills: packed kernel (+ the in-kernel z-drop scan)
+            pr = dict(w=30001, zdrop=400, end_bonus=-1, flag=APPROX | JOB_ZDROP)
+        elif kind == 3:         # extensions through the universal kernel
+            pr = dict(w=int(rng.choice([751, 40, 17])), zdrop=int(rng.choice([400, 100, -1])), end_bonus=int(rng.choice([-1, 10])), flag=int(rng.choice([EXT, EXT | RIGHT | REVC])))
+        elif kind == 4:         # exact global alignment, band-limited or not
+            pr = dict(w=int(rng.choice([-1, 30, 5])), zdrop=int(rng.choice([-1, 200])), end_bonus=-1, flag=int(rng.choice([0, RIGHT, SCORE_ONLY])))
+        else:                   # local score probe (ksw_ll_i16): w = gap open, zdrop = gap extension
+            pr = dict(w=4, zdrop=2, end_bonus=0, flag=JOB_LL)
+        pairs.append((q, t)); params.append(pr)
+    got = run_jobs(emu, mat, 4, 2, 24, 1, pairs, params)
+    n_zd = 0
+    for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
+        g, zd = got[i]
+        if pr["flag"] & JOB_LL:
+            sc, qe, te = O.oracle_ll_i16(qq, tt, mat, 4, 2)
+            assert (g["score"], g["max_q"], g["max_t"]) == (sc, qe, te), (i, g)
+            continue
+        exp = O.oracle_extd2(qq, tt, mat, 4, 2, 24, 1, pr["w"], pr["zdrop"], pr["end_bonus"], pr["flag"] & 0xff)
+        assert g == exp, (i, len(qq), len(tt), pr, {k: (g[k], exp[k]) for k in exp if g[k] != exp[k]})
+        if (pr["flag"] & JOB_ZDROP) and zd[0] >= 0:
+            assert zd == zdrop_scan(qq, tt, mat, exp["cigar"], 4, 2), (i, zd)
+            n_zd += 1
+    assert n_zd >= 20

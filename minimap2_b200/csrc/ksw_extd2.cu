@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 					}
 				}
 				if (!stop && r == qlen + tlen - 2 && en0 == tlen - 1) ez.score = H0; // only thread 0's copy is meaningful
+				gsync<G>(); // thread 0 read u[]/v[] of this row: the other lanes must not start overwriting them for the next row before that
 			}
 			if (stop) break;
 			last_st = st, last_en = en;

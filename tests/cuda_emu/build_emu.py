@@ -75,14 +75,21 @@ def build(name, files, extra=("emu_stubs.cc",)):
         return lib
     gen = []
     for f in files:
-        o = os.path.join(BUILD, f.replace(".cu", ".emu.cc").replace(".cc", ".emu.cc") if not f.endswith(".cu") else f.replace(".cu", ".emu.cc"))
+        o = os.path.join(BUILD, f.rsplit(".", 1)[0] + ".emu.cc")
         open(o, "w").write("#line 1 \"%s\"\n" % os.path.join(CSRC, f) + transform(open(os.path.join(CSRC, f)).read()))
         gen.append(o)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-w", "-include", os.path.join(HERE, "cuda_emu.h"),
-           "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + gen + [os.path.join(HERE, "emu_runtime.cc")] + [os.path.join(HERE, x) for x in extra] + ["-o", lib]
+           "-I" + os.path.join(HERE, "fake_include"), "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + gen + [os.path.join(HERE, "emu_runtime.cc")] + [os.path.join(HERE, x) for x in extra] + ["-lz", "-o", lib]
     subprocess.check_call(cmd)
     return lib
 
 
+ALL = ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu", "sketch.cu", "scan.cu", "seed.cu", "chain.cu", "index.cu", "map.cu", "synth.cu",
+       "align.cc", "hits.cc", "format.cc", "options.cc", "fastx.cc"]
+
 if __name__ == "__main__":
-    print(build("mmb_emu_k3", ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu"]))
+    which = sys.argv[1] if len(sys.argv) > 1 else "k3"
+    if which == "k3":
+        print(build("mmb_emu_k3", ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu"]))
+    else:
+        print(build("mmb_emu_all", ALL, extra=()))

@@ -1,0 +1,42 @@
+"""CPU: the whole product pipeline -- index build, sketch, seeding, sort, chaining, alignment kernels, scheduler, host logic, CLI --
+compiled for the SIMT emulator of tests/cuda_emu (every CUDA kernel source unchanged, one OS thread per CUDA thread) and run on
+the small golden cases; the output must equal the reference's recorded output byte for byte. Slow by nature (seconds per
+kilobase), so only the small cases run here; the -m gpu suite covers everything on the real device."""
+import os
+import subprocess
+import sys
+import pytest
+import oracle_lib as O
+
+sys.path.insert(0, os.path.join(O.ROOT, "tests", "cuda_emu"))
+GOLD = os.path.join(O.ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def emu_cli():
+    import build_emu
+    lib = build_emu.build("mmb_emu_all", build_emu.ALL, extra=())
+    exe = os.path.join(os.path.dirname(lib), "minimap2-emu")
+    main = os.path.join(O.ROOT, "minimap2_b200", "cli", "main.cc")
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(lib), os.path.getmtime(main)):
+        subprocess.check_call(["g++", "-O1", "-I" + os.path.join(O.ROOT, "include"), "-o", exe, main, "-L" + os.path.dirname(lib), "-lmmb_emu_all",
+                               "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return exe
+
+
+def cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m.CASES
+
+
+@pytest.mark.parametrize("name", ["mt_paf_cigar", "mt_sam", "inv_paf_cigar", "x3s_paf_cigar", "t2_paf_cigar", "mt_paf_single_affine"])
+def test_emulated_pipeline_matches_recorded_reference(emu_cli, name):
+    env = dict(os.environ, MM_B200_GROUPS="1")
+    p = subprocess.run([emu_cli, "-t", "4"] + cases()[name], cwd=os.path.join(GOLD, "data"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200, env=env)
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    got = [l for l in p.stdout.decode().splitlines() if not l.startswith("@PG")]
+    exp = open(os.path.join(GOLD, "expected", name + ".txt")).read().splitlines()
+    assert got == exp, (len(got), len(exp), [(a[:200], b[:200]) for a, b in zip(got, exp) if a != b][:2])

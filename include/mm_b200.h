@@ -55,7 +55,7 @@ uint64_t mmb_profile_units(mmb_ctx_t *ctx, int which, int reset); /* algorithmic
 /* job-level addressing flags (how the kernel walks the resident sequences) */
 #define MMB_JOB_Q_COMP       0x10000 /* complement query bases (3-c, N stays 4): reverse strand (align.c:1056-1061) */
 #define MMB_JOB_LL           0x20000 /* run ksw_ll_i16 (local score) instead of extd2 */
-#define MMB_JOB_SPLICE       0x80000 /* the job is a ksw_exts2 call (align.c:352-355). No CUDA kernel runs it yet: mm_map* refuses -x splice */
+#define MMB_JOB_SPLICE       0x80000 /* the job is a ksw_exts2 call (align.c:352-355): q/e = gap open/extend, q2 = intron open, MMB_KSW_SPLICE_* select the model */
 #define MMB_JOB_ZDROP        0x40000 /* also run mm_test_zdrop's scan over the resulting CIGAR (align.c:61-89); see zd_* below */
 
 typedef struct {
@@ -85,6 +85,7 @@ typedef struct {      /* ksw_extz_t (ksw2.h:34-43) without the pointer */
 typedef struct {      /* scoring: what align.c:655 ksw_gen_ts_mat + mm_mapopt_t a,b,q,e,q2,e2 give */
 	int8_t mat[25];
 	int8_t q, e, q2, e2;
+	int8_t noncan, junc_bonus, junc_pen; /* spliced alignment only (MMB_JOB_SPLICE): mm_mapopt_t noncan / junc_bonus / junc_pen */
 } mmb_ksw_score_t;
 
 /* Kernel-level entry with HOST buffers (used by the parity tests and for single calls):

@@ -49,6 +49,9 @@ struct KswArgs {
 	int8_t q, e, q2, e2;   // already ordered so that q+e <= q2+e2
 	int8_t skip;           // -min(mat) > 2(q+e): the reference returns immediately (:100)
 	int long_thres, long_diff;
+	int8_t sp[4];          // spliced variant: penalties of the four signal classes (ksw2_exts2_sse.c:113-121)
+	uint8_t *gws;          // per-worker DP state in HBM for targets that do not fit shared memory (null: shared memory)
+	size_t gws_stride;
 };
 
 __device__ __forceinline__ uint32_t blend4(uint32_t a, uint32_t b, uint32_t m) { return (a & ~m) | (b & m); } // m ? b : a
@@ -117,7 +120,7 @@ __device__ __forceinline__ void push_cigar(uint32_t *cig, int &n, uint32_t op, i
 // step only needs one traceback byte that lies inside a 32-row x 32-column window below-left of the current cell (a step
 // lowers r by 1 or 2 and i by 0 or 1). The warp therefore stages that window from HBM/L2 into shared memory with 32
 // independent loads per lane (one memory latency per ~16-32 steps instead of one per step), then lane 0 walks inside it.
-__device__ int backtrack_tiled(const uint8_t *p, int n_col, int qlen, int tlen, int w, int i0, int j0, uint32_t *cig, uint8_t *tile, int lane)
+__device__ int backtrack_tiled(const uint8_t *p, int n_col, int qlen, int tlen, int w, int i0, int j0, uint32_t *cig, uint8_t *tile, int lane, int min_intron_len)
 {
 	int n = 0, i = i0, j = j0, state = 0;
 	for (;;) {
@@ -156,20 +159,23 @@ __device__ int backtrack_tiled(const uint8_t *p, int n_col, int qlen, int tlen, 
 				if (state == 0) state = tmp & 7;
 				if (force >= 0) state = force;
 				if (state == 0) push_cigar(cig, n, 0, 1), --i, --j;
-				else if (state == 1 || state == 3) push_cigar(cig, n, 2, 1), --i;
+				else if (state == 1 || (state == 3 && min_intron_len <= 0)) push_cigar(cig, n, 2, 1), --i;
+				else if (state == 3) push_cigar(cig, n, 3, 1), --i; // an intron (ksw2.h:152)
 				else push_cigar(cig, n, 1, 1), --j;
 			}
 		}
 		__syncwarp();
 	}
 	if (lane == 0) {
-		if (i >= 0) push_cigar(cig, n, 2, i + 1);
+		if (i >= 0) push_cigar(cig, n, min_intron_len > 0 && i >= min_intron_len? 3 : 2, i + 1);
 		if (j >= 0) push_cigar(cig, n, 1, j + 1);
 	}
 	return n;
 }
 
-template<int G>
+// SP = true is ksw_exts2_sse (ksw2_exts2_sse.c:26-465): the second gap state is an intron (open q2, free extension, A.e2 == 0 here)
+// whose closing / opening is scored with the acceptor / donor signal of the target position; no band; y2[] holds the donor array.
+template<int G, bool SP>
 __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -179,14 +185,15 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 	const int wk = threadIdx.x / G, g = threadIdx.x % G;
 	const int worker = blockIdx.x * NW + wk;
 	const int L = A.L, LQ = A.LQ;
-	const size_t wbytes = (size_t)15 * L + LQ + 64 + 1024;
-	uint8_t *base = smem_raw + wbytes * wk;
-	uint8_t *bt_tile = base + wbytes - 1024;
+	const size_t wbytes = (size_t)16 * L + LQ + 64 + 1024;
+	uint8_t *base = A.gws? A.gws + A.gws_stride * worker : smem_raw + wbytes * wk;
+	uint8_t *bt_tile = A.gws? smem_raw + (size_t)1024 * wk : base + wbytes - 1024;
 	// state arrays (all offsets multiples of 16)
 	uint8_t *u = base, *y = u + L, *y2 = y + L, *s = y2 + L, *sf = s + L;
 	uint8_t *vb[2] = { sf + L, sf + 2 * L }, *xb[2] = { sf + 3 * L, sf + 4 * L }, *x2b[2] = { sf + 5 * L, sf + 6 * L };
 	uint8_t *qr = sf + 7 * L + 16;               // 16 zero bytes in front, >=32 behind
 	int32_t *H = (int32_t*)(sf + 7 * L + LQ + 64);
+	uint8_t *acc = (uint8_t*)(H + L);             // acceptor signals (SP only)
 	uint8_t *p = A.pws + A.pws_stride * worker;
 	uint32_t *cig = A.cigws + A.cigws_stride * worker;
 	const int8_t q = A.q, e = A.e, q2 = A.q2, e2 = A.e2;
@@ -194,7 +201,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 	const uint32_t Q4 = rep4(q), Q24 = rep4(q2), QE4 = rep4(qe), QE24 = rep4(qe2);
 	const uint32_t NQE4 = rep4((int8_t)(-q - e)), NQE24 = rep4((int8_t)(-q2 - e2));
 	const uint32_t MCH4 = rep4(A.mat[0]), MIS4 = rep4(A.mat[1]);
-	const uint32_t SCN4 = rep4(A.mat[24] == 0? (int8_t)(-e2) : A.mat[24]);
+	const uint32_t SCN4 = rep4(A.mat[24] == 0? (int8_t)(SP? -e : -e2) : A.mat[24]); // ksw2_extd2_sse.c:87 / ksw2_exts2_sse.c:80
 
 	for (;;) {
 		if (g == 0) s_job[wk] = atomicAdd(A.counter, 1);
@@ -247,6 +254,41 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 			qr[k] = c;
 		}
 		gsync<G>();
+		if (SP) { // donor / acceptor arrays (ksw2_exts2_sse.c:111-190; no junction annotation)
+			const bool fo = (flag & MMB_KSW_SPLICE_FOR) != 0, re = (flag & MMB_KSW_SPLICE_REV) != 0, rc = (flag & MMB_KSW_REV_CIGAR) != 0;
+			for (int i = g; i < tlen16; i += G) {
+				int8_t d = 0, a = 0;
+				if (fo || re) {
+					d = a = (int8_t)-A.sp[3];
+					if (i < tlen - 4) {
+						const int c1 = sf[i + 1], c2 = sf[i + 2], c3 = sf[i + 3];
+						int z = 3;
+						if (!rc) {
+							if (fo) { if (c1 == 2 && c2 == 3) z = c3 == 0 || c3 == 2? -1 : 0; else if (c1 == 2 && c2 == 1) z = 1; else if (c1 == 0 && c2 == 3) z = 2; }
+							else { if (c1 == 1 && c2 == 3) z = c3 == 0 || c3 == 2? -1 : 0; else if (c1 == 2 && c2 == 3) z = 2; }
+						} else {
+							if (fo) { if (c1 == 2 && c2 == 0) z = c3 == 1 || c3 == 3? -1 : 0; else if (c1 == 1 && c2 == 0) z = 2; }
+							else { if (c1 == 1 && c2 == 0) z = c3 == 1 || c3 == 3? -1 : 0; else if (c1 == 1 && c2 == 2) z = 1; else if (c1 == 3 && c2 == 0) z = 2; }
+						}
+						d = z < 0? 0 : (int8_t)-A.sp[z];
+					}
+					if (i >= 2 && i < tlen) {
+						const int c0 = sf[i - 2], c1 = sf[i - 1], c2 = sf[i];
+						int z = 3;
+						if (!rc) {
+							if (fo) { if (c1 == 0 && c2 == 2) z = c0 == 1 || c0 == 3? -1 : 0; else if (c1 == 0 && c2 == 1) z = 2; }
+							else { if (c1 == 0 && c2 == 1) z = c0 == 1 || c0 == 3? -1 : 0; else if (c1 == 2 && c2 == 1) z = 1; else if (c1 == 0 && c2 == 3) z = 2; }
+						} else {
+							if (fo) { if (c1 == 3 && c2 == 2) z = c0 == 0 || c0 == 2? -1 : 0; else if (c1 == 1 && c2 == 2) z = 1; else if (c1 == 3 && c2 == 0) z = 2; }
+							else { if (c1 == 3 && c2 == 1) z = c0 == 0 || c0 == 2? -1 : 0; else if (c1 == 3 && c2 == 2) z = 2; }
+						}
+						a = z < 0? 0 : (int8_t)-A.sp[z];
+					}
+				}
+				y2[i] = (uint8_t)d, acc[i] = (uint8_t)a;
+			}
+			gsync<G>();
+		}
 
 		int last_st = -1, last_en = -1;
 		int H0 = 0, last_H0_t = 0;      // approximate-max tracker (thread 0)
@@ -312,6 +354,32 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 				const uint32_t VT1 = Vo << 8 | vp, XT1 = Xo << 8 | xp, X2T1 = X2o << 8 | x2p;
 				uint32_t Aa = __vadd4(XT1, VT1), Bb = __vadd4(Y, U), A2 = __vadd4(X2T1, VT1), B2 = __vadd4(Y2, U);
 				uint32_t Z = S, D = 0, m;
+				if (SP) { // ksw2_exts2_sse.c:36-66,283-380: three candidates, no clip, the intron state is floored by the donor signal
+					const uint32_t DON = *(const uint32_t*)(y2 + t0), A2A = __vadd4(A2, *(const uint32_t*)(acc + t0));
+					if (!right) {
+						m = __vcmpgts4(Aa, Z);  D = m & 0x01010101u;            Z = blend4(Z, Aa, m);
+						m = __vcmpgts4(Bb, Z);  D = blend4(D, 0x02020202u, m);  Z = blend4(Z, Bb, m);
+						m = __vcmpgts4(A2A, Z); D = blend4(D, 0x03030303u, m);  Z = blend4(Z, A2A, m);
+					} else {
+						m = __vcmpgts4(Z, Aa);  D = ~m & 0x01010101u;           Z = blend4(Aa, Z, m);
+						m = __vcmpgts4(Z, Bb);  D = blend4(0x02020202u, D, m);  Z = blend4(Bb, Z, m);
+						m = __vcmpgts4(Z, A2A); D = blend4(0x03030303u, D, m);  Z = blend4(A2A, Z, m);
+					}
+					*(uint32_t*)(u + t0) = __vsub4(Z, VT1);
+					*(uint32_t*)(vn + t0) = __vsub4(Z, U);
+					uint32_t T = __vsub4(Z, Q4);
+					Aa = __vsub4(Aa, T), Bb = __vsub4(Bb, T);
+					A2 = __vsub4(A2, __vsub4(Z, Q24));
+					if (!right) {
+						m = __vcmpgts4(Aa, 0);   *(uint32_t*)(xn + t0)  = __vsub4(Aa & m, QE4);             D |= m & 0x08080808u;
+						m = __vcmpgts4(Bb, 0);   *(uint32_t*)(y + t0)   = __vsub4(Bb & m, QE4);             D |= m & 0x10101010u;
+						m = __vcmpgts4(A2, DON); *(uint32_t*)(x2n + t0) = __vsub4(blend4(DON, A2, m), Q24); D |= m & 0x20202020u;
+					} else {
+						m = ~__vcmpgts4(0, Aa);   *(uint32_t*)(xn + t0)  = __vsub4(Aa & m, QE4);             D |= m & 0x08080808u;
+						m = ~__vcmpgts4(0, Bb);   *(uint32_t*)(y + t0)   = __vsub4(Bb & m, QE4);             D |= m & 0x10101010u;
+						m = ~__vcmpgts4(DON, A2); *(uint32_t*)(x2n + t0) = __vsub4(blend4(DON, A2, m), Q24); D |= m & 0x20202020u;
+					}
+				} else {
 				if (!right) { // :232-243
 					m = __vcmpgts4(Aa, Z); D = m & 0x01010101u;            Z = blend4(Z, Aa, m);
 					m = __vcmpgts4(Bb, Z); D = blend4(D, 0x02020202u, m);  Z = blend4(Z, Bb, m);
@@ -340,6 +408,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 					m = ~__vcmpgts4(0, Bb); *(uint32_t*)(y + t0)   = __vsub4(Bb & m, QE4);  D |= m & 0x10101010u;
 					m = ~__vcmpgts4(0, A2); *(uint32_t*)(x2n + t0) = __vsub4(A2 & m, QE24); D |= m & 0x20202020u;
 					m = ~__vcmpgts4(0, B2); *(uint32_t*)(y2 + t0)  = __vsub4(B2 & m, QE24); D |= m & 0x40404040u;
+				}
 				}
 				if (with_cigar) *(uint32_t*)(prow + (t0 - st)) = D;
 			}
@@ -423,7 +492,7 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 			else if (ez.max_t >= 0 && ez.max_q >= 0) bi = ez.max_t, bj = ez.max_q;
 			__threadfence_block();
 			gsync<G>();
-			if (g < 32 && bi >= 0) n_cig = backtrack_tiled(p, n_col, qlen, tlen, w, bi, bj, cig, bt_tile, g);
+			if (g < 32 && bi >= 0) n_cig = backtrack_tiled(p, n_col, qlen, tlen, w, bi, bj, cig, bt_tile, g, SP? A.long_thres : 0);
 			if (G == 32) n_cig = __shfl_sync(0xffffffffu, n_cig, 0);
 			else { if (g == 0) s_red[0] = n_cig; __syncthreads(); n_cig = s_red[0]; __syncthreads(); }
 		}
@@ -584,18 +653,28 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 	int lt = e != e2? (q2 - q) / (e - e2) - 1 : 0; // :102-105
 	if (q2 + e2 + lt * e2 > q + e + lt * e) ++lt;
 	A.long_thres = lt, A.long_diff = lt * (e - e2) - (q2 - q) - e2;
+	A.gws = nullptr, A.gws_stride = 0;
+	{ // signal-class penalties of the spliced kernel (ksw2_exts2_sse.c:113-121); the model bits are the same for every job of a batch
+		bool cmplx = false, flank = false;
+		for (int i = 0; i < n_jobs; ++i) if (h_jobs[i].flag & MMB_JOB_SPLICE) { cmplx = (h_jobs[i].flag & MMB_KSW_SPLICE_CMPLX) != 0, flank = (h_jobs[i].flag & MMB_KSW_SPLICE_FLANK) != 0; break; }
+		static const int sp0[4] = { 8, 15, 21, 30 };
+		for (int t = 0; t < 4; ++t) A.sp[t] = cmplx? (int8_t)((double)sp0[t] / 3. + .499) : (int8_t)(t == 0? (flank? sc->noncan / 2 : 0) : sc->noncan);
+	}
 
-	// tiers: {max len16, group size, workers per CTA}
+	// tiers: {max len16, group size, workers per CTA}; the last tier keeps the DP state in HBM instead of shared memory
 	struct Tier { int maxlen, G, nw; };
-	const Tier tiers[] = { {256, 32, 8}, {512, 32, 8}, {1024, 32, 4}, {13000, 256, 1} };
-	const int n_tiers = 4;
-	std::vector<std::vector<int>> tj(n_tiers + 1);
+	Tier tiers[] = { {256, 32, 8}, {512, 32, 8}, {1024, 32, 4}, {13000, 256, 1}, {1 << 20, 256, 1} };
+	const int n_tiers = 5;
+	static const int smem_maxlen = getenv("MM_B200_KSW_SMEM_MAXLEN")? atoi(getenv("MM_B200_KSW_SMEM_MAXLEN")) : 13000; // test hook: push shorter jobs into the HBM-state tier
+	for (int k = 0; k < n_tiers - 1; ++k) tiers[k].maxlen = std::min(tiers[k].maxlen, std::max(16, smem_maxlen));
+	std::vector<std::vector<int>> tj(2 * (n_tiers + 1)); // [0, n_tiers]: ksw_extd2 jobs, [n_tiers+1, ..]: spliced (ksw_exts2) jobs
 	uint64_t cells = 0, io_bytes = 0;
 	std::vector<int> llj, fastj;
 	static const bool use_fast = getenv("MM_B200_NO_FAST_KSW") == nullptr;
 	for (int i = 0; i < n_jobs; ++i) {
 		if (h_jobs[i].flag & MMB_JOB_LL) { llj.push_back(i); continue; }
-		if (use_fast && mmb_ksw_fast_eligible(h_jobs[i])) {
+		const bool spl = (h_jobs[i].flag & MMB_JOB_SPLICE) != 0;
+		if (use_fast && !spl && mmb_ksw_fast_eligible(h_jobs[i])) {
 			fastj.push_back(i);
 			cells += (uint64_t)h_jobs[i].qlen * h_jobs[i].tlen, io_bytes += (uint64_t)h_jobs[i].qlen + h_jobs[i].tlen + 40;
 			continue;
@@ -604,9 +683,9 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		cells += (uint64_t)std::max(h_jobs[i].qlen, 0) * std::max(h_jobs[i].tlen, 0);
 		io_bytes += (uint64_t)std::max(h_jobs[i].qlen, 0) + std::max(h_jobs[i].tlen, 0) + 40;
 		while (k < n_tiers && m > tiers[k].maxlen) ++k;
-		tj[k].push_back(i);
+		tj[(spl? n_tiers + 1 : 0) + k].push_back(i);
 	}
-	if (!tj[n_tiers].empty()) {
+	if (!tj[n_tiers].empty() || !tj[2 * n_tiers + 1].empty()) {
 		fprintf(stderr, "[ERROR] ksw job longer than %d not supported by this build\n", tiers[n_tiers - 1].maxlen);
 		abort();
 	}
@@ -636,32 +715,44 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 	size_t g_off = (size_t)n_jobs + 64;
 	std::vector<KswPlan> plans;
 	mmb_ksw_fast_plan(ctx, sc, fastj, h_jobs, d_jobs, d_query, d_target, t_packed, d_res, d_cigar, cigar_cap, d_cigar_used, d_queues, plans);
+	for (int pass = 0; pass < 2; ++pass) { // 0: dual-affine (ksw_extd2), 1: spliced (ksw_exts2)
+		if (pass == 1) { // ksw2_exts2_sse.c:71-95: no (q,e)/(q2,e2) reordering; the intron state has no extension cost
+			A.q = sc->q, A.e = sc->e, A.q2 = sc->q2, A.e2 = 0;
+			A.skip = (-min_sc > 2 * (sc->q + sc->e)) || sc->q2 <= sc->q + sc->e;
+			int lt2 = sc->e > 0? (sc->q2 - sc->q) / sc->e - 1 : 0;
+			if (sc->q2 > sc->q + sc->e + lt2 * sc->e) ++lt2;
+			A.long_thres = lt2, A.long_diff = lt2 * sc->e - (sc->q2 - sc->q);
+		}
 	for (int k = 0; k < n_tiers; ++k) {
-		std::vector<int> &v = tj[k];
+		std::vector<int> &v = tj[pass * (n_tiers + 1) + k];
 		if (v.empty()) continue;
 		mmb_order_by_cells(v, h_jobs);
 		int maxq = 0, maxt = 0; size_t maxp = 0; int maxsum = 0;
 		for (int i : v) {
 			const mmb_ksw_job_t &j = h_jobs[i];
 			maxq = std::max(maxq, j.qlen), maxt = std::max(maxt, j.tlen), maxsum = std::max(maxsum, j.qlen + j.tlen);
-			int w = j.w < 0? std::max(j.qlen, j.tlen) : j.w;
+			int w = j.w < 0 || pass == 1? std::max(j.qlen, j.tlen) : j.w;
 			int n_col = std::min(j.qlen, j.tlen);
 			n_col = ((std::min(n_col, w + 1) + 15) / 16 + 1) * 16;
 			maxp = std::max(maxp, (size_t)(j.qlen + j.tlen - 1) * n_col + 16);
 		}
 		A.L = (maxt + 15) / 16 * 16, A.LQ = (maxq + 15) / 16 * 16;
 		const int G = tiers[k].G, nw = tiers[k].nw, threads = G * nw;
-		size_t smem = ((size_t)15 * A.L + A.LQ + 64 + 1024) * nw;
+		const bool gstate = k == n_tiers - 1;
+		const size_t state_bytes = (size_t)16 * A.L + A.LQ + 64 + 1024;
+		size_t smem = gstate? (size_t)1024 * nw : state_bytes * nw;
 		int cta_per_sm = 1;
 		{ // opt in to the full shared-memory carve-out once (never lowered: several scheduler groups launch concurrently)
 			static std::once_flag once;
 			std::call_once(once, [&]() {
-				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
-				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
+				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
+				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
+				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
+				MMB_CUDA_CHECK(cudaFuncSetAttribute(ksw_extd2_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024));
 			});
 		}
-		if (G == 32) MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<32>, threads, smem));
-		else MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, ksw_extd2_kernel<256>, threads, smem));
+		void (*kern)(KswArgs) = G == 32? (pass? ksw_extd2_kernel<32, true> : ksw_extd2_kernel<32, false>) : (pass? ksw_extd2_kernel<256, true> : ksw_extd2_kernel<256, false>);
+		MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cta_per_sm, kern, threads, smem));
 		if (smem > ctx->smem_optin - 1024 || cta_per_sm < 1) {
 			fprintf(stderr, "[ERROR] ksw tier %d needs %zu B shared memory per CTA\n", k, smem);
 			abort();
@@ -669,27 +760,29 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		int grid = ctx->n_sm * cta_per_sm;
 		int need = ((int)v.size() + nw - 1) / nw;
 		grid = std::max(1, std::min(grid, need));
-		const int workers = grid * nw;
 		maxp = (maxp + 255) & ~(size_t)255;
-		// bound the traceback workspace (8 GB): fewer resident workers for very large matrices
-		while ((size_t)workers * maxp > ((size_t)8 << 30) && grid > 1) grid = (grid + 1) / 2;
+		const size_t gws_stride = gstate? (state_bytes + 255) & ~(size_t)255 : 0;
+		// bound the workspace (8 GB): fewer resident workers for very large matrices
+		while ((size_t)grid * nw * (maxp + gws_stride) > ((size_t)8 << 30) && grid > 1) grid = (grid + 1) / 2;
 		A.pws_stride = maxp, A.cigws_stride = (size_t)maxsum + 8;
 		int *d_order = d_queues + g_off; g_off += v.size() + 1;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		A.counter = d_order, A.order = d_order + 1, A.n = (int)v.size();
 		KswPlan pl;
-		pl.pws_bytes = A.pws_stride * (size_t)grid * nw, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nw;
+		const size_t pws_area = A.pws_stride * (size_t)grid * nw;
+		pl.pws_bytes = pws_area + gws_stride * (size_t)grid * nw, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nw;
 		const KswArgs A0 = A;
 		pl.go = [=](uint8_t *pws, uint32_t *cigws) {
 			KswArgs B = A0;
 			B.pws = pws, B.cigws = cigws;
-			if (G == 32) ksw_extd2_kernel<32><<<grid, threads, smem, ctx->stream>>>(B);
-			else ksw_extd2_kernel<256><<<grid, threads, smem, ctx->stream>>>(B);
+			B.gws = gstate? pws + pws_area : nullptr, B.gws_stride = gws_stride;
+			kern<<<grid, threads, smem, ctx->stream>>>(B);
 			MMB_CUDA_CHECK(cudaGetLastError());
 			++ctx->n_launch;
 		};
 		plans.push_back(pl);
+	}
 	}
 	// one workspace sized for the largest launch (they run one after another on the stream), then the kernels back to back
 	size_t pws_bytes = 0, cigws_bytes = 0;

@@ -483,6 +483,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				sc.mat[0 * m + 2] = t, sc.mat[1 * m + 3] = t, sc.mat[2 * m + 0] = t, sc.mat[3 * m + 1] = t;
 			}
 			sc.q = (int8_t)opt->q, sc.e = (int8_t)opt->e, sc.q2 = (int8_t)opt->q2, sc.e2 = (int8_t)opt->e2;
+			sc.noncan = (int8_t)opt->noncan, sc.junc_bonus = (int8_t)opt->junc_bonus, sc.junc_pen = (int8_t)opt->junc_pen;
 		}
 		std::vector<int> active;
 		for (int j = 0; j < n; ++j) if (!rs[live[j]].done) active.push_back(live[j]);

@@ -13,8 +13,8 @@
 #undef __launch_bounds__
 #define __launch_bounds__(...)
 #define MMB_EMU 1
-#define cudaFuncSetAttribute(f, a, v) (cudaSuccess)                 /* kernels are plain functions here */
-#define cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, f, b, s) (*(n) = 1, cudaSuccess)
+#define cudaFuncSetAttribute(...) (cudaSuccess)                      /* kernels are plain functions here */
+#define cudaOccupancyMaxActiveBlocksPerMultiprocessor(n, ...) (*(n) = 1, cudaSuccess)
 
 extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;

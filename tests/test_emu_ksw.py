@@ -10,12 +10,12 @@ import pytest
 import oracle_lib as O
 
 sys.path.insert(0, os.path.join(O.ROOT, "tests", "cuda_emu"))
+sys.path.insert(0, O.ROOT)
 EXT, RIGHT, REVC, APPROX, SCORE_ONLY = 0x40, 0x02, 0x80, 0x08, 0x01
 JOB_LL, JOB_ZDROP = 0x20000, 0x40000
 
 
-@pytest.fixture(scope="module")
-def emu():
+def load_emu():
     import build_emu
     from minimap2_b200._lib import KswJob, KswRes, KswScore
     L = C.CDLL(build_emu.build("mmb_emu_k3", ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu"]))
@@ -25,6 +25,11 @@ def emu():
     ctx = C.c_void_p(L.mmb_ctx_create(0))
     assert ctx.value
     return L, ctx, KswJob, KswRes, KswScore
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu()
 
 
 def run_jobs(emu, mat, q, e, q2, e2, pairs, params):
@@ -116,3 +121,81 @@ def test_emulated_kernels_match_oracle(emu):
             assert zd == zdrop_scan(qq, tt, mat, exp["cigar"], 4, 2), (i, zd)
             n_zd += 1
     assert n_zd >= 20
+
+
+def small_spliced_pair(rng, n_exon, err):
+    ex = [rng.integers(0, 4, int(rng.integers(20, 90))).astype(np.uint8) for _ in range(n_exon)]
+    parts = [ex[0]]
+    for k in range(1, n_exon):
+        intron = rng.integers(0, 4, int(rng.integers(30, 200))).astype(np.uint8)
+        sig = int(rng.integers(0, 5))
+        if sig < 3: intron[:2] = [2, 3]; intron[-2:] = [0, 2]
+        elif sig == 3: intron[:2] = [2, 1]; intron[-2:] = [0, 2]
+        parts += [intron, ex[k]]
+    q = O.mutate(np.concatenate(ex), rng, err=err)
+    return (q if len(q) else np.array([0], dtype=np.uint8)), np.concatenate(parts)
+
+
+def check_splice_jobs(emu, rng, models, n_jobs, max_exons):
+    L, ctx, KswJob, KswRes, KswScore = emu
+    SPF, SPR, JOB_SPLICE = 0x100, 0x200, 0x80000
+    mat = O.simple_mat(1, 2, 1)
+    for model in models:  # the model bits are per batch (mm_mapopt_t), the strand bits per job
+        pairs, params = [], []
+        for it in range(n_jobs):
+            q, t = small_spliced_pair(rng, int(rng.integers(1, max_exons + 1)), float(rng.choice([0.0, 0.03, 0.1])))
+            if rng.random() < 0.1:
+                q[rng.integers(0, len(q))] = 4
+            base = int(rng.choice([0, APPROX, EXT, EXT | RIGHT | REVC, RIGHT]))
+            pairs.append((q, t)); params.append(dict(w=-1, zdrop=int(rng.choice([-1, 200])), end_bonus=int(rng.choice([-1, 10])), flag=base | int(rng.choice([SPF, SPR])) | model | JOB_SPLICE))
+        n = len(pairs)
+        qcat = np.concatenate([p[0] for p in pairs]); tcat = np.concatenate([p[1] for p in pairs])
+        jobs = (KswJob * n)(); qo = to = tot = 0
+        for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
+            j = jobs[i]
+            j.q_start, j.t_start, j.q_step, j.t_step, j.qlen, j.tlen = qo, to, 1, 1, len(qq), len(tt)
+            j.w, j.zdrop, j.end_bonus, j.flag = pr["w"], pr["zdrop"], pr["end_bonus"], pr["flag"]
+            qo += len(qq); to += len(tt); tot += len(qq) + len(tt) + 2
+        sc = KswScore()
+        for i in range(25):
+            sc.mat[i] = int(mat[i])
+        sc.q, sc.e, sc.q2, sc.e2, sc.noncan, sc.junc_bonus, sc.junc_pen = 2, 1, 32, 0, 9, 9, 5
+        res = (KswRes * n)(); cig = np.zeros(tot, dtype=np.uint32)
+        used = L.mmb_ksw_batch_host(ctx, C.byref(sc), n, jobs, qcat.ctypes.data, len(qcat), tcat.ctypes.data, len(tcat), res, cig.ctypes.data, len(cig))
+        assert used >= 0
+        for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
+            r = res[i]
+            g = dict(max=r.max, zdropped=r.zdropped, max_q=r.max_q, max_t=r.max_t, mqe=r.mqe, mqe_t=r.mqe_t, mte=r.mte, mte_q=r.mte_q, score=r.score,
+                     n_cigar=r.n_cigar, reach_end=r.reach_end, cigar=[int(x) for x in cig[r.cigar_off:r.cigar_off + r.n_cigar]])
+            exp = O.oracle_exts2(qq, tt, mat, 2, 1, 32, 9, pr["zdrop"], pr["end_bonus"], 9, 5, pr["flag"] & 0x1fff)
+            assert g == exp, (hex(model), i, len(qq), len(tt), hex(pr["flag"]), {k: (g[k], exp[k]) for k in exp if g[k] != exp[k] and k != "cigar"}, g["cigar"][:8], exp["cigar"][:8])
+
+
+def test_emulated_splice_kernel_matches_oracle(emu):
+    """ksw_extd2_kernel<G, SP=true> (ksw_exts2_sse: intron state, donor/acceptor signals) under the emulator vs the oracle's restatement"""
+    FLANK, CMPLX = 0x400, 0x800
+    check_splice_jobs(emu, np.random.default_rng(77), (FLANK | CMPLX, FLANK, 0), 30, 4)
+
+
+def test_emulated_hbm_state_tier():
+    """the tier that keeps the DP state in HBM (targets > 13000 on the device): MM_B200_KSW_SMEM_MAXLEN moves tiny jobs there. The
+    library reads the variable once, hence the separate process."""
+    import subprocess
+    env = dict(os.environ, MM_B200_KSW_SMEM_MAXLEN="48")
+    p = subprocess.run([sys.executable, os.path.abspath(__file__), "hbm-tier"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1800)
+    assert p.returncode == 0 and b"HBM_TIER_OK" in p.stdout, p.stdout.decode()[-2000:]
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "hbm-tier":
+    e = load_emu()
+    rng = np.random.default_rng(5)
+    mat = O.simple_mat(2, 4, 1)
+    pairs, params = [], []
+    for it in range(3):
+        t = rng.integers(0, 4, int(rng.integers(60, 110))).astype(np.uint8)
+        q = O.mutate(t, rng, err=0.1)
+        pairs.append((q, t)); params.append(dict(w=int(rng.choice([-1, 20])), zdrop=200, end_bonus=-1, flag=[0, EXT, EXT | RIGHT | REVC][it % 3]))
+    for (g, _), (qq, tt), pr in zip(run_jobs(e, mat, 4, 2, 24, 1, pairs, params), pairs, params):
+        assert g == O.oracle_extd2(qq, tt, mat, 4, 2, 24, 1, pr["w"], pr["zdrop"], pr["end_bonus"], pr["flag"])
+    check_splice_jobs(e, rng, (0x400 | 0x800,), 3, 2)
+    print("HBM_TIER_OK")

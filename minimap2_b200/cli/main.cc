@@ -96,6 +96,13 @@ int main(int argc, char *argv[])
 		else if (c == 'b') opt.transition = atoi(optarg);
 		else if (c == 's') opt.min_dp_max = atoi(optarg);
 		else if (c == 'C') opt.noncan = atoi(optarg);
+		else if (c == 'u') { // transcript strand (main.c:332-341)
+			if (*optarg == 'b') opt.flag |= MM_F_SPLICE_FOR | MM_F_SPLICE_REV;
+			else if (*optarg == 'f') opt.flag |= MM_F_SPLICE_FOR, opt.flag &= ~MM_F_SPLICE_REV;
+			else if (*optarg == 'r') opt.flag |= MM_F_SPLICE_REV, opt.flag &= ~MM_F_SPLICE_FOR;
+			else if (*optarg == 'n') opt.flag &= ~(MM_F_SPLICE_FOR | MM_F_SPLICE_REV);
+			else { fprintf(stderr, "[ERROR] unrecognized cDNA direction\n"); return 1; }
+		}
 		else if (c == 'I') ipt.batch_size = parse_num(optarg);
 		else if (c == 'K') opt.mini_batch_size = parse_num(optarg);
 		else if (c == 'e') opt.occ_dist = (int)parse_num(optarg);

@@ -229,8 +229,8 @@ std::mutex g_group_mu;
 void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 {
 	const char *what = nullptr;
-	if (opt->flag & MM_F_SPLICE) what = "spliced alignment (-x splice: ksw_exts2)";
-	else if (opt->flag & MM_F_SR) what = "short-read mode (-x sr)";
+	if (opt->flag & (MM_F_SR | MM_F_SR_RNA)) what = "short-read mode (-x sr / splice:sr)";
+	else if (opt->max_occ > opt->mid_occ) what = "re-chaining with a second occurrence cutoff (-f INT,INT)";
 	else if (opt->flag & MM_F_RMQ) what = "RMQ chaining as the primary chainer (--rmq / asm presets)";
 	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
 	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";

@@ -57,25 +57,33 @@ void __syncthreads()
 	else B.cv.wait(lk, [&]() { return B.gen != g; });
 }
 
+// One set of OS threads per launch; the blocks of the grid run one after another on it (thread t plays CUDA thread t of every block).
 void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
 	const int nt = (int)(block.x * block.y * block.z);
-	for (unsigned bz = 0; bz < grid.z; ++bz) for (unsigned by = 0; by < grid.y; ++by) for (unsigned bx = 0; bx < grid.x; ++bx) {
-		BlockState B;
+	const long n_blocks = (long)grid.x * grid.y * grid.z;
+	if (n_blocks <= 0 || nt <= 0) return;
+	BlockState B;
+	std::mutex gmu; std::condition_variable gcv; // block-to-block hand-over
+	long cur = 0; int done = 0;
+	auto reset_block = [&]() {
 		B.warps = std::vector<WarpState>((nt + 31) / 32);
 		for (int t = 0; t < nt; ++t) B.warps[t >> 5].alive |= 1u << (t & 31);
-		B.alive = nt;
+		B.alive = nt, B.arrived = 0, B.gen = 0;
 		B.smem.assign(smem_bytes + 64, 0);
-		g_block = &B;
-		std::vector<std::thread> th;
-		for (int t = 0; t < nt; ++t)
-			th.emplace_back([&, t]() {
-				tl_tid = t;
-				threadIdx.x = t % block.x, threadIdx.y = t / block.x % block.y, threadIdx.z = t / (block.x * block.y);
-				blockIdx.x = bx, blockIdx.y = by, blockIdx.z = bz;
-				blockDim = block, gridDim = grid;
+	};
+	reset_block();
+	g_block = &B;
+	std::vector<std::thread> th;
+	for (int t = 0; t < nt; ++t)
+		th.emplace_back([&, t]() {
+			tl_tid = t;
+			blockDim = block, gridDim = grid;
+			threadIdx.x = t % block.x, threadIdx.y = t / block.x % block.y, threadIdx.z = t / (block.x * block.y);
+			for (long bi = 0; bi < n_blocks; ++bi) {
+				blockIdx.x = (unsigned)(bi % grid.x), blockIdx.y = (unsigned)(bi / grid.x % grid.y), blockIdx.z = (unsigned)(bi / ((long)grid.x * grid.y));
 				body();
-				{ // the thread leaves: pending rendezvous of its warp / block may now be complete
+				{ // the thread leaves the block: pending rendezvous of its warp / block may now be complete
 					WarpState &W = B.warps[t >> 5];
 					std::lock_guard<std::mutex> lk(W.mu);
 					W.alive &= ~(1u << (t & 31));
@@ -87,10 +95,14 @@ void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<vo
 					if (B.alive > 0 && B.arrived >= B.alive) { B.arrived = 0, ++B.gen; }
 					B.cv.notify_all();
 				}
-			});
-		for (auto &x : th) x.join();
-		g_block = nullptr;
-	}
+				// wait until every thread has left, then the last one prepares the next block
+				std::unique_lock<std::mutex> lk(gmu);
+				if (++done == nt) { done = 0; if (bi + 1 < n_blocks) reset_block(); ++cur; gcv.notify_all(); }
+				else gcv.wait(lk, [&]() { return cur > bi; });
+			}
+		});
+	for (auto &x : th) x.join();
+	g_block = nullptr;
 }
 
 // ---- CUDA runtime on host memory ----

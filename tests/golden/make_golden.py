@@ -44,6 +44,8 @@ CASES = {
     "hifi_paf_cigar": ["-x", "map-hifi", "-c", "synth-ref.fa", "synth-hifi.fa"],
     "mt_paf_single_affine": ["-c", "-O4", "-E2", "MT-human.fa", "MT-orang.fa"],          # q == q2, e == e2: ksw_extz2 in the reference
     "ont_paf_single_affine": ["-x", "map-ont", "-c", "-O6", "-E2", "synth-ref.fa", "synth-ont.fa"],
+    "splice_paf_cs": ["-x", "splice", "-c", "--cs", "synth-gene.fa", "synth-cdna.fa"],          # ksw_exts2 path: introns, ts:A, both transcript strands
+    "splice_sam_fwd": ["-x", "splice", "-uf", "-a", "--MD", "synth-gene.fa", "synth-cdna.fa"],   # forward transcript strand only
 }
 
 
@@ -54,6 +56,29 @@ def write_synthetic_inputs():
     synth.write_fasta(os.path.join(DATA, "synth-ont.fa"), ["ont%d" % i for i in range(len(reads))], reads)
     reads = synth.make_reads(contigs, 12, 6000, 0.01, 112, chimeric_frac=0.0)
     synth.write_fasta(os.path.join(DATA, "synth-hifi.fa"), ["hifi%d" % i for i in range(len(reads))], reads)
+
+
+def write_spliced_inputs():
+    """a 60 kb 'gene region' with planted GT..AG / CT..AC signals and cDNA reads made of 2-4 exons (3 % errors), both strands"""
+    rng = np.random.default_rng(3)
+    contigs = synth.random_genome(60_000, 31, n_contigs=1, repeat_frac=0.0)
+    g = np.frombuffer(bytes(contigs[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for i in range(10):
+        pos = int(rng.integers(1000, len(g) - 12000)); exons = []; rev = i % 2 == 1
+        for k in range(int(rng.integers(2, 5))):
+            el = int(rng.integers(90, 300)); exons.append((pos, pos + el)); il = int(rng.integers(150, 1500))
+            if i % 3 != 2:
+                d, a = (b"GT", b"AG") if not rev else (b"CT", b"AC")
+                g[pos + el:pos + el + 2] = list(d); g[pos + el + il - 2:pos + el + il] = list(a)
+            pos += el + il
+        tr = np.concatenate([g[s:e] for s, e in exons])
+        if rev:
+            tr = comp[tr[::-1]]
+        reads.append(synth.mutate_ascii(tr, rng, 0.03))
+    synth.write_fasta(os.path.join(DATA, "synth-gene.fa"), ["chr0"], [g.tobytes()])
+    synth.write_fasta(os.path.join(DATA, "synth-cdna.fa"), ["tr%d" % i for i in range(len(reads))], reads)
 
 
 def run_cases():
@@ -190,5 +215,6 @@ if __name__ == "__main__":
     if not (O.have_ref() and os.path.exists(O.REF_BIN)):
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference is mounted")
     write_synthetic_inputs()
+    write_spliced_inputs()
     run_cases()
     make_vectors()

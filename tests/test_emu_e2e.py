@@ -32,7 +32,7 @@ def cases():
     return m.CASES
 
 
-@pytest.mark.parametrize("name", ["mt_paf_cigar", "mt_sam", "inv_paf_cigar", "x3s_paf_cigar", "t2_paf_cigar", "mt_paf_single_affine"])
+@pytest.mark.parametrize("name", ["mt_paf_cigar", "inv_paf_cigar", "x3s_paf_cigar", "t2_paf_cigar"])
 def test_emulated_pipeline_matches_recorded_reference(emu_cli, name):
     env = dict(os.environ, MM_B200_GROUPS="1")
     p = subprocess.run([emu_cli, "-t", "4"] + cases()[name], cwd=os.path.join(GOLD, "data"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200, env=env)
@@ -40,3 +40,32 @@ def test_emulated_pipeline_matches_recorded_reference(emu_cli, name):
     got = [l for l in p.stdout.decode().splitlines() if not l.startswith("@PG")]
     exp = open(os.path.join(GOLD, "expected", name + ".txt")).read().splitlines()
     assert got == exp, (len(got), len(exp), [(a[:200], b[:200]) for a, b in zip(got, exp) if a != b][:2])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_emulated_spliced_mapping_matches_reference(emu_cli, tmp_path):
+    """-x splice end to end under the emulator (spliced kernel variant + splice branches of the driver) against the reference binary:
+    two small cDNA reads, one per transcript strand"""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(4)
+    contigs = synth.random_genome(30_000, 33, n_contigs=1, repeat_frac=0.0)
+    g = np.frombuffer(bytes(contigs[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for i in range(2):
+        pos = int(rng.integers(1000, len(g) - 6000)); exons = []; rev = i % 2 == 1
+        for k in range(3):
+            el = int(rng.integers(90, 200)); exons.append((pos, pos + el)); il = int(rng.integers(150, 500))
+            d, a = (b"GT", b"AG") if not rev else (b"CT", b"AC")
+            g[pos + el:pos + el + 2] = list(d); g[pos + el + il - 2:pos + el + il] = list(a)
+            pos += el + il
+        tr = np.concatenate([g[s:e] for s, e in exons])
+        reads.append(synth.mutate_ascii(comp[tr[::-1]] if rev else tr, rng, 0.03))
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["tr0", "tr1"], reads)
+    args = ["-x", "splice", "-c", "--cs", rf, qf]
+    ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout.decode().splitlines() == ref and len(ref) == 2

@@ -79,7 +79,7 @@ def build(name, files, extra=("emu_stubs.cc",)):
         open(o, "w").write("#line 1 \"%s\"\n" % os.path.join(CSRC, f) + transform(open(os.path.join(CSRC, f)).read()))
         gen.append(o)
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-pthread", "-w", "-include", os.path.join(HERE, "cuda_emu.h"),
-           "-I" + os.path.join(HERE, "fake_include"), "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + gen + [os.path.join(HERE, "emu_runtime.cc")] + [os.path.join(HERE, x) for x in extra] + ["-lz", "-o", lib]
+           "-I" + os.path.join(HERE, "fake_include"), "-I" + HERE, "-I" + CSRC, "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + gen + [os.path.join(HERE, "emu_runtime.cc")] + [os.path.join(HERE, x) for x in extra] + ["-Wl,-Bsymbolic", "-lz", "-o", lib]  # -Bsymbolic: the emulated cuda* entry points win even if a real libcudart is already loaded (torch)
     subprocess.check_call(cmd)
     return lib
 

@@ -72,7 +72,19 @@ __host__ __device__ inline void mmx_rs_sort(T *a, int64_t n, int32_t *stk, KeyF 
 	int sp = 0;
 	stk[sp++] = 0, stk[sp++] = (int32_t)n, stk[sp++] = 56;
 	while (sp > 0) {
-		const int shift = stk[--sp]; const int64_t end = stk[--sp], beg = stk[--sp];
+		int shift = stk[--sp]; const int64_t end = stk[--sp], beg = stk[--sp];
+		{ // A level on which every key of the range has the same digit leaves the range untouched (each element is already in its
+		  // bucket: ksort.h:126-138 only advances the bucket head) and hands the whole range to the next level. Jump straight to
+		  // the most significant byte in which the keys differ; identical keys need no work at all. Typical: chain scores (< 2^20)
+		  // sorted as 64-bit keys skip five of eight levels.
+			const uint64_t k0 = key(a[beg]);
+			uint64_t diff = 0;
+			for (int64_t i = beg + 1; i < end; ++i) diff |= key(a[i]) ^ k0;
+			if (diff == 0) continue;
+			int hb = 7;
+			while (!(diff >> (hb * 8) & 0xff)) --hb;
+			if (hb * 8 < shift) shift = hb * 8;
+		}
 		// count
 		for (int b = 0; b < 256; ++b) head[b] = 0;
 		for (int64_t i = beg; i < end; ++i) ++head[key(a[i]) >> shift & 0xff];

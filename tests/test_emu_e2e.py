@@ -69,3 +69,20 @@ def test_emulated_spliced_mapping_matches_reference(emu_cli, tmp_path):
     p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     assert p.stdout.decode().splitlines() == ref and len(ref) == 2
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_mmi_files_are_interchangeable(emu_cli, tmp_path):
+    """mm_idx_dump / mm_idx_load (index.c:475-569): the reference maps with an index file written here and this library maps with one
+    written by the reference, both giving the recorded reference output"""
+    data = os.path.join(GOLD, "data")
+    exp = open(os.path.join(GOLD, "expected", "mt_paf_cigar.txt")).read().splitlines()
+    mine, theirs = str(tmp_path / "mine.mmi"), str(tmp_path / "ref.mmi")
+    env = dict(os.environ, MM_B200_GROUPS="1")
+    subprocess.run([emu_cli, "-t", "2", "-d", mine, os.path.join(data, "MT-human.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    subprocess.run([O.REF_BIN, "-t", "2", "-d", theirs, os.path.join(data, "MT-human.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert os.path.getsize(mine) == os.path.getsize(theirs)
+    out = subprocess.run([O.REF_BIN, "-t", "2", "-c", mine, os.path.join(data, "MT-orang.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE).stdout.decode().splitlines()
+    assert out == exp
+    out = subprocess.run([emu_cli, "-t", "2", "-c", theirs, os.path.join(data, "MT-orang.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=1200).stdout.decode().splitlines()
+    assert out == exp

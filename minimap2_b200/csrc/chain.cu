@@ -225,20 +225,82 @@ __global__ void __launch_bounds__(128) chain_fill_kernel(ChainArgs A)
 	}
 }
 
+// mg_chain_backtrack + compact_a (lchain.c:27-111), one WARP per read: collecting the candidate ends (f >= min_sc), clearing t[] and
+// every bulk copy of compact_a are done by all lanes with coalesced accesses; the two unstable sorts and the peeling of chains
+// (a pointer chase through p[] whose order is part of the contract) stay sequential on lane 0.
 __global__ void __launch_bounds__(128) chain_bt_kernel(ChainArgs A)
 {
-	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	const int lane = threadIdx.x & 31;
+	const int rd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	if (rd >= A.n_reads) return;
+	const unsigned full = 0xffffffffu;
 	const int64_t off = A.a_off[rd];
 	const int32_t n = (int32_t)(A.a_off[rd + 1] - off);
-	A.n_u[rd] = 0, A.n_v[rd] = 0;
+	if (lane == 0) A.n_u[rd] = 0, A.n_v[rd] = 0;
 	if (n <= 0) return;
 	const mmb_chain_par_t &P = A.par;
-	const int32_t max_drop = P.is_cdna? INT32_MAX : P.bw;
-	int32_t n_u, n_v;
-	backtrack_compact(A.a + off, n, A.f + off, A.p + off, A.v + off, A.t + off, A.z + off, A.b + off, A.stk + A.stk_off[rd], P.min_sc, P.min_cnt, max_drop,
-					  A.u + off, A.a_out + off, &n_u, &n_v);
-	A.n_u[rd] = n_u, A.n_v[rd] = n_v;
+	const int32_t max_drop = P.is_cdna? INT32_MAX : P.bw, min_sc = P.min_sc, min_cnt = P.min_cnt;
+	const m128 *a = A.a + off;
+	const int32_t *f = A.f + off, *p = A.p + off;
+	int32_t *v = A.v + off, *t = A.t + off, *stk = A.stk + A.stk_off[rd];
+	m128 *z = A.z + off, *b = A.b + off, *ao = A.a_out + off;
+	uint64_t *u = A.u + off;
+	// candidate chain ends in anchor order (lchain.c:35-37), t[] cleared on the way
+	int32_t n_z = 0;
+	for (int32_t i0 = 0; i0 < n; i0 += 32) {
+		const int32_t i = i0 + lane;
+		const int32_t fi = i < n? f[i] : INT32_MIN;
+		const bool keep = i < n && fi >= min_sc;
+		const unsigned m = __ballot_sync(full, keep);
+		if (keep) { const int32_t k = n_z + __popc(m & ((1u << lane) - 1)); z[k].x = (uint64_t)(int64_t)fi, z[k].y = (uint64_t)i; }
+		n_z += __popc(m);
+		if (i < n) t[i] = 0;
+	}
+	__syncwarp();
+	if (n_z == 0) return;
+	int32_t n_u = 0, n_v = 0;
+	if (lane == 0) { // lchain.c:38-66: best end first; one filling pass suffices (v[] and u[] have capacity n)
+		mmx_rs_sort(z, (int64_t)n_z, stk, KeyX128());
+		for (int32_t k = n_z - 1; k >= 0; --k) {
+			if (t[z[k].y] == 0) {
+				const int32_t n_v0 = n_v, end_i = bk_end(max_drop, z, f, p, t, k);
+				int32_t i, sc;
+				for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
+				sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+				if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+				else n_v = n_v0;
+			}
+		}
+		A.n_u[rd] = n_u, A.n_v[rd] = n_v;
+	}
+	n_u = __shfl_sync(full, n_u, 0), n_v = __shfl_sync(full, n_v, 0);
+	__syncwarp();
+	if (n_u == 0) return;
+	// compact_a (lchain.c:78-111): chains laid out in b[] with their anchors in ascending order, then ordered by first target position
+	m128 *w = z; // z is free now; n_u <= n_z
+	int32_t k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t k0 = k, ni = (int32_t)u[i];
+		for (int32_t j = lane; j < ni; j += 32) b[k0 + j] = a[v[k0 + (ni - j - 1)]];
+		k += ni;
+	}
+	__syncwarp();
+	if (lane == 0) {
+		k = 0;
+		for (int32_t i = 0; i < n_u; ++i) { w[i].x = b[k].x, w[i].y = (uint64_t)k << 32 | (uint64_t)i; k += (int32_t)u[i]; }
+		mmx_rs_sort(w, (int64_t)n_u, stk, KeyX128());
+	}
+	__syncwarp();
+	k = 0;
+	for (int32_t i = 0; i < n_u; ++i) {
+		const int32_t j = (int32_t)w[i].y, nn = (int32_t)u[j], src = (int32_t)(w[i].y >> 32);
+		for (int32_t q = lane; q < nn; q += 32) ao[k + q] = b[src + q];
+		k += nn;
+	}
+	__syncwarp();
+	for (int32_t i = lane; i < n_u; i += 32) w[i].x = u[(int32_t)w[i].y]; // the chain's u value travels with its rank
+	__syncwarp();
+	for (int32_t i = lane; i < n_u; i += 32) u[i] = w[i].x;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -380,7 +442,7 @@ void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, c
 	A.n_u = d_n_u, A.n_v = d_n_v, A.u = d_u, A.a_out = d_a_out;
 	ProfScope prof(ctx, MMB_PROF_CHAIN, (uint64_t)n_tot);
 	chain_fill_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
-	chain_bt_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(A);
+	chain_bt_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
 	MMB_CUDA_CHECK(cudaGetLastError());
 	ctx->n_launch += 2;
 }

@@ -160,12 +160,126 @@ __device__ __forceinline__ void heap_down(uint64_t *b, int i, int n) // max-heap
 	b[i] = tmp;
 }
 
+#define SEL_CAP 2048
+// mm_collect_matches (seed.c:98-132) for reads with at most SEL_CAP minimizers, one WARP per read: the lookups that hit are compacted
+// by ballots into shared memory (occurrence count, query position, span), the high-occurrence streak selection (seed.c:56-96, a
+// sequential scan with a 128-entry heap) runs on lane 0 over that shared copy, and the final pass (rep_len, anchor offsets by a
+// warp scan, mini_pos, compaction of the kept seeds) is lane-parallel again. Longer reads go through select_kernel below.
+__global__ void __launch_bounds__(128) select_warp_kernel(SeedArgs A)
+{
+	extern __shared__ __align__(16) uint8_t sel_sm[];
+	const int lane = threadIdx.x & 31, wk = threadIdx.x >> 5;
+	const int rd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (rd >= A.n_reads) return;
+	const unsigned full = 0xffffffffu, lt = (1u << lane) - 1;
+	const int64_t base = A.mz_off[rd];
+	const int n = A.n_mz[rd], qlen = A.qlen[rd];
+	if (n > SEL_CAP) return;
+	uint32_t *sn = (uint32_t*)(sel_sm + (size_t)wk * SEL_CAP * 10), *qp = sn + SEL_CAP;
+	uint8_t *sp = (uint8_t*)(qp + SEL_CAP), *fl = sp + SEL_CAP;
+	const m128 *mz = A.mz + base;
+	const uint32_t *s_n = A.s_n + base;
+	uint32_t *kidx = A.k_idx + base;
+	// mm_seed_collect_all (seed.c:30-52)
+	int n_m0 = 0;
+	for (int i0 = 0; i0 < n; i0 += 32) {
+		const int i = i0 + lane;
+		uint32_t cnt = 0, tandem = 0; uint64_t x = 0, y = 0;
+		if (i < n) {
+			cnt = s_n[i], x = mz[i].x, y = mz[i].y;
+			if (i > 0 && x >> 8 == mz[i - 1].x >> 8) tandem = 1;
+			if (i < n - 1 && x >> 8 == mz[i + 1].x >> 8) tandem = 1;
+		}
+		const bool keep = cnt > 0;
+		const unsigned m = __ballot_sync(full, keep);
+		if (keep) {
+			const int k = n_m0 + __popc(m & lt);
+			kidx[k] = (uint32_t)i | tandem << 31;
+			sn[k] = cnt, qp[k] = (uint32_t)y, sp[k] = (uint8_t)(x & 0xff), fl[k] = 0;
+		}
+		n_m0 += __popc(m);
+	}
+	__syncwarp();
+	const int max_occ = A.max_occ, max_max_occ = A.max_max_occ, dist = A.occ_dist;
+	if (dist > 0 && max_max_occ > max_occ) { // mm_seed_select (seed.c:56-96)
+		bool any = false;
+		for (int j = lane; j < n_m0; j += 32) any = any || (int)sn[j] > max_occ;
+		if (n_m0 > 1 && __any_sync(full, any)) {
+			if (lane == 0) {
+				uint64_t b[128];
+				for (int i = 0, last0 = -1; i <= n_m0; ++i) {
+					if (i == n_m0 || (int)sn[i] <= max_occ) {
+						if (i - last0 > 1) {
+							const int ps = last0 < 0? 0 : (int)(qp[last0] >> 1);
+							const int pe = i == n_m0? qlen : (int)(qp[i] >> 1);
+							const int st = last0 + 1, en = i;
+							int max_high_occ = (int)((double)(pe - ps) / dist + .499);
+							if (max_high_occ > 0) {
+								if (max_high_occ > 128) max_high_occ = 128;
+								int j, k;
+								for (j = st, k = 0; j < en && k < max_high_occ; ++j, ++k) b[k] = (uint64_t)sn[j] << 32 | (uint32_t)j;
+								for (int h = (k >> 1) - 1; h >= 0; --h) heap_down(b, h, k);
+								for (; j < en; ++j)
+									if ((int32_t)sn[j] < (int32_t)(b[0] >> 32)) { b[0] = (uint64_t)sn[j] << 32 | (uint32_t)j; heap_down(b, 0, k); }
+								for (j = 0; j < k; ++j) fl[(uint32_t)b[j]] = 1;
+							}
+							for (int j = st; j < en; ++j) fl[j] ^= 1;
+							for (int j = st; j < en; ++j) if ((int)sn[j] > max_max_occ) fl[j] = 1;
+						}
+						last0 = i;
+					}
+				}
+			}
+			__syncwarp();
+		}
+	} else {
+		for (int j = lane; j < n_m0; j += 32) if ((int)sn[j] > max_occ) fl[j] = 1;
+		__syncwarp();
+	}
+	// seed.c:113-130
+	int rep_st = 0, rep_en = 0, rep_len = 0, n_keep = 0; // rep_*: lane 0 only
+	int64_t n_a = 0;
+	uint64_t *mini_pos = A.mini_pos + base;
+	uint32_t *k_aoff = A.k_aoff + base;
+	for (int j0 = 0; j0 < n_m0; j0 += 32) {
+		const int j = j0 + lane;
+		const bool valid = j < n_m0, f = valid && fl[j], kept = valid && !fl[j];
+		const unsigned mf = __ballot_sync(full, f), mk = __ballot_sync(full, kept);
+		if (lane == 0) // masked stretches merge in query order
+			for (unsigned mm = mf; mm; mm &= mm - 1) {
+				const int jj = j0 + __ffs(mm) - 1;
+				const int en = (int)(qp[jj] >> 1) + 1, st = en - (int)sp[jj];
+				if (st > rep_en) { rep_len += rep_en - rep_st; rep_st = st, rep_en = en; }
+				else rep_en = en;
+			}
+		uint32_t inc = kept? sn[j] : 0;
+		const uint32_t mine = inc;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { const uint32_t yv = __shfl_up_sync(full, inc, o); if (lane >= o) inc += yv; }
+		const uint32_t e = valid? kidx[j] : 0;
+		__syncwarp(); // every lane has read its kidx entry before the compaction overwrites earlier slots
+		if (kept) {
+			const int dst = n_keep + __popc(mk & lt);
+			k_aoff[dst] = (uint32_t)(n_a + (inc - mine));
+			mini_pos[dst] = (uint64_t)sp[j] << 32 | qp[j] >> 1;
+			kidx[dst] = e;
+		}
+		n_keep += __popc(mk);
+		n_a += __shfl_sync(full, inc, 31);
+	}
+	if (lane == 0) {
+		rep_len += rep_en - rep_st;
+		A.n_keep[rd] = n_keep, A.rep_len[rd] = rep_len, A.n_a[rd] = n_a;
+	}
+}
+
 __global__ void __launch_bounds__(128) select_kernel(SeedArgs A)
 {
 	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
 	if (rd >= A.n_reads) return;
 	const int64_t base = A.mz_off[rd];
 	const int n = A.n_mz[rd], qlen = A.qlen[rd];
+	if (n <= SEL_CAP) return;              // select_warp_kernel's share
 	const m128 *mz = A.mz + base;
 	const uint32_t *s_n = A.s_n + base;
 	uint32_t *kidx = A.k_idx + base;       // kept-seed list: minimizer index | tandem<<31 ; first used as the m[] list
@@ -542,8 +656,14 @@ void mmb_seed_select_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz)
 	mzflt_kernel<<<rb, 128, 0, ctx->stream>>>(A);
 	++ctx->n_launch;
 	if (total_mz > 0) lookup_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
-	select_kernel<<<rb, 128, 0, ctx->stream>>>(A);
-	ctx->n_launch += 3;
+	{
+		const size_t smem = (size_t)SEL_CAP * 10 * 4;
+		static std::once_flag once;
+		std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(select_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); });
+		select_warp_kernel<<<(unsigned)(((int64_t)A.n_reads * 32 + 127) / 128), 128, smem, ctx->stream>>>(A);
+	}
+	select_kernel<<<rb, 128, 0, ctx->stream>>>(A); // reads with more than SEL_CAP minimizers
+	ctx->n_launch += 4;
 	if ((A.flag & MMB_SKIP_FLAGS) && total_mz > 0) { // skip_seed changes the anchor counts (map.c:78-100)
 		skip_count_kernel<<<(unsigned)((total_mz + 255) / 256), 256, 0, ctx->stream>>>(A, total_mz);
 		skip_offsets_kernel<<<rb, 128, 0, ctx->stream>>>(A);

@@ -86,3 +86,28 @@ def test_mmi_files_are_interchangeable(emu_cli, tmp_path):
     assert out == exp
     out = subprocess.run([emu_cli, "-t", "2", "-c", theirs, os.path.join(data, "MT-orang.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=1200).stdout.decode().splitlines()
     assert out == exp
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_emulated_high_occurrence_seed_selection_matches_reference(emu_cli, tmp_path):
+    """mm_seed_select (seed.c:56-96) on the device: a genome made mostly of copies of one 400 bp unit and -f 3 put most minimizers of
+    every read above mid_occ, so the streak selection (heap of the lowest-occurrence seeds per stretch, max_max_occ cut, rep_len)
+    decides which seeds are kept; -e 150 makes several seeds per stretch survive. Output equals the reference binary's."""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(11)
+    g = np.frombuffer(bytes(synth.random_genome(9_000, 5)[0]), dtype=np.uint8).copy()
+    unit = g[200:600].copy()
+    for k in range(9):
+        s = 900 + k * 800
+        g[s:s + 400] = unit
+        g[s + rng.integers(0, 400, 3)] = list(b"ACG")  # a few point differences between the copies
+    reads = [synth.mutate_ascii(g[s:s + 1300], rng, 0.04) for s in (300, 2500, 5200)]
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["r0", "r1", "r2"], reads)
+    args = ["-c", "-f", "3", "-e", "150", rf, qf]
+    ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout.decode().splitlines() == ref and len(ref) >= 3
+    assert any("rl:i:" in l and "rl:i:0" not in l for l in ref)  # the selection really masked something

@@ -120,7 +120,7 @@ typedef struct {
  * (n_v[i] of them). u_out capacity must be >= total anchors/ min_cnt... (pass total anchors to be safe). */
 int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
 						 int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy);
-/* Same layout, but every read goes through mg_lchain_rmq (lchain.c:251-357; the long-join rescue chainer of map.c:283-292).
+/* Same layout, but every read goes through mg_lchain_rmq (lchain.c:251-357; the MM_F_RMQ chainer of map.c:275-276 and the long-join rescue chainer of map.c:283-292).
  * par: max_dist_x = max_dist, max_dist_inner, bw, max_skip, rmq_size_cap, min_cnt, min_sc, chn_pen_gap, chn_pen_skip. */
 int mmb_chain_rmq_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
 							 int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy);

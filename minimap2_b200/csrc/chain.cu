@@ -325,18 +325,22 @@ __global__ void __launch_bounds__(64) chain_rescue_kernel(ChainArgs A, RescuePar
 {
 	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
 	if (rd >= A.n_reads) return;
-	const int32_t n_u0 = A.n_u[rd];
-	if (n_u0 <= 1) return;
 	const int64_t off = A.a_off[rd];
 	m128 *a = A.a_out + off;
 	uint64_t *u = A.u + off;
-	const int32_t n = A.n_v[rd], qlen = R.qlen[rd];
-	{
+	int32_t *stk = A.stk + A.stk_off[rd];
+	int32_t n;
+	if (R.primary) { // first chainer: all anchors of the read, in the order the seed sort left them (already copied into a_out)
+		n = (int32_t)(A.a_off[rd + 1] - off);
+		if (n == 0) { A.n_u[rd] = 0, A.n_v[rd] = 0; return; } // lchain.c:261-264
+	} else {         // map.c:283-291
+		if (A.n_u[rd] <= 1) return;
+		n = A.n_v[rd];
+		const int32_t qlen = R.qlen[rd];
 		const int32_t st = (int32_t)a[0].y, en = (int32_t)a[(int32_t)u[0] - 1].y;
 		if (!(qlen - (en - st) > R.rescue_size || (float)(en - st) > (float)qlen * R.rescue_ratio)) return;
+		mmx_rs_sort(a, (int64_t)n, stk, KeyX128());
 	}
-	int32_t *stk = A.stk + A.stk_off[rd];
-	mmx_rs_sort(a, (int64_t)n, stk, KeyX128());
 	int32_t *f = A.f + off, *p = A.p + off, *v = A.v + off, *t = A.t + off;
 	int32_t max_dist = R.max_dist, max_dist_inner = R.max_dist_inner;
 	const int32_t bw = R.bw, max_chn_skip = R.max_skip, cap = R.rmq_size_cap;
@@ -420,6 +424,23 @@ __global__ void stk_len_kernel(const int64_t *a_off, int n_reads, int64_t *stk_o
 
 #include "scan.cuh"
 
+// scratch layout shared by the DP, backtrack and RMQ kernels: f,p,v,t (4 x int32 n_tot) | z (m128 n_tot) | b (m128 n_tot); sort stacks
+static void chain_scratch_setup(mmb_ctx_t *ctx, ChainArgs &A, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
+								int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2)
+{
+	A.n_reads = n_reads, A.a_off = d_a_off, A.a = d_a;
+	const size_t n = (size_t)n_tot + 4;
+	uint8_t *s = (uint8_t*)scratch.reserve(n * (16 + 16 + 16) + 256);
+	A.f = (int32_t*)s, A.p = A.f + n, A.v = A.p + n, A.t = A.v + n;
+	A.z = (m128*)(s + n * 16), A.b = A.z + n;
+	int64_t *d_stk_off = (int64_t*)scratch2.reserve(((size_t)n_reads + 1) * 8 + ((size_t)n_tot / 65 * 24 + (size_t)n_reads * 48 + 64) * 4);
+	stk_len_kernel<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(d_a_off, n_reads, d_stk_off);
+	++ctx->n_launch;
+	mmb_exclusive_scan_i64_async(ctx, d_stk_off, n_reads);
+	A.stk_off = d_stk_off, A.stk = (int32_t*)(d_stk_off + n_reads + 1);
+	A.n_u = d_n_u, A.n_v = d_n_v, A.u = d_u, A.a_out = d_a_out;
+}
+
 // Device-level launcher (asynchronous). d_a: anchors (sorted by x per read), d_a_off: n_reads+1 offsets, total anchors n_tot.
 // Outputs (device): d_n_u, d_n_v (n_reads), d_u (n_tot, at the read's anchor offset), d_a_out (n_tot).
 void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
@@ -427,19 +448,8 @@ void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, c
 {
 	if (n_reads <= 0) return;
 	ChainArgs A;
-	A.par = *par, A.n_reads = n_reads, A.a_off = d_a_off, A.a = d_a;
-	// scratch layout: f,p,v,t (4 x int32 n_tot) | z (m128 n_tot) | b (m128 n_tot)
-	const size_t n = (size_t)n_tot + 4;
-	uint8_t *s = (uint8_t*)scratch.reserve(n * (16 + 16 + 16) + 256);
-	A.f = (int32_t*)s, A.p = A.f + n, A.v = A.p + n, A.t = A.v + n;
-	A.z = (m128*)(s + n * 16), A.b = A.z + n;
-	// stack offsets
-	int64_t *d_stk_off = (int64_t*)scratch2.reserve(((size_t)n_reads + 1) * 8 + ((size_t)n_tot / 65 * 24 + (size_t)n_reads * 48 + 64) * 4);
-	stk_len_kernel<<<(n_reads + 255) / 256, 256, 0, ctx->stream>>>(d_a_off, n_reads, d_stk_off);
-	++ctx->n_launch;
-	mmb_exclusive_scan_i64_async(ctx, d_stk_off, n_reads);
-	A.stk_off = d_stk_off, A.stk = (int32_t*)(d_stk_off + n_reads + 1);
-	A.n_u = d_n_u, A.n_v = d_n_v, A.u = d_u, A.a_out = d_a_out;
+	A.par = *par;
+	chain_scratch_setup(ctx, A, n_reads, d_a, d_a_off, n_tot, d_n_u, d_n_v, d_u, d_a_out, scratch, scratch2);
 	ProfScope prof(ctx, MMB_PROF_CHAIN, (uint64_t)n_tot);
 	chain_fill_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
 	chain_bt_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
@@ -494,8 +504,28 @@ void mmb_chain_rescue_device(mmb_ctx_t *ctx, const RescuePar *rp, int n_reads, c
 	++ctx->n_launch;
 }
 
-// Kernel-level entry for mg_lchain_rmq alone (lchain.c:251-357), HOST buffers: every read is re-chained by the rescue kernel
-// regardless of the mapper's rescue condition (map.c:283-292). Used by the parity tests against the reference function.
+void mmb_chain_rmq_primary_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
+								  int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf)
+{
+	if (n_reads <= 0) return;
+	ChainArgs A;
+	memset(&A, 0, sizeof(A));
+	chain_scratch_setup(ctx, A, n_reads, d_a, d_a_off, n_tot, d_n_u, d_n_v, d_u, d_a_out, scratch, scratch2);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_a_out, d_a, sizeof(m128) * (size_t)n_tot, cudaMemcpyDeviceToDevice, ctx->stream)); // the kernel chains in place
+	RescuePar R;
+	memset(&R, 0, sizeof(R));
+	R.primary = 1, R.qlen = nullptr;
+	R.max_dist = par->max_dist_x, R.max_dist_inner = par->max_dist_inner, R.bw = par->bw, R.max_skip = par->max_skip;
+	R.rmq_size_cap = par->rmq_size_cap, R.min_cnt = par->min_cnt, R.min_sc = par->min_sc;
+	R.pen_gap = par->chn_pen_gap, R.pen_skip = par->chn_pen_skip;
+	R.tree = (uint8_t*)treebuf.reserve(((size_t)n_tot + (size_t)n_reads + 8) * 64), R.tree_off = d_a_off; // 64 B of tree node per anchor
+	ProfScope prof(ctx, MMB_PROF_CHAIN, (uint64_t)n_tot);
+	chain_rescue_kernel<<<(n_reads + 63) / 64, 64, 0, ctx->stream>>>(A, R);
+	MMB_CUDA_CHECK(cudaGetLastError());
+	++ctx->n_launch;
+}
+
+// Kernel-level entry for mg_lchain_rmq alone (lchain.c:251-357), HOST buffers. Used by the parity tests against the reference function.
 // par: max_dist_x = max_dist, max_dist_inner, bw, max_skip, rmq_size_cap, min_cnt, min_sc, chn_pen_gap, chn_pen_skip.
 extern "C" int mmb_chain_rmq_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,
 										int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy)
@@ -504,35 +534,13 @@ extern "C" int mmb_chain_rmq_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *p
 	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
 	const int64_t n_tot = a_off[n_reads];
 	m128 *d_a = ctx->d_a.as<m128>((size_t)n_tot + 1);
-	int64_t *d_off = ctx->d_b.as<int64_t>((size_t)n_reads * 2 + 2), *d_toff = d_off + n_reads + 1;
-	int32_t *d_nu = ctx->d_c.as<int32_t>((size_t)n_reads * 3 + 3), *d_nv = d_nu + n_reads, *d_qlen = d_nv + n_reads;
+	int64_t *d_off = ctx->d_b.as<int64_t>((size_t)n_reads + 1);
+	int32_t *d_nu = ctx->d_c.as<int32_t>((size_t)n_reads * 2 + 2), *d_nv = d_nu + n_reads;
 	uint64_t *d_u = ctx->d_d.as<uint64_t>((size_t)n_tot + 1);
 	m128 *d_ao = ctx->d_e.as<m128>((size_t)n_tot + 1);
 	MMB_CUDA_CHECK(cudaMemcpyAsync(d_a, anchors_xy, sizeof(m128) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
 	MMB_CUDA_CHECK(cudaMemcpyAsync(d_off, a_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
-	mmb_chain_par_t dp = *par;
-	dp.use_rmq = 0;
-	mmb_chain_device(ctx, &dp, n_reads, d_a, d_off, n_tot, d_nu, d_nv, d_u, d_ao, ctx->d_f, ctx->d_g); // sets up the scratch the rescue kernel reuses
-	// pretend every read came out of the DP as two chains over all of its anchors, so that the kernel re-chains it
-	std::vector<int32_t> h_nu(n_reads), h_nv(n_reads), h_q(n_reads, INT32_MAX);
-	std::vector<uint64_t> h_u((size_t)n_tot + 1, 0);
-	for (int i = 0; i < n_reads; ++i) {
-		const int64_t n = a_off[i + 1] - a_off[i];
-		h_nv[i] = (int32_t)n, h_nu[i] = n > 0? 2 : 0;
-		if (n > 0) h_u[a_off[i]] = 1;
-	}
-	MMB_CUDA_CHECK(cudaMemcpyAsync(d_nu, h_nu.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-	MMB_CUDA_CHECK(cudaMemcpyAsync(d_nv, h_nv.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-	MMB_CUDA_CHECK(cudaMemcpyAsync(d_qlen, h_q.data(), sizeof(int32_t) * n_reads, cudaMemcpyHostToDevice, ctx->stream));
-	MMB_CUDA_CHECK(cudaMemcpyAsync(d_u, h_u.data(), sizeof(uint64_t) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
-	MMB_CUDA_CHECK(cudaMemcpyAsync(d_ao, anchors_xy, sizeof(m128) * n_tot, cudaMemcpyHostToDevice, ctx->stream));
-	MMB_CUDA_CHECK(cudaMemcpyAsync(d_toff, a_off, sizeof(int64_t) * (n_reads + 1), cudaMemcpyHostToDevice, ctx->stream));
-	RescuePar rp;
-	rp.qlen = d_qlen, rp.rescue_size = 0, rp.rescue_ratio = 0.0f;
-	rp.max_dist = par->max_dist_x, rp.max_dist_inner = par->max_dist_inner, rp.bw = par->bw, rp.max_skip = par->max_skip;
-	rp.rmq_size_cap = par->rmq_size_cap, rp.min_cnt = par->min_cnt, rp.min_sc = par->min_sc;
-	rp.pen_gap = par->chn_pen_gap, rp.pen_skip = par->chn_pen_skip, rp.tree = nullptr, rp.tree_off = d_toff;
-	mmb_chain_rescue_device(ctx, &rp, n_reads, d_off, n_tot, d_nu, d_nv, d_u, d_ao, ctx->d_f, ctx->d_g, ctx->d_h, n_tot);
+	mmb_chain_rmq_primary_device(ctx, par, n_reads, d_a, d_off, n_tot, d_nu, d_nv, d_u, d_ao, ctx->d_f, ctx->d_g, ctx->d_h);
 	MMB_CUDA_CHECK(cudaMemcpyAsync(n_u, d_nu, sizeof(int32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
 	MMB_CUDA_CHECK(cudaMemcpyAsync(n_v, d_nv, sizeof(int32_t) * n_reads, cudaMemcpyDeviceToHost, ctx->stream));
 	MMB_CUDA_CHECK(cudaMemcpyAsync(u_out, d_u, sizeof(uint64_t) * n_tot, cudaMemcpyDeviceToHost, ctx->stream));

@@ -231,7 +231,6 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 	const char *what = nullptr;
 	if (opt->flag & (MM_F_SR | MM_F_SR_RNA)) what = "short-read mode (-x sr / splice:sr)";
 	else if (opt->max_occ > opt->mid_occ) what = "re-chaining with a second occurrence cutoff (-f INT,INT)";
-	else if (opt->flag & MM_F_RMQ) what = "RMQ chaining as the primary chainer (--rmq / asm presets)";
 	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
 	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
 	else if (mi->n_alt) what = "ALT contigs";
@@ -367,7 +366,10 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	int32_t *d_n_u = bb.n_u.as<int32_t>((size_t)n), *d_n_v = bb.n_v.as<int32_t>((size_t)n);
 	uint64_t *d_u = bb.u.as<uint64_t>((size_t)total_a + 4);
 	m128 *d_a_out = bb.a_out.as<m128>((size_t)total_a + 4);
-	mmb_chain_device(ctx, &cp, n, S.a_sorted, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2);
+	if (opt->flag & MM_F_RMQ) { // map.c:275-276
+		cp.use_rmq = 1, cp.max_dist_x = opt->max_gap, cp.max_dist_inner = opt->rmq_inner_dist, cp.rmq_size_cap = opt->rmq_size_cap;
+		mmb_chain_rmq_primary_device(ctx, &cp, n, S.a_sorted, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2, bb.t1);
+	} else mmb_chain_device(ctx, &cp, n, S.a_sorted, d_a_off, total_a, d_n_u, d_n_v, d_u, d_a_out, bb.ch1, bb.ch2);
 	// dense copies for the host: offsets for u, a and mini_pos
 	int64_t *d_doff = bb.doff.as<int64_t>((size_t)(n + 1) * 3);
 	int64_t *d_uo = d_doff, *d_vo = d_doff + (n + 1), *d_mo = d_doff + 2 * (n + 1);
@@ -377,6 +379,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		++ctx->n_launch;
 		const int64_t tv = mmb_exclusive_scan_i64(ctx, d_vo, n, true);
 		RescuePar rp;
+		rp.primary = 0;
 		rp.qlen = d_qlen, rp.rescue_size = opt->rmq_rescue_size, rp.rescue_ratio = opt->rmq_rescue_ratio;
 		rp.max_dist = opt->max_gap, rp.max_dist_inner = opt->rmq_inner_dist, rp.bw = opt->bw_long, rp.max_skip = opt->max_chain_skip;
 		rp.rmq_size_cap = opt->rmq_size_cap, rp.min_cnt = opt->min_cnt, rp.min_sc = opt->min_chain_score;

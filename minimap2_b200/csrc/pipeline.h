@@ -40,6 +40,10 @@ struct RescuePar {            // long-join rescue with mg_lchain_rmq (map.c:283-
 	int32_t max_dist, max_dist_inner, bw, max_skip, rmq_size_cap, min_cnt, min_sc;
 	float pen_gap, pen_skip;
 	uint8_t *tree; const int64_t *tree_off;
+	int32_t primary;              // 1: mg_lchain_rmq as the first chainer (map.c:275-276): every read, anchors taken as they are (no re-sort)
 };
+// mg_lchain_rmq as the primary chainer (MM_F_RMQ, map.c:275-276); same outputs as mmb_chain_device
+void mmb_chain_rmq_primary_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const m128 *d_a, const int64_t *d_a_off, int64_t n_tot,
+								  int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf);
 void mmb_chain_rescue_device(mmb_ctx_t *ctx, const RescuePar *rp, int n_reads, const int64_t *d_a_off, int64_t n_tot,
 							 int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf, int64_t tot_v);

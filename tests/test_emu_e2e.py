@@ -111,3 +111,28 @@ def test_emulated_high_occurrence_seed_selection_matches_reference(emu_cli, tmp_
     assert p.returncode == 0, p.stderr.decode()[-2000:]
     assert p.stdout.decode().splitlines() == ref and len(ref) >= 3
     assert any("rl:i:" in l and "rl:i:0" not in l for l in ref)  # the selection really masked something
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset,div", [("asm5", 0.004), ("asm20", 0.03)])
+def test_emulated_assembly_presets_match_reference(emu_cli, tmp_path, preset, div):
+    """-x asm5 / asm20 (MM_F_RMQ: mg_lchain_rmq is the first chainer, map.c:275-276, followed by the bw_long re-chain of
+    map.c:283-292; heavy gap costs, bw 1000/100000): two contigs against a small genome, one carrying a 250 bp deletion and a
+    reverse-complemented tail. Output equals the reference binary's."""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(21)
+    g = np.frombuffer(bytes(synth.random_genome(24_000, 9)[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    if preset == "asm5":  # sparse seeds (w=19) and unpacked scoring make this the slow one under emulation: keep it short
+        cs = [np.concatenate([g[1000:2100], g[2350:3300]]), comp[g[9000:10200][::-1]]]
+    else:
+        cs = [np.concatenate([g[1000:3200], g[3450:5200], comp[g[5200:6500][::-1]]]), g[9000:13500]]
+    contigs = [synth.mutate_ascii(c, rng, div) for c in cs]
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "asm.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["ctg0", "ctg1"], contigs)
+    args = ["-x", preset, "-c", "--cs", rf, qf]
+    ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
+    assert p.returncode == 0, p.stderr.decode()[-2000:]
+    assert p.stdout.decode().splitlines() == ref and len(ref) >= 2

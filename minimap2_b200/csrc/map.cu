@@ -721,7 +721,72 @@ extern "C" mm_reg1_t *mm_map(const mm_idx_t *mi, int qlen, const char *seq, int 
 	return regs;
 }
 
-// ---- mm_map_file (map.c:663-691): read mini-batches, map them on the GPU, print in input order ----
+// ---- mm_map_file (map.c:541-691): three overlapped steps like the reference's worker_pipeline -- a reader thread parses the next
+// mini-batch while the current one is on the GPU, and a writer thread formats (in parallel over reads) and prints the previous one.
+// Output order is the input order. ----
+namespace {
+
+struct FileBatch {
+	std::vector<FastxRecord> recs;
+	std::vector<int> qlens, n_regs, rep_len;
+	std::vector<const char*> seqs, names;
+	std::vector<mm_reg1_t*> regs;
+};
+
+template<class T> class HandOff { // bounded FIFO between two pipeline steps
+public:
+	explicit HandOff(size_t cap) : cap_(cap) {}
+	void push(T v) {
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_.wait(lk, [&] { return q_.size() < cap_; });
+		q_.push_back(std::move(v));
+		cv_.notify_all();
+	}
+	void close() { std::lock_guard<std::mutex> lk(mu_); closed_ = true; cv_.notify_all(); }
+	bool pop(T &v) { // false once closed and drained
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_.wait(lk, [&] { return !q_.empty() || closed_; });
+		if (q_.empty()) return false;
+		v = std::move(q_.front());
+		q_.pop_front();
+		cv_.notify_all();
+		return true;
+	}
+private:
+	std::mutex mu_; std::condition_variable cv_; std::deque<T> q_; size_t cap_; bool closed_ = false;
+};
+
+// output step (map.c:578-641) for reads [lo,hi) of one batch, appended to `out`; frees the hits
+void format_reads(std::string &out, FileBatch &fb, int lo, int hi, const mm_idx_t *idx, const mm_mapopt_t *opt, bool with_comment)
+{
+	for (int i = lo; i < hi; ++i) {
+		const FastxRecord &rec = fb.recs[i];
+		const char *qual = rec.qual.empty()? nullptr : rec.qual.c_str();
+		const int n_regs = fb.n_regs[i];
+		mm_reg1_t *regs = fb.regs[i];
+		if (n_regs > 0) {
+			for (int j = 0; j < n_regs; ++j) {
+				const mm_reg1_t *rg = &regs[j];
+				if ((opt->flag & MM_F_NO_PRINT_2ND) && rg->id != rg->parent) continue;
+				if (opt->flag & MM_F_OUT_SAM) hl_write_sam(out, idx, fb.names[i], fb.seqs[i], qual, fb.qlens[i], j, n_regs, regs, opt->flag, fb.rep_len[i]);
+				else { hl_set_seq_for_tags(fb.seqs[i]); hl_write_paf(out, idx, fb.names[i], fb.qlens[i], rg, opt->flag, fb.rep_len[i]); }
+				if (with_comment && !rec.comment.empty()) out += '\t', out += rec.comment;
+				out += '\n';
+			}
+		} else if ((opt->flag & MM_F_PAF_NO_HIT) || ((opt->flag & MM_F_OUT_SAM) && !(opt->flag & MM_F_SAM_HIT_ONLY))) {
+			if (opt->flag & MM_F_OUT_SAM) hl_write_sam(out, idx, fb.names[i], fb.seqs[i], qual, fb.qlens[i], -1, 0, nullptr, opt->flag, fb.rep_len[i]);
+			else hl_write_paf(out, idx, fb.names[i], fb.qlens[i], nullptr, opt->flag, fb.rep_len[i]);
+			if (with_comment && !rec.comment.empty()) out += '\t', out += rec.comment;
+			out += '\n';
+		}
+		for (int j = 0; j < n_regs; ++j) free(regs[j].p);
+		free(regs);
+		fb.regs[i] = nullptr;
+	}
+}
+
+} // namespace
+
 extern "C" int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads)
 {
 	if (n_segs != 1) { fprintf(stderr, "[ERROR] minimap2_b200: multi-file (paired) input is not implemented\n"); return -1; }
@@ -732,53 +797,56 @@ extern "C" int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn
 	}
 	const bool with_qual = (opt->flag & MM_F_OUT_SAM) && !(opt->flag & MM_F_NO_QUAL);
 	const bool with_comment = (opt->flag & MM_F_COPY_COMMENT) != 0;
-	std::string out;
-	int64_t n_processed = 0;
-	for (;;) {
-		std::vector<FastxRecord> recs;
-		int64_t size = 0;
-		FastxRecord r;
-		int ret;
-		while ((ret = rd.next(r, with_qual, with_comment)) > 0) { // mm_bseq_read3 (bseq.c:80-119)
-			size += (int64_t)r.seq.size();
-			recs.push_back(std::move(r));
-			if (size >= opt->mini_batch_size) break;
-		}
-		if (recs.empty()) break;
-		const int n = (int)recs.size();
-		std::vector<int> qlens(n), n_regs(n), rep_len(n);
-		std::vector<const char*> seqs(n), names(n);
-		std::vector<mm_reg1_t*> regs(n);
-		for (int i = 0; i < n; ++i) qlens[i] = (int)recs[i].seq.size(), seqs[i] = recs[i].seq.c_str(), names[i] = recs[i].name.c_str();
-		mm_map_batch(idx, n, qlens.data(), seqs.data(), names.data(), n_regs.data(), regs.data(), rep_len.data(), opt, n_threads);
-		for (int i = 0; i < n; ++i) { // output step (map.c:578-641)
-			const char *qual = recs[i].qual.empty()? nullptr : recs[i].qual.c_str();
-			if (n_regs[i] > 0) {
-				for (int j = 0; j < n_regs[i]; ++j) {
-					const mm_reg1_t *rg = &regs[i][j];
-					if ((opt->flag & MM_F_NO_PRINT_2ND) && rg->id != rg->parent) continue;
-					out.clear();
-					if (opt->flag & MM_F_OUT_SAM) hl_write_sam(out, idx, names[i], seqs[i], qual, qlens[i], j, n_regs[i], regs[i], opt->flag, rep_len[i]);
-					else { hl_set_seq_for_tags(seqs[i]); hl_write_paf(out, idx, names[i], qlens[i], rg, opt->flag, rep_len[i]); }
-					if (with_comment && !recs[i].comment.empty()) out += "\t" + recs[i].comment;
-					puts(out.c_str());
-				}
-			} else if ((opt->flag & MM_F_PAF_NO_HIT) || ((opt->flag & MM_F_OUT_SAM) && !(opt->flag & MM_F_SAM_HIT_ONLY))) {
-				out.clear();
-				if (opt->flag & MM_F_OUT_SAM) hl_write_sam(out, idx, names[i], seqs[i], qual, qlens[i], -1, 0, nullptr, opt->flag, rep_len[i]);
-				else hl_write_paf(out, idx, names[i], qlens[i], nullptr, opt->flag, rep_len[i]);
-				if (with_comment && !recs[i].comment.empty()) out += "\t" + recs[i].comment;
-				puts(out.c_str());
+	typedef std::unique_ptr<FileBatch> BatchPtr;
+	HandOff<BatchPtr> parsed(1), mapped(1);
+	std::thread reader([&]() { // step 0: mm_bseq_read3 (bseq.c:80-119)
+		for (;;) {
+			BatchPtr fb(new FileBatch);
+			int64_t size = 0;
+			FastxRecord r;
+			int ret;
+			while ((ret = rd.next(r, with_qual, with_comment)) > 0) {
+				size += (int64_t)r.seq.size();
+				fb->recs.push_back(std::move(r));
+				if (size >= opt->mini_batch_size) break;
 			}
-			for (int j = 0; j < n_regs[i]; ++j) free(regs[i][j].p);
-			free(regs[i]);
+			if (fb->recs.empty()) break;
+			const int n = (int)fb->recs.size();
+			fb->qlens.resize(n), fb->n_regs.resize(n), fb->rep_len.resize(n), fb->seqs.resize(n), fb->names.resize(n), fb->regs.resize(n);
+			for (int i = 0; i < n; ++i) fb->qlens[i] = (int)fb->recs[i].seq.size(), fb->seqs[i] = fb->recs[i].seq.c_str(), fb->names[i] = fb->recs[i].name.c_str();
+			parsed.push(std::move(fb));
+			if (ret <= 0) break;
 		}
-		n_processed += n;
+		parsed.close();
+	});
+	std::thread writer([&]() { // step 2: format in parallel over blocks of reads, print in input order
+		const int n_fmt = n_threads < 1? 1 : n_threads > 16? 16 : n_threads;
+		BatchPtr fb;
+		while (mapped.pop(fb)) {
+			const int n = (int)fb->recs.size(), blk = 128, n_blk = (n + blk - 1) / blk;
+			std::vector<std::string> outs(n_blk);
+			std::atomic<int> next(0);
+			auto work = [&]() { for (int b; (b = next.fetch_add(1)) < n_blk;) format_reads(outs[b], *fb, b * blk, std::min(n, (b + 1) * blk), idx, opt, with_comment); };
+			std::vector<std::thread> th;
+			for (int t = 1; t < n_fmt && t < n_blk; ++t) th.emplace_back(work);
+			work();
+			for (auto &x : th) x.join();
+			for (const std::string &o : outs) fwrite(o.data(), 1, o.size(), stdout);
+			fb.reset();
+		}
+		fflush(stdout);
+	});
+	BatchPtr fb;
+	while (parsed.pop(fb)) { // step 1: the GPU pipeline
+		const int n = (int)fb->recs.size();
+		mm_map_batch(idx, n, fb->qlens.data(), fb->seqs.data(), fb->names.data(), fb->n_regs.data(), fb->regs.data(), fb->rep_len.data(), opt, n_threads);
 		if (mm_verbose >= 3)
 			fprintf(stderr, "[M::%s::%.3f*%.2f] mapped %d sequences\n", __func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), n);
-		if (ret <= 0) break;
+		mapped.push(std::move(fb));
 	}
-	fflush(stdout);
+	mapped.close();
+	reader.join();
+	writer.join();
 	return 0;
 }
 

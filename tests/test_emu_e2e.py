@@ -32,20 +32,11 @@ def cases():
     return m.CASES
 
 
-@pytest.mark.parametrize("name", ["mt_paf_cigar", "inv_paf_cigar", "x3s_paf_cigar", "t2_paf_cigar"])
-def test_emulated_pipeline_matches_recorded_reference(emu_cli, name):
-    env = dict(os.environ, MM_B200_GROUPS="1")
-    p = subprocess.run([emu_cli, "-t", "4"] + cases()[name], cwd=os.path.join(GOLD, "data"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1200, env=env)
-    assert p.returncode == 0, p.stderr.decode()[-2000:]
-    got = [l for l in p.stdout.decode().splitlines() if not l.startswith("@PG")]
-    exp = open(os.path.join(GOLD, "expected", name + ".txt")).read().splitlines()
-    assert got == exp, (len(got), len(exp), [(a[:200], b[:200]) for a, b in zip(got, exp) if a != b][:2])
+HAVE_REF = os.path.exists(O.REF_BIN)
+GOLDEN = ["inv_paf_cigar", "x3s_paf_cigar", "t2_paf_cigar"]  # MT-human/MT-orang goes through the .mmi test below
 
 
-@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
-def test_emulated_spliced_mapping_matches_reference(emu_cli, tmp_path):
-    """-x splice end to end under the emulator (spliced kernel variant + splice branches of the driver) against the reference binary:
-    two small cDNA reads, one per transcript strand"""
+def _splice_inputs(d):
     import numpy as np
     import synth
     rng = np.random.default_rng(4)
@@ -57,24 +48,122 @@ def test_emulated_spliced_mapping_matches_reference(emu_cli, tmp_path):
         pos = int(rng.integers(1000, len(g) - 6000)); exons = []; rev = i % 2 == 1
         for k in range(3):
             el = int(rng.integers(90, 200)); exons.append((pos, pos + el)); il = int(rng.integers(150, 500))
-            d, a = (b"GT", b"AG") if not rev else (b"CT", b"AC")
-            g[pos + el:pos + el + 2] = list(d); g[pos + el + il - 2:pos + el + il] = list(a)
+            d_, a_ = (b"GT", b"AG") if not rev else (b"CT", b"AC")
+            g[pos + el:pos + el + 2] = list(d_); g[pos + el + il - 2:pos + el + il] = list(a_)
             pos += el + il
         tr = np.concatenate([g[s:e] for s, e in exons])
         reads.append(synth.mutate_ascii(comp[tr[::-1]] if rev else tr, rng, 0.03))
-    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    rf, qf = os.path.join(d, "sp_ref.fa"), os.path.join(d, "sp_reads.fa")
     synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["tr0", "tr1"], reads)
-    args = ["-x", "splice", "-c", "--cs", rf, qf]
-    ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
-    p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
-    assert p.returncode == 0, p.stderr.decode()[-2000:]
-    assert p.stdout.decode().splitlines() == ref and len(ref) == 2
+    return ["-x", "splice", "-c", "--cs", rf, qf]
 
 
-@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def _high_occ_inputs(d):
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(11)
+    g = np.frombuffer(bytes(synth.random_genome(9_000, 5)[0]), dtype=np.uint8).copy()
+    unit = g[200:600].copy()
+    for k in range(9):
+        s = 900 + k * 800
+        g[s:s + 400] = unit
+        g[s + rng.integers(0, 400, 3)] = list(b"ACG")  # a few point differences between the copies
+    reads = [synth.mutate_ascii(g[s:s + 1300], rng, 0.04) for s in (300, 2500, 5200)]
+    rf, qf = os.path.join(d, "ho_ref.fa"), os.path.join(d, "ho_reads.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["r0", "r1", "r2"], reads)
+    return ["-c", "-f", "3", "-e", "150", "-K", "1500", rf, qf]  # -K: two mini-batches through the overlapped read/map/write steps
+
+
+def _asm_inputs(d, preset, div):
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(21)
+    g = np.frombuffer(bytes(synth.random_genome(24_000, 9)[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    if preset == "asm5":  # sparse seeds (w=19) and unpacked scoring make this the slow one under emulation: keep it short
+        cs = [np.concatenate([g[1000:2100], g[2350:3300]]), comp[g[9000:10200][::-1]]]
+    else:
+        cs = [np.concatenate([g[1000:3200], g[3450:5200], comp[g[5200:6500][::-1]]]), g[9000:13500]]
+    contigs = [synth.mutate_ascii(c, rng, div) for c in cs]
+    rf, qf = os.path.join(d, preset + "_ref.fa"), os.path.join(d, preset + "_asm.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["ctg0", "ctg1"], contigs)
+    return ["-x", preset, "-c", "--cs", rf, qf]
+
+
+@pytest.fixture(scope="module")
+def emu_runs(emu_cli, tmp_path_factory):
+    """Every emulated CLI run of this module, started together (4 at a time): the emulator spends most of its time in thread
+    rendezvous, so the runs overlap well and the module's wall time is that of the longest chain rather than the sum."""
+    from concurrent.futures import ThreadPoolExecutor
+    d = str(tmp_path_factory.mktemp("emu_e2e"))
+    env = dict(os.environ, MM_B200_GROUPS="1")
+    data = os.path.join(GOLD, "data")
+    jobs = {}
+    for name in GOLDEN:
+        jobs[name] = (cases()[name], data, None)
+    if HAVE_REF:
+        jobs["splice"] = (_splice_inputs(d), d, True)
+        jobs["high_occ"] = (_high_occ_inputs(d), d, True)
+        jobs["asm5"] = (_asm_inputs(d, "asm5", 0.004), d, True)
+        jobs["asm20"] = (_asm_inputs(d, "asm20", 0.03), d, True)
+
+    def one(item):
+        name, (args, cwd, with_ref) = item
+        ref = None
+        if with_ref:
+            ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
+        p = subprocess.run([emu_cli, "-t", "4"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=env)
+        return name, dict(rc=p.returncode, err=p.stderr.decode()[-2000:], out=p.stdout.decode().splitlines(), ref=ref)
+
+    order = sorted(jobs.items(), key=lambda kv: {"splice": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
+    with ThreadPoolExecutor(4) as ex:
+        return dict(ex.map(one, order))
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_emulated_pipeline_matches_recorded_reference(emu_runs, name):
+    r = emu_runs[name]
+    assert r["rc"] == 0, r["err"]
+    got = [l for l in r["out"] if not l.startswith("@PG")]
+    exp = open(os.path.join(GOLD, "expected", name + ".txt")).read().splitlines()
+    assert got == exp, (len(got), len(exp), [(a[:200], b[:200]) for a, b in zip(got, exp) if a != b][:2])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_spliced_mapping_matches_reference(emu_runs):
+    """-x splice end to end under the emulator (spliced kernel variant + splice branches of the driver) against the reference binary:
+    two small cDNA reads, one per transcript strand"""
+    r = emu_runs["splice"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) == 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_high_occurrence_seed_selection_matches_reference(emu_runs):
+    """mm_seed_select (seed.c:56-96) on the device: a genome made mostly of copies of one 400 bp unit and -f 3 put most minimizers of
+    every read above mid_occ, so the streak selection (heap of the lowest-occurrence seeds per stretch, max_max_occ cut, rep_len)
+    decides which seeds are kept; -e 150 makes several seeds per stretch survive. Output equals the reference binary's."""
+    r = emu_runs["high_occ"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) >= 3
+    assert any("rl:i:" in l and "rl:i:0" not in l for l in r["ref"])  # the selection really masked something
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+@pytest.mark.parametrize("preset", ["asm5", "asm20"])
+def test_emulated_assembly_presets_match_reference(emu_runs, preset):
+    """-x asm5 / asm20 (MM_F_RMQ: mg_lchain_rmq is the first chainer, map.c:275-276, followed by the bw_long re-chain of
+    map.c:283-292; heavy gap costs, bw 1000/100000): two contigs against a small genome, one carrying a 250 bp deletion and a
+    reverse-complemented tail. Output equals the reference binary's."""
+    r = emu_runs[preset]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) >= 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
 def test_mmi_files_are_interchangeable(emu_cli, tmp_path):
     """mm_idx_dump / mm_idx_load (index.c:475-569): the reference maps with an index file written here and this library maps with one
-    written by the reference, both giving the recorded reference output"""
+    written by the reference, both giving the recorded reference output (MT-human / MT-orang, the golden mt_paf_cigar case)"""
     data = os.path.join(GOLD, "data")
     exp = open(os.path.join(GOLD, "expected", "mt_paf_cigar.txt")).read().splitlines()
     mine, theirs = str(tmp_path / "mine.mmi"), str(tmp_path / "ref.mmi")
@@ -86,53 +175,3 @@ def test_mmi_files_are_interchangeable(emu_cli, tmp_path):
     assert out == exp
     out = subprocess.run([emu_cli, "-t", "2", "-c", theirs, os.path.join(data, "MT-orang.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=1200).stdout.decode().splitlines()
     assert out == exp
-
-
-@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
-def test_emulated_high_occurrence_seed_selection_matches_reference(emu_cli, tmp_path):
-    """mm_seed_select (seed.c:56-96) on the device: a genome made mostly of copies of one 400 bp unit and -f 3 put most minimizers of
-    every read above mid_occ, so the streak selection (heap of the lowest-occurrence seeds per stretch, max_max_occ cut, rep_len)
-    decides which seeds are kept; -e 150 makes several seeds per stretch survive. Output equals the reference binary's."""
-    import numpy as np
-    import synth
-    rng = np.random.default_rng(11)
-    g = np.frombuffer(bytes(synth.random_genome(9_000, 5)[0]), dtype=np.uint8).copy()
-    unit = g[200:600].copy()
-    for k in range(9):
-        s = 900 + k * 800
-        g[s:s + 400] = unit
-        g[s + rng.integers(0, 400, 3)] = list(b"ACG")  # a few point differences between the copies
-    reads = [synth.mutate_ascii(g[s:s + 1300], rng, 0.04) for s in (300, 2500, 5200)]
-    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
-    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["r0", "r1", "r2"], reads)
-    args = ["-c", "-f", "3", "-e", "150", rf, qf]
-    ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
-    p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
-    assert p.returncode == 0, p.stderr.decode()[-2000:]
-    assert p.stdout.decode().splitlines() == ref and len(ref) >= 3
-    assert any("rl:i:" in l and "rl:i:0" not in l for l in ref)  # the selection really masked something
-
-
-@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
-@pytest.mark.parametrize("preset,div", [("asm5", 0.004), ("asm20", 0.03)])
-def test_emulated_assembly_presets_match_reference(emu_cli, tmp_path, preset, div):
-    """-x asm5 / asm20 (MM_F_RMQ: mg_lchain_rmq is the first chainer, map.c:275-276, followed by the bw_long re-chain of
-    map.c:283-292; heavy gap costs, bw 1000/100000): two contigs against a small genome, one carrying a 250 bp deletion and a
-    reverse-complemented tail. Output equals the reference binary's."""
-    import numpy as np
-    import synth
-    rng = np.random.default_rng(21)
-    g = np.frombuffer(bytes(synth.random_genome(24_000, 9)[0]), dtype=np.uint8).copy()
-    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
-    if preset == "asm5":  # sparse seeds (w=19) and unpacked scoring make this the slow one under emulation: keep it short
-        cs = [np.concatenate([g[1000:2100], g[2350:3300]]), comp[g[9000:10200][::-1]]]
-    else:
-        cs = [np.concatenate([g[1000:3200], g[3450:5200], comp[g[5200:6500][::-1]]]), g[9000:13500]]
-    contigs = [synth.mutate_ascii(c, rng, div) for c in cs]
-    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "asm.fa")
-    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["ctg0", "ctg1"], contigs)
-    args = ["-x", preset, "-c", "--cs", rf, qf]
-    ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
-    p = subprocess.run([emu_cli, "-t", "4"] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(os.environ, MM_B200_GROUPS="1"))
-    assert p.returncode == 0, p.stderr.decode()[-2000:]
-    assert p.stdout.decode().splitlines() == ref and len(ref) >= 2

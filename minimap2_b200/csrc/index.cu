@@ -645,7 +645,31 @@ static int unsupported(const char *what)
 	if (mm_verbose >= 1) fprintf(stderr, "[ERROR] %s is not supported by minimap2_b200 (index annotations are out of scope)\n", what);
 	return -1;
 }
-extern "C" int mm_idx_alt_read(mm_idx_t *, const char *) { return unsupported("--alt"); }
+extern "C" int mm_idx_alt_read(mm_idx_t *mi, const char *fn) // index.c:648-670: one contig name per line (first token), plain or gzipped
+{
+	gzFile fp = fn && strcmp(fn, "-")? gzopen(fn, "r") : gzdopen(0, "r");
+	if (fp == 0) return -1;
+	if (mi->h == 0) mm_idx_index_name(mi);
+	int n_alt = 0, c;
+	std::string tok;
+	bool in_tok = true; // still inside the first token of the current line
+	auto flush = [&]() {
+		const int id = mm_idx_name2id(mi, tok.c_str());
+		if (id >= 0) mi->seq[id].is_alt = 1, ++n_alt;
+		tok.clear(), in_tok = true;
+	};
+	bool any = false;
+	while ((c = gzgetc(fp)) >= 0) {
+		any = true;
+		if (c == '\n') { flush(); any = false; }
+		else if (in_tok) { if (isspace(c)) in_tok = false; else tok += (char)c; }
+	}
+	if (any) flush(); // last line without a newline
+	gzclose(fp);
+	mi->n_alt = n_alt;
+	if (mm_verbose >= 3) fprintf(stderr, "[M::%s] found %d ALT contigs\n", __func__, n_alt);
+	return n_alt;
+}
 extern "C" int mm_idx_bed_read(mm_idx_t *, const char *, int) { return unsupported("--junc-bed"); }
 extern "C" int mm_idx_bed_junc(const mm_idx_t *, int32_t, int32_t st, int32_t en, uint8_t *s) { memset(s, 0, en - st); return 0; }
 extern "C" int32_t mm_idx_spsc_read(mm_idx_t *, const char *, int32_t) { return unsupported("--spsc"); }

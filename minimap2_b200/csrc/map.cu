@@ -233,7 +233,6 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 	else if (opt->max_occ > opt->mid_occ) what = "re-chaining with a second occurrence cutoff (-f INT,INT)";
 	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
 	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
-	else if (mi->n_alt) what = "ALT contigs";
 	if (what) {
 		fprintf(stderr, "[ERROR] minimap2_b200: %s is not implemented in this build; refusing to run (no CPU fallback)\n", what);
 		abort();
@@ -440,6 +439,10 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		r.a.assign(r.a_src, r.a_src + r.n_a);
 		int n_regs0 = r.n_u;
 		mm_reg1_t *regs0 = hl_gen_regs(r.hash, r.qlen, r.n_u, r.u, r.a.data(), 0);
+		if (mi->n_alt) { // map.c:321-324 (mm_mark_alt, hit.c:91-97)
+			for (int k = 0; k < n_regs0; ++k) if (mi->seq[regs0[k].rid].is_alt) regs0[k].is_alt = 1;
+			hl_hit_sort(&n_regs0, regs0, opt->alt_drop);
+		}
 		if (!(opt->flag & MM_F_ALL_CHAINS)) { // chain_post (map.c:206-213)
 			hl_set_parent(opt->mask_level, opt->mask_len, n_regs0, regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
 			hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 1, (int)(opt->max_gap * 0.8), &n_regs0, regs0);

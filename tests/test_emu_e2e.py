@@ -90,6 +90,19 @@ def _asm_inputs(d, preset, div):
     return ["-x", preset, "-c", "--cs", rf, qf]
 
 
+def _alt_inputs(d):
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(31)
+    g = np.frombuffer(bytes(synth.random_genome(12_000, 13)[0]), dtype=np.uint8).copy()
+    alt = np.frombuffer(synth.mutate_ascii(g[3000:7000], rng, 0.003), dtype=np.uint8)  # an ALT haplotype of chr0:3000-7000
+    reads = [synth.mutate_ascii(alt[500:1900], rng, 0.05), synth.mutate_ascii(g[3600:5000], rng, 0.05), synth.mutate_ascii(g[8000:9200], rng, 0.05)]
+    rf, qf, af = os.path.join(d, "alt_ref.fa"), os.path.join(d, "alt_reads.fa"), os.path.join(d, "alt.txt")
+    synth.write_fasta(rf, ["chr0", "chr0_alt"], [g.tobytes(), alt.tobytes()]); synth.write_fasta(qf, ["r0", "r1", "r2"], reads)
+    open(af, "w").write("chr0_alt\tsome comment\nnot_a_contig\n")
+    return ["-c", "--alt", af, "--alt-drop", "0.2", rf, qf]
+
+
 @pytest.fixture(scope="module")
 def emu_runs(emu_cli, tmp_path_factory):
     """Every emulated CLI run of this module, started together (4 at a time): the emulator spends most of its time in thread
@@ -106,6 +119,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["high_occ"] = (_high_occ_inputs(d), d, True)
         jobs["asm5"] = (_asm_inputs(d, "asm5", 0.004), d, True)
         jobs["asm20"] = (_asm_inputs(d, "asm20", 0.03), d, True)
+        jobs["alt"] = (_alt_inputs(d), d, True)
 
     def one(item):
         name, (args, cwd, with_ref) = item
@@ -158,6 +172,17 @@ def test_emulated_assembly_presets_match_reference(emu_runs, preset):
     r = emu_runs[preset]
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"] and len(r["ref"]) >= 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_alt_contigs_match_reference(emu_runs):
+    """--alt (mm_idx_alt_read index.c:648-670, mm_mark_alt + the ALT-aware mm_hit_sort / mm_set_parent of hit.c:91-223 at
+    map.c:321-324): reads from a region with an ALT haplotype; the ALT hits are down-weighted like the reference does."""
+    r = emu_runs["alt"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) >= 4
+    r0 = [l.split("\t") for l in r["ref"] if l.startswith("r0\t")]  # sampled from the ALT haplotype, yet the primary contig wins with MAPQ 60
+    assert r0[0][5] == "chr0" and r0[0][11] == "60" and "tp:A:P" in r0[0] and r0[1][5] == "chr0_alt" and "tp:A:S" in r0[1]
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

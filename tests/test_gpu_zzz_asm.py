@@ -40,3 +40,24 @@ def test_synthetic_contigs(tmp_path, preset, div):
     synth.write_fasta(qf, ["ctg%d" % i for i in range(len(asm))], asm)
     n = compare(["-x", preset, "-c", "--cs", rf, qf])
     assert n >= len(asm)
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_alt_contigs(tmp_path):
+    """--alt / --alt-drop (index.c:648-670, hit.c:91-223, map.c:321-324): ALT haplotypes of several regions next to the primary contigs"""
+    rng = np.random.default_rng(5)
+    contigs = synth.random_genome(600_000, 51, n_contigs=2, repeat_frac=0.1)
+    names = ["chr0", "chr1"]; seqs = [bytes(c) for c in contigs]; alts = []
+    for i in range(6):
+        c = np.frombuffer(seqs[i % 2], dtype=np.uint8)
+        s = int(rng.integers(0, len(c) - 40_000)); L = int(rng.integers(8_000, 40_000))
+        alts.append(synth.mutate_ascii(c[s:s + L], rng, [0.002, 0.01, 0.03][i % 3]))
+        names.append("chr%d_alt%d" % (i % 2, i)); seqs.append(alts[-1])
+    reads = synth.make_reads([np.frombuffer(x, dtype=np.uint8) for x in seqs], 400, 5000, 0.08, 77, chimeric_frac=0.03)
+    rf, qf, af = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa"), str(tmp_path / "alt.txt")
+    synth.write_fasta(rf, names, seqs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    open(af, "w").write("".join(n + "\n" for n in names[2:]))
+    n = compare(["-x", "map-ont", "-c", "--alt", af, rf, qf])
+    assert n >= 400
+    compare(["-x", "map-ont", "-a", "--alt", af, "--alt-drop", "0.3", rf, qf], sam=True)

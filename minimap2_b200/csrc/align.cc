@@ -7,6 +7,7 @@
 // requested in the same wave. The batch scheduler (map.cc) replays a read after each wave until nothing is missing;
 // the last replay then executes exactly the reference's sequence of decisions.
 #include "hostlogic.h"
+#include <emmintrin.h>
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -133,7 +134,7 @@ struct Driver {
 	const uint8_t *qptr(int rev, int qs) const { return ra.qseq[rev] + qs; }
 	void get_tseq(uint32_t rid, int st, int en, std::vector<uint8_t> &buf) const {
 		HpScope hp_(HP_TSEQ);
-		buf.resize(en > st? en - st : 0);
+		buf.resize((en > st? en - st : 0) + 16); // 16 bytes of slack: update_extra compares 16-byte blocks
 		if (en > st) mm_idx_getseq(mi, rid, st, en, buf.data());
 	}
 
@@ -340,6 +341,8 @@ struct Driver {
 			int64_t matfx[25];
 			for (int i = 0; i < 25; ++i) matfx[i] = (int64_t)mat[i] << 32;
 			int64_t sfx = 0, maxfx = 0;
+			const int64_t afx = matfx[0];
+			const bool diag_ok = mat[0] > 0 && mat[6] == mat[0] && mat[12] == mat[0] && mat[18] == mat[0]; // one positive match score
 			int32_t blen = 0, mlen = 0, n_ambi_tot = 0, is_spliced = 0;
 			toff = qoff = 0;
 			for (uint32_t k = 0; k < p->n_cigar && fixed_ok; ++k) {
@@ -347,6 +350,29 @@ struct Driver {
 				if (op == MM_CIGAR_MATCH) {
 					int n_ambi = 0, n_diff = 0;
 					const uint8_t *pq = qseq + qoff, *pt = tseq + toff;
+					if (diag_ok) {
+						// runs of identical unambiguous bases add run * a at once (the running score only rises there, so
+						// testing the maximum at the end of the run is the same as testing it at every base); 16 bases
+						// per comparison, both buffers carry 16 bytes of slack
+						for (uint32_t l0 = 0; l0 < len; l0 += 16) {
+							const uint32_t nb = len - l0 < 16? len - l0 : 16;
+							const __m128i vq = _mm_loadu_si128((const __m128i*)(pq + l0)), vt = _mm_loadu_si128((const __m128i*)(pt + l0));
+							const __m128i same = _mm_cmpeq_epi8(vq, vt), amb = _mm_cmpgt_epi8(_mm_or_si128(vq, vt), _mm_set1_epi8(3));
+							uint32_t ev = (uint32_t)_mm_movemask_epi8(_mm_or_si128(amb, _mm_xor_si128(same, _mm_set1_epi8(-1)))) & ((1u << nb) - 1);
+							uint32_t pos = 0;
+							while (ev) {
+								const uint32_t b = (uint32_t)__builtin_ctz(ev);
+								if (b > pos) { sfx += (int64_t)(b - pos) * afx; maxfx = maxfx > sfx? maxfx : sfx; }
+								const int cq = pq[l0 + b], ct = pt[l0 + b];
+								if ((ct | cq) > 3) ++n_ambi; else ++n_diff;
+								sfx += matfx[ct * 5 + cq];
+								if (sfx < 0) sfx = 0;
+								else maxfx = maxfx > sfx? maxfx : sfx;
+								pos = b + 1, ev &= ev - 1;
+							}
+							if (nb > pos) { sfx += (int64_t)(nb - pos) * afx; maxfx = maxfx > sfx? maxfx : sfx; }
+						}
+					} else
 					for (uint32_t l = 0; l < len; ++l) {
 						const int cq = pq[l], ct = pt[l];
 						const int amb = (ct | cq) > 3;

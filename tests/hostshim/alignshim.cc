@@ -58,6 +58,17 @@ static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t 
 	return d;
 }
 
+// host-cost profiling (tests/hostshim/profile_driver.py): cycles spent in requesting replays [0] and in the final replay [1]
+static uint64_t g_replay_cycles[2];
+void hs_prof_enable(int on) { g_hp_on = on != 0; g_replay_cycles[0] = g_replay_cycles[1] = 0; memset(g_hp, 0, sizeof(g_hp)); }
+void hs_prof_read(uint64_t *sections, uint64_t *replays)
+{
+	hl_hp_flush();
+	memcpy(sections, g_hp, sizeof(g_hp));
+	replays[0] = g_replay_cycles[0], replays[1] = g_replay_cycles[1];
+}
+int hs_prof_n_sections(void) { return HP_N; }
+
 // regs: libc-malloc'd array of n_regs hits (after chain post-processing), a: their anchors. Returns the aligned hits.
 mm_reg1_t *hs_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, int qlen, const char *qstr, int *n_regs_, const mm_reg1_t *regs0, int n_a, const m128 *a0,
 							 int *n_waves)
@@ -72,7 +83,7 @@ mm_reg1_t *hs_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, int qle
 			mat[0 * 5 + 2] = t, mat[1 * 5 + 3] = t, mat[2 * 5 + 0] = t, mat[3 * 5 + 1] = t;
 		}
 	}
-	std::vector<uint8_t> qf(qlen), qr(qlen);
+	std::vector<uint8_t> qf(qlen + 16), qr(qlen + 16); // the driver may read 16 bytes past a sequence (block compares)
 	for (int i = 0; i < qlen; ++i) { const uint8_t c = nt4_of((uint8_t)qstr[i]); qf[i] = c, qr[qlen - 1 - i] = c < 4? 3 - c : 4; }
 	ReadAlign ra;
 	ra.reset();
@@ -89,7 +100,9 @@ mm_reg1_t *hs_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, int qle
 		int n_regs = *n_regs_;
 		mm_reg1_t *regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
 		memcpy(regs, regs0, sizeof(mm_reg1_t) * n_regs);
+		const uint64_t c0 = __builtin_ia32_rdtsc();
 		regs = hl_align_skeleton(opt, mi, ra, &n_regs, regs, n_a, a.data());
+		g_replay_cycles[ra.incomplete? 0 : 1] += __builtin_ia32_rdtsc() - c0;
 		if (!ra.incomplete) { out = regs, n_out = n_regs; if (n_waves) *n_waves = wave; break; }
 		for (int i = 0; i < n_regs; ++i) free(regs[i].p);
 		free(regs);

@@ -103,6 +103,22 @@ def _alt_inputs(d):
     return ["-c", "--alt", af, "--alt-drop", "0.2", rf, qf]
 
 
+def _ava_inputs(d):
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(41)
+    g = np.frombuffer(bytes(synth.random_genome(7_000, 19)[0]), dtype=np.uint8).copy()
+    g[4200:4600] = g[600:1000]  # a repeat, so that some minimizers exceed the occurrence cutoff of the read index
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = []
+    for i, s in enumerate(range(0, 5000, 1000)):
+        x = g[s:s + 2000]
+        reads.append(synth.mutate_ascii(comp[x[::-1]] if i % 2 else x, rng, 0.05))
+    qf = os.path.join(d, "ava_reads.fa")
+    synth.write_fasta(qf, ["rd%d" % i for i in (3, 0, 4, 1, 2)], reads)  # names out of order: the NO_DUAL name comparison matters
+    return ["-x", "ava-ont", "-f", "2", qf, qf]
+
+
 @pytest.fixture(scope="module")
 def emu_runs(emu_cli, tmp_path_factory):
     """Every emulated CLI run of this module, started together (4 at a time): the emulator spends most of its time in thread
@@ -120,6 +136,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["asm5"] = (_asm_inputs(d, "asm5", 0.004), d, True)
         jobs["asm20"] = (_asm_inputs(d, "asm20", 0.03), d, True)
         jobs["alt"] = (_alt_inputs(d), d, True)
+        jobs["ava"] = (_ava_inputs(d), d, True)
 
     def one(item):
         name, (args, cwd, with_ref) = item
@@ -183,6 +200,15 @@ def test_emulated_alt_contigs_match_reference(emu_runs):
     assert r["out"] == r["ref"] and len(r["ref"]) >= 4
     r0 = [l.split("\t") for l in r["ref"] if l.startswith("r0\t")]  # sampled from the ALT haplotype, yet the primary contig wins with MAPQ 60
     assert r0[0][5] == "chr0" and r0[0][11] == "60" and "tp:A:P" in r0[0] and r0[1][5] == "chr0_alt" and "tp:A:S" in r0[1]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_all_vs_all_overlap_matches_reference(emu_runs):
+    """-x ava-ont reads-vs-reads (skip_seed of map.c:78-100 with NO_DIAG / NO_DUAL on the device, occ_dist = 0 branch of the seed
+    selection, ALL_CHAINS, no base-level alignment): five overlapping reads, alternating strands, names out of order"""
+    r = emu_runs["ava"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) >= 4
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

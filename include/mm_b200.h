@@ -104,6 +104,12 @@ int64_t mmb_ksw_batch_host(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs
 int64_t mmb_sketch_batch_host(mmb_ctx_t *ctx, int n_seq, const char *seqs, const int64_t *off, int w, int k, int is_hpc,
 							  uint32_t rid0, uint64_t *out_xy /* mm128_t pairs */, int64_t out_cap, int64_t *n_out);
 
+/* Junction annotation for MMB_JOB_SPLICE jobs (replaces the junc[] argument of ksw_exts2_sse, ksw2_exts2_sse.c:26-31, that
+ * align.c:638-643 fills with mm_idx_bed_junc, index.c:802-826): n annotated introns sorted by st, [st,en) in the coordinates of the
+ * target array the jobs address, strand +1/-1. A job marks exactly the introns that lie entirely inside its target window, as
+ * mm_idx_bed_junc does for the window mm_align1 passes. n = 0 clears it. Returns -1 if st[] is not sorted. */
+int mmb_ctx_set_junctions(mmb_ctx_t *ctx, int64_t n, const int64_t *st, const int64_t *en, const int8_t *strand);
+
 /* ---------------------------------------------------------------------------------------------------------
  * K2c: chaining   (replaces mg_lchain_dp lchain.c:148-217 incl. mg_chain_backtrack/compact_a, and mg_lchain_rmq :250-368)
  * --------------------------------------------------------------------------------------------------------- */

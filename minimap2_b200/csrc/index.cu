@@ -7,6 +7,7 @@
 // open-addressing table is filled with atomicCAS. Occurrence lists come out ordered by position inside a key, the
 // order the reference establishes with radix_sort_64 (index.c:264-266), so mm_idx_get-dependent results are identical.
 #include "index.h"
+#include "annot.h"
 #include <emmintrin.h>
 #include "mm_algo.cuh"
 #include "fastx.h"
@@ -281,9 +282,11 @@ extern "C" void mm_idx_destroy(mm_idx_t *mi) // index.c:62-91
 		mm_idx_bucket_s *B = mi->B;
 		if (B->ctx) cudaSetDevice(B->ctx->device);
 		if (!B->external) { cudaFree(B->d_tab); cudaFree(B->d_pos); cudaFree(B->d_S); cudaFree(B->d_seq_off); cudaFree(B->d_seq_len); cudaFree(B->d_cnt_sorted); } cudaFree(B->d_name_rank); cudaFree(B->d_ukeys); cudaFree(B->d_ucnt); cudaFree(B->d_uoff);
+		if (B->d_junc) cudaFree(B->d_junc);
 		delete B->h_map;
 		delete B;
 	}
+	if (mi->I) { for (uint32_t i = 0; i < mi->n_seq; ++i) free(mi->I[i].a); free(mi->I); }
 	for (uint32_t i = 0; i < mi->n_seq; ++i) free(mi->seq[i].name);
 	free(mi->seq); free(mi->S); free(mi);
 }
@@ -670,8 +673,37 @@ extern "C" int mm_idx_alt_read(mm_idx_t *mi, const char *fn) // index.c:648-670:
 	if (mm_verbose >= 3) fprintf(stderr, "[M::%s] found %d ALT contigs\n", __func__, n_alt);
 	return n_alt;
 }
-extern "C" int mm_idx_bed_read(mm_idx_t *, const char *, int) { return unsupported("--junc-bed"); }
-extern "C" int mm_idx_bed_junc(const mm_idx_t *, int32_t, int32_t st, int32_t en, uint8_t *s) { memset(s, 0, en - st); return 0; }
+// index.c:796-800 + the device copy the spliced kernel reads: introns of all contigs in global S coordinates, sorted by start
+extern "C" int mm_idx_bed_read(mm_idx_t *mi, const char *fn, int read_junc)
+{
+	if (mi->h == 0) mm_idx_index_name(mi);
+	long n0 = 0, n = 0;
+	if (mi->I) { for (uint32_t i = 0; i < mi->n_seq; ++i) free(mi->I[i].a); free(mi->I); mi->I = 0; }
+	mi->I = mmx_bed_read(fn, mi->n_seq, read_junc, -1, [&](const char *name) { return mm_idx_name2id(mi, name); }, &n0, &n);
+	mm_idx_bucket_s *B = mi->B;
+	if (B) {
+		if (B->ctx) MMB_CUDA_CHECK(cudaSetDevice(B->ctx->device));
+		if (B->d_junc) { MMB_CUDA_CHECK(cudaFree(B->d_junc)); B->d_junc = nullptr; }
+		B->n_junc = 0;
+	}
+	if (mi->I == 0) return 0;
+	if (mm_verbose >= 3) fprintf(stderr, "[%s] read %ld introns, %ld of which are non-redundant\n", __func__, n0, n);
+	if (B && n > 0) {
+		std::vector<int64_t> h((size_t)n * 2 + ((size_t)n + 7) / 8);
+		int8_t *hs = (int8_t*)(h.data() + (size_t)n * 2);
+		int64_t k = 0;
+		for (uint32_t i = 0; i < mi->n_seq; ++i)
+			for (int32_t j = 0; j < mi->I[i].n; ++j, ++k) {
+				const mm_idx_intv1_t &t = mi->I[i].a[j];
+				h[k] = (int64_t)mi->seq[i].offset + t.st, h[n + k] = (int64_t)mi->seq[i].offset + t.en, hs[k] = (int8_t)t.strand;
+			}
+		MMB_CUDA_CHECK(cudaMalloc((void**)&B->d_junc, h.size() * 8));
+		MMB_CUDA_CHECK(cudaMemcpy(B->d_junc, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+		B->n_junc = n;
+	}
+	return 0;
+}
+extern "C" int mm_idx_bed_junc(const mm_idx_t *mi, int32_t ctg, int32_t st, int32_t en, uint8_t *s) { return mmx_bed_junc(mi->I, (int32_t)mi->n_seq, ctg, st, en, s); }
 extern "C" int32_t mm_idx_spsc_read(mm_idx_t *, const char *, int32_t) { return unsupported("--spsc"); }
 extern "C" int32_t mm_idx_spsc_read2(mm_idx_t *, const char *, int32_t, float) { return unsupported("--spsc"); }
 extern "C" int64_t mm_idx_spsc_get(const mm_idx_t *, int32_t, int64_t st0, int64_t en0, int32_t, uint8_t *sc) { memset(sc, 0, en0 - st0); return 0; }

@@ -50,6 +50,10 @@ struct KswArgs {
 	int8_t skip;           // -min(mat) > 2(q+e): the reference returns immediately (:100)
 	int long_thres, long_diff;
 	int8_t sp[4];          // spliced variant: penalties of the four signal classes (ksw2_exts2_sse.c:113-121)
+	const long long *jst, *jen; // annotated introns sorted by jst, [jst,jen) in target coordinates (mm_idx_bed_junc, index.c:802-826); spliced variant
+	const int8_t *jstrand;
+	int n_junc;            // 0: no annotation
+	int8_t junc_bonus;
 	uint8_t *gws;          // per-worker DP state in HBM for targets that do not fit shared memory (null: shared memory)
 	size_t gws_stride;
 };
@@ -254,8 +258,30 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 			qr[k] = c;
 		}
 		gsync<G>();
-		if (SP) { // donor / acceptor arrays (ksw2_exts2_sse.c:111-190; no junction annotation)
+		if (SP) { // donor / acceptor arrays (ksw2_exts2_sse.c:111-190) + annotated junctions (:220-241)
 			const bool fo = (flag & MMB_KSW_SPLICE_FOR) != 0, re = (flag & MMB_KSW_SPLICE_REV) != 0, rc = (flag & MMB_KSW_REV_CIGAR) != 0;
+			const bool with_junc = A.n_junc > 0 && (fo || re);
+			if (with_junc) {
+				// junc[] of this call = mm_idx_bed_junc over the job's target window, reversed with the target for a reversed job
+				// (align.c:787-790): flags of the introns lying entirely inside the window, OR-ed into s[] (all zero here) and
+				// cleared again below
+				const long long wlo = jb.t_step > 0? jb.t_start : jb.t_start - (tlen - 1), whi = wlo + tlen;
+				int lo = 0, hi = A.n_junc;
+				while (hi > lo) { const int mid = lo + ((hi - lo) >> 1); if (A.jst[mid] >= wlo) hi = mid; else lo = mid + 1; }
+				for (int k = lo + g; k < A.n_junc; k += G) {
+					const long long st = A.jst[k];
+					if (st >= whi) break;
+					const long long en = A.jen[k];
+					const int sd = A.jstrand[k];
+					if (en <= whi && sd != 0) {
+						const int i1 = (int)(jb.t_step > 0? st - jb.t_start : jb.t_start - st);
+						const int i2 = (int)(jb.t_step > 0? en - 1 - jb.t_start : jb.t_start - (en - 1));
+						atomicOr((unsigned*)(s + (i1 & ~3)), (unsigned)(sd > 0? 1 : 8) << ((i1 & 3) * 8));
+						atomicOr((unsigned*)(s + (i2 & ~3)), (unsigned)(sd > 0? 2 : 4) << ((i2 & 3) * 8));
+					}
+				}
+				gsync<G>();
+			}
 			for (int i = g; i < tlen16; i += G) {
 				int8_t d = 0, a = 0;
 				if (fo || re) {
@@ -284,10 +310,21 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 						}
 						a = z < 0? 0 : (int8_t)-A.sp[z];
 					}
+					if (with_junc) { // ksw2_exts2_sse.c:220-241 (int8 wrap-around like the reference's array arithmetic)
+						const int jd = i < tlen - 1? s[i + 1] : 0, ja = i < tlen? s[i] : 0;
+						const int dm = rc? (fo? 2 : 0) | (re? 4 : 0) : (fo? 1 : 0) | (re? 8 : 0);
+						const int am = rc? (fo? 1 : 0) | (re? 8 : 0) : (fo? 2 : 0) | (re? 4 : 0);
+						if (jd & dm) d = (int8_t)(d + A.junc_bonus);
+						if (ja & am) a = (int8_t)(a + A.junc_bonus);
+					}
 				}
 				y2[i] = (uint8_t)d, acc[i] = (uint8_t)a;
 			}
 			gsync<G>();
+			if (with_junc) {
+				for (int i = g * 4; i < tlen16; i += G * 4) *(uint32_t*)(s + i) = 0;
+				gsync<G>();
+			}
 		}
 
 		int last_st = -1, last_en = -1;
@@ -659,6 +696,8 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		for (int i = 0; i < n_jobs; ++i) if (h_jobs[i].flag & MMB_JOB_SPLICE) { cmplx = (h_jobs[i].flag & MMB_KSW_SPLICE_CMPLX) != 0, flank = (h_jobs[i].flag & MMB_KSW_SPLICE_FLANK) != 0; break; }
 		static const int sp0[4] = { 8, 15, 21, 30 };
 		for (int t = 0; t < 4; ++t) A.sp[t] = cmplx? (int8_t)((double)sp0[t] / 3. + .499) : (int8_t)(t == 0? (flank? sc->noncan / 2 : 0) : sc->noncan);
+		A.jst = (const long long*)ctx->junc_st, A.jen = (const long long*)ctx->junc_en, A.jstrand = ctx->junc_strand;
+		A.n_junc = (int)ctx->n_junc, A.junc_bonus = sc->junc_bonus;
 	}
 
 	// tiers: {max len16, group size, workers per CTA}; the last tier keeps the DP state in HBM instead of shared memory

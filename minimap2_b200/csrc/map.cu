@@ -252,6 +252,9 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	mm_idx_bucket_s *B = mi->B;
 	mmb_ctx_t *ctx = G.ctx;
 	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	// annotated introns of the index (mm_idx_bed_read) for the spliced kernel: what mm_get_junc / mm_idx_bed_junc feed ksw_exts2 (align.c:638-643)
+	ctx->n_junc = B->n_junc, ctx->junc_st = B->d_junc, ctx->junc_en = B->d_junc? B->d_junc + B->n_junc : nullptr;
+	ctx->junc_strand = B->d_junc? (const int8_t*)(B->d_junc + 2 * B->n_junc) : nullptr;
 	BatchBufs &bb = G.bb;
 	if (n_threads < 1) n_threads = 1;
 	if ((int)bb.rs_pool.size() < n_reads) bb.rs_pool.resize(n_reads), bb.ra_pool.resize(n_reads);

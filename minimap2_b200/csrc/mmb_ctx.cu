@@ -46,13 +46,30 @@ extern "C" void mmb_ctx_destroy(mmb_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->d_a.release(); c->d_b.release(); c->d_c.release(); c->d_d.release();
-	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release();
+	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release(); c->d_junc.release();
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
 
 extern "C" void *mmb_ctx_stream(mmb_ctx_t *c) { return (void*)c->stream; }
+
+// Annotated introns for MMB_JOB_SPLICE jobs of the kernel-level entry points (host arrays, sorted by st; coordinates index the
+// target array passed to mmb_ksw_batch_host). n = 0 removes the annotation.
+extern "C" int mmb_ctx_set_junctions(mmb_ctx_t *c, int64_t n, const int64_t *st, const int64_t *en, const int8_t *strand)
+{
+	MMB_CUDA_CHECK(cudaSetDevice(c->device));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	c->junc_st = c->junc_en = nullptr, c->junc_strand = nullptr, c->n_junc = 0;
+	if (n <= 0) return 0;
+	for (int64_t i = 1; i < n; ++i) if (st[i] < st[i - 1]) return -1;
+	uint8_t *d = (uint8_t*)c->d_junc.reserve((size_t)n * 17 + 64);
+	MMB_CUDA_CHECK(cudaMemcpy(d, st, (size_t)n * 8, cudaMemcpyHostToDevice));
+	MMB_CUDA_CHECK(cudaMemcpy(d + (size_t)n * 8, en, (size_t)n * 8, cudaMemcpyHostToDevice));
+	MMB_CUDA_CHECK(cudaMemcpy(d + (size_t)n * 16, strand, (size_t)n, cudaMemcpyHostToDevice));
+	c->junc_st = (const int64_t*)d, c->junc_en = (const int64_t*)(d + (size_t)n * 8), c->junc_strand = (const int8_t*)(d + (size_t)n * 16), c->n_junc = n;
+	return 0;
+}
 
 extern "C" uint64_t mmb_launch_count(mmb_ctx_t *c, int reset)
 {

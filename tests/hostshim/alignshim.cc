@@ -5,6 +5,8 @@
 // same chains, so the driver logic is checked without a GPU and independently of the CUDA kernels.
 #include "hostlogic.h"
 #include "../../oracle/mm2o.h"
+#include "annot.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -47,9 +49,20 @@ static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t 
 	}
 	mm2o_ez_t ez;
 	memset(&ez, 0, sizeof(ez));
-	if (j.flag & MMB_JOB_SPLICE) // ksw_exts2 as mm_align_pair calls it (align.c:352-355); no junction annotation: junc[] is all zero there
+	if (j.flag & MMB_JOB_SPLICE) { // ksw_exts2 as mm_align_pair calls it (align.c:352-355), junc[] as mm_get_junc fills it (align.c:638-643,787-790)
+		std::vector<uint8_t> junc;
+		if (mi->I && j.tlen > 0) {
+			const int64_t lo = j.t_step > 0? j.t_start : j.t_start - (j.tlen - 1);
+			int32_t rid = 0;
+			while (rid + 1 < (int32_t)mi->n_seq && (int64_t)mi->seq[rid + 1].offset <= lo) ++rid;
+			const int32_t st = (int32_t)(lo - (int64_t)mi->seq[rid].offset);
+			junc.resize(j.tlen);
+			mmx_bed_junc((const mm_idx_intv_s*)mi->I, (int32_t)mi->n_seq, rid, st, st + j.tlen, junc.data());
+			if (j.t_step < 0) std::reverse(junc.begin(), junc.end());
+		}
 		mm2o_exts2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->noncan, j.zdrop, j.end_bonus, opt->junc_bonus, opt->junc_pen,
-				   j.flag & 0x1fff, nullptr, &ez);
+				   j.flag & 0x1fff, junc.empty()? nullptr : junc.data(), &ez);
+	}
 	else mm2o_extd2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->e2, j.w, j.zdrop, j.end_bonus, j.flag & 0xff, &ez);
 	d.r.max = ez.max, d.r.zdropped = ez.zdropped, d.r.max_q = ez.max_q, d.r.max_t = ez.max_t, d.r.mqe = ez.mqe, d.r.mqe_t = ez.mqe_t;
 	d.r.mte = ez.mte, d.r.mte_q = ez.mte_q, d.r.score = ez.score, d.r.n_cigar = ez.n_cigar, d.r.reach_end = ez.reach_end;
@@ -141,4 +154,20 @@ int hs_write_sam(char *buf, int cap, const mm_idx_t *mi, const char *qname, cons
 	memcpy(buf, s.data(), s.size()); buf[s.size()] = 0;
 	return (int)s.size();
 }
+}
+
+// ---- junction annotation (csrc/annot.h) next to the reference's mm_idx_bed_read / mm_idx_bed_junc ----
+#include <unordered_map>
+extern "C" {
+// reads fn with the product's BED reader against the contig names of mi (any mm_idx_t); returns the per-contig interval array
+void *hs_bed_read(const mm_idx_t *mi, const char *fn, int read_junc)
+{
+	std::unordered_map<std::string, int> ids;
+	for (uint32_t i = 0; i < mi->n_seq; ++i) ids[mi->seq[i].name] = (int)i;
+	return mmx_bed_read(fn, mi->n_seq, read_junc, -1, [&](const char *name) { auto it = ids.find(name); return it == ids.end()? -1 : it->second; }, nullptr, nullptr);
+}
+int hs_bed_n(const void *I, int ctg) { return ((const mm_idx_intv_s*)I)[ctg].n; }
+void hs_bed_get(const void *I, int ctg, int k, int32_t *out) { const mm_idx_intv1_t &t = ((const mm_idx_intv_s*)I)[ctg].a[k]; out[0] = t.st, out[1] = t.en, out[2] = t.cnt, out[3] = t.strand; }
+int hs_bed_junc(const void *I, int n_seq, int ctg, int st, int en, uint8_t *s) { return mmx_bed_junc((const mm_idx_intv_s*)I, n_seq, ctg, st, en, s); }
+void hs_bed_free(void *I, int n_seq) { for (int i = 0; i < n_seq; ++i) free(((mm_idx_intv_s*)I)[i].a); free(I); }
 }

@@ -91,8 +91,10 @@ def compare_formats(H, R, api, mi, qname, qstr, n, pm, pr, rep_len, flag):
         assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, ref_line[:300], buf.raw[:min(ln, 300)])
 
 
-def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0, k=15, tweak=None):
+def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0, k=15, tweak=None, bed=None):
     mi, keep = build_ref_index(R, contigs, names, w=w, k=k)
+    if bed:  # junction annotation (main.c:467-471): both drivers read it from mi->I
+        R.mm_idx_bed_read(mi, bed.encode(), 1)
     io, mo = api.IdxOpt(), api.MapOpt()
     R.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
     R.mm_set_opt(None, C.byref(io), C.byref(mo)); R.mm_set_opt(preset.encode(), C.byref(io), C.byref(mo))
@@ -224,6 +226,78 @@ def test_driver_on_spliced_reads(libs):
         reads.append(synth.mutate_ascii(tr, rng, 0.03))
     contigs = [g.tobytes()]
     n, _ = run_case(H, R, api, contigs, ["chr0"], reads, preset="splice", w=5, is_cdna=1)
+    assert n >= 30
+
+
+def _spliced_set(seed, n_reads, glen=300_000):
+    """cDNA reads over a random genome; returns (genome bytes, reads, introns [(st, en, strand)])"""
+    rng = np.random.default_rng(seed)
+    g = np.frombuffer(bytes(synth.random_genome(glen, seed + 1, n_contigs=1, repeat_frac=0.0)[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads, introns = [], []
+    for i in range(n_reads):
+        pos = int(rng.integers(2000, len(g) - 60000)); exons = []; rev = i % 2 == 1
+        for k in range(int(rng.integers(2, 6))):
+            el = int(rng.integers(60, 300)); exons.append((pos, pos + el)); il = int(rng.integers(150, 5000))
+            if i % 3 == 0:  # canonical signals for a third of the transcripts only: the others depend on the annotation
+                d, a_ = (b"GT", b"AG") if not rev else (b"CT", b"AC")
+                g[pos + el:pos + el + 2] = list(d); g[pos + el + il - 2:pos + el + il] = list(a_)
+            introns.append((pos + el, pos + el + il, -1 if rev else 1))
+            pos += el + il
+        introns.pop()  # the stretch after the last exon is not an intron
+        tr = np.concatenate([g[s:e] for s, e in exons])
+        reads.append(synth.mutate_ascii(comp[tr[::-1]] if rev else tr, rng, 0.04))
+    return g.tobytes(), reads, introns
+
+
+def _write_bed(path, introns, rng):
+    """BED6 lines (one intron each) in random order with duplicates, shifted decoys, a strandless line and an unknown contig"""
+    lines = []
+    for st, en, sd in introns:
+        lines.append("chr0\t%d\t%d\tj\t%d\t%s" % (st, en, int(rng.integers(0, 100)), "+" if sd > 0 else "-"))
+        if rng.random() < 0.3:
+            lines.append(lines[-1])
+        if rng.random() < 0.3:
+            d = int(rng.integers(-6, 7))
+            lines.append("chr0\t%d\t%d\tdecoy\t0\t%s" % (st + d, en + d, "+" if rng.random() < 0.5 else "-"))
+    lines.append("chr0\t100\t900\tnostrand\t0\t.")
+    lines.append("chrUn\t100\t900\tx\t0\t+")
+    # a BED12 transcript: three blocks -> two introns (3000-3400 and 3600-5000)
+    lines.append("chr0\t2900\t5100\ttx\t0\t+\t2900\t5100\t0\t3\t100,200,100,\t0,500,2100,")
+    order = rng.permutation(len(lines))
+    open(path, "w").write("".join(lines[i] + "\n" for i in order))
+
+
+def test_bed_reader_and_junction_flags_match_reference(libs, tmp_path):
+    """mm_idx_bed_read / mm_idx_bed_junc (index.c:672-826) restated in csrc/annot.h vs the reference library: merged interval lists
+    and the per-window flag arrays on random windows"""
+    H, R, api = libs
+    rng = np.random.default_rng(3)
+    g, reads, introns = _spliced_set(50, 40)
+    bed = str(tmp_path / "anno.bed"); _write_bed(bed, introns, rng)
+    mi, keep = build_ref_index(R, [g], ["chr0"], w=5)
+    R.mm_idx_bed_read(mi, bed.encode(), 1)
+    H.hs_bed_read.restype = C.c_void_p
+    I = H.hs_bed_read(mi, bed.encode(), 1)
+    n = H.hs_bed_n(C.c_void_p(I), 0)
+    assert n >= len(set(introns))
+    for _ in range(400):
+        st = int(rng.integers(0, len(g) - 10)); en = min(len(g), st + int(rng.integers(1, 30000)))
+        a = np.zeros(en - st, dtype=np.uint8); b = np.full(en - st, 77, dtype=np.uint8)
+        ra = R.mm_idx_bed_junc(mi, 0, st, en, a.ctypes.data_as(C.c_void_p))
+        rb = H.hs_bed_junc(C.c_void_p(I), 1, 0, st, en, b.ctypes.data_as(C.c_void_p))
+        assert ra == rb and np.array_equal(a, b), (st, en)
+    H.hs_bed_free(C.c_void_p(I), 1)
+
+
+def test_driver_with_junction_annotation(libs, tmp_path):
+    """-x splice --junc-bed: the junction flags reach ksw_exts2 exactly as mm_get_junc / mm_idx_bed_junc pass them (per-call windows,
+    reversed for the left extension), for annotated non-canonical introns, decoys next to the true sites and both strands"""
+    H, R, api = libs
+    rng = np.random.default_rng(5)
+    g, reads, introns = _spliced_set(60, 36)
+    bed = str(tmp_path / "anno.bed"); _write_bed(bed, introns, rng)
+    n, _ = run_case(H, R, api, [g], ["chr0"], reads, preset="splice", w=5, is_cdna=1, bed=bed)
     assert n >= 30
 
 

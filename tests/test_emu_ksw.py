@@ -123,27 +123,31 @@ def test_emulated_kernels_match_oracle(emu):
     assert n_zd >= 20
 
 
-def small_spliced_pair(rng, n_exon, err):
+def small_spliced_pair(rng, n_exon, err, introns_out=None):
     ex = [rng.integers(0, 4, int(rng.integers(20, 90))).astype(np.uint8) for _ in range(n_exon)]
-    parts = [ex[0]]
+    parts = [ex[0]]; pos = len(ex[0])
     for k in range(1, n_exon):
         intron = rng.integers(0, 4, int(rng.integers(30, 200))).astype(np.uint8)
         sig = int(rng.integers(0, 5))
         if sig < 3: intron[:2] = [2, 3]; intron[-2:] = [0, 2]
         elif sig == 3: intron[:2] = [2, 1]; intron[-2:] = [0, 2]
+        if introns_out is not None:
+            introns_out.append((pos, pos + len(intron)))
+        pos += len(intron) + len(ex[k])
         parts += [intron, ex[k]]
     q = O.mutate(np.concatenate(ex), rng, err=err)
     return (q if len(q) else np.array([0], dtype=np.uint8)), np.concatenate(parts)
 
 
-def check_splice_jobs(emu, rng, models, n_jobs, max_exons):
+def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False):
     L, ctx, KswJob, KswRes, KswScore = emu
     SPF, SPR, JOB_SPLICE = 0x100, 0x200, 0x80000
     mat = O.simple_mat(1, 2, 1)
     for model in models:  # the model bits are per batch (mm_mapopt_t), the strand bits per job
-        pairs, params = [], []
+        pairs, params, true_introns = [], [], []
         for it in range(n_jobs):
-            q, t = small_spliced_pair(rng, int(rng.integers(1, max_exons + 1)), float(rng.choice([0.0, 0.03, 0.1])))
+            true_introns.append([])
+            q, t = small_spliced_pair(rng, int(rng.integers(1, max_exons + 1)), float(rng.choice([0.0, 0.03, 0.1])), true_introns[-1])
             if rng.random() < 0.1:
                 q[rng.integers(0, len(q))] = 4
             base = int(rng.choice([0, APPROX, EXT, EXT | RIGHT | REVC, RIGHT]))
@@ -151,11 +155,35 @@ def check_splice_jobs(emu, rng, models, n_jobs, max_exons):
         n = len(pairs)
         qcat = np.concatenate([p[0] for p in pairs]); tcat = np.concatenate([p[1] for p in pairs])
         jobs = (KswJob * n)(); qo = to = tot = 0
+        introns, juncs = [], [None] * n
         for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
             j = jobs[i]
             j.q_start, j.t_start, j.q_step, j.t_step, j.qlen, j.tlen = qo, to, 1, 1, len(qq), len(tt)
             j.w, j.zdrop, j.end_bonus, j.flag = pr["w"], pr["zdrop"], pr["end_bonus"], pr["flag"]
+            if with_junc:
+                # annotated introns in the coordinates of the concatenated target: inside this job's window, or sticking out of it
+                # (those must be ignored, index.c:816); every other job reads its target backwards (t_step = -1, reversed junc[])
+                lt = len(tt); flags = np.zeros(lt, dtype=np.uint8)
+                cand = [(to + int(rng.integers(-5, lt)), int(rng.integers(1, 60))) for _ in range(max(1, lt // 30))]
+                cand = [(st, st + ln) for st, ln in cand]
+                for st, en in true_introns[i]:  # the real introns, some of them shifted by a few bases
+                    d = int(rng.choice([0, 0, 0, -2, 3]))
+                    cand.append((to + st + d, to + en + d))
+                for st, en in cand:
+                    sd = int(rng.choice([1, -1, -1, 1, 0]))
+                    introns.append((st, en, sd))
+                    if st >= to and en <= to + lt and sd != 0:
+                        flags[st - to] |= 1 if sd > 0 else 8; flags[en - 1 - to] |= 2 if sd > 0 else 4
+                if i % 2:
+                    j.t_start, j.t_step = to + lt - 1, -1
+                    pairs[i] = (qq, tt[::-1].copy()); flags = flags[::-1].copy()
+                juncs[i] = flags
             qo += len(qq); to += len(tt); tot += len(qq) + len(tt) + 2
+        if with_junc:
+            # the device reads a reversed job backwards from the forward array, so tcat stays as built; pairs[i] now holds what the oracle sees
+            introns.sort(key=lambda x: x[0])
+            st = np.array([x[0] for x in introns], dtype=np.int64); en = np.array([x[1] for x in introns], dtype=np.int64); sd = np.array([x[2] for x in introns], dtype=np.int8)
+            assert L.mmb_ctx_set_junctions(ctx, C.c_int64(len(introns)), st.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p)) == 0
         sc = KswScore()
         for i in range(25):
             sc.mat[i] = int(mat[i])
@@ -163,12 +191,25 @@ def check_splice_jobs(emu, rng, models, n_jobs, max_exons):
         res = (KswRes * n)(); cig = np.zeros(tot, dtype=np.uint32)
         used = L.mmb_ksw_batch_host(ctx, C.byref(sc), n, jobs, qcat.ctypes.data, len(qcat), tcat.ctypes.data, len(tcat), res, cig.ctypes.data, len(cig))
         assert used >= 0
+        if with_junc:
+            L.mmb_ctx_set_junctions(ctx, C.c_int64(0), None, None, None)
+        n_changed = 0
         for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
             r = res[i]
             g = dict(max=r.max, zdropped=r.zdropped, max_q=r.max_q, max_t=r.max_t, mqe=r.mqe, mqe_t=r.mqe_t, mte=r.mte, mte_q=r.mte_q, score=r.score,
                      n_cigar=r.n_cigar, reach_end=r.reach_end, cigar=[int(x) for x in cig[r.cigar_off:r.cigar_off + r.n_cigar]])
-            exp = O.oracle_exts2(qq, tt, mat, 2, 1, 32, 9, pr["zdrop"], pr["end_bonus"], 9, 5, pr["flag"] & 0x1fff)
+            exp = O.oracle_exts2(qq, tt, mat, 2, 1, 32, 9, pr["zdrop"], pr["end_bonus"], 9, 5, pr["flag"] & 0x1fff, juncs[i])
+            if with_junc:
+                n_changed += exp != O.oracle_exts2(qq, tt, mat, 2, 1, 32, 9, pr["zdrop"], pr["end_bonus"], 9, 5, pr["flag"] & 0x1fff)
             assert g == exp, (hex(model), i, len(qq), len(tt), hex(pr["flag"]), {k: (g[k], exp[k]) for k in exp if g[k] != exp[k] and k != "cigar"}, g["cigar"][:8], exp["cigar"][:8])
+        assert not with_junc or n_changed >= 3, n_changed  # the annotation really changed some of the expected results
+
+
+def test_emulated_splice_kernel_with_junction_annotation(emu):
+    """the annotated-junction branch of ksw_exts2_sse (:220-241) in the spliced kernel: the flags are derived on the device from a
+    sorted intron table (mmb_ctx_set_junctions) with mm_idx_bed_junc's window rule, for forward and reversed targets"""
+    FLANK, CMPLX = 0x400, 0x800
+    check_splice_jobs(emu, np.random.default_rng(78), (FLANK | CMPLX, 0), 24, 3, with_junc=True)
 
 
 def test_emulated_splice_kernel_matches_oracle(emu):

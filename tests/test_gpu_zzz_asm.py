@@ -61,3 +61,32 @@ def test_alt_contigs(tmp_path):
     n = compare(["-x", "map-ont", "-c", "--alt", af, rf, qf])
     assert n >= 400
     compare(["-x", "map-ont", "-a", "--alt", af, "--alt-drop", "0.3", rf, qf], sam=True)
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_junction_annotation_vs_reference(tmp_path):
+    """-x splice --junc-bed (mm_idx_bed_read index.c:672-800; junction flags per ksw_exts2 call, align.c:638-643, derived in the
+    kernel from the device intron table with mm_idx_bed_junc's window rule): transcripts over a genome where only a third of the
+    introns carry canonical signals, annotation with duplicates, shifted decoys and both strands"""
+    from test_aligndriver_vs_ref import _spliced_set, _write_bed
+    rng = np.random.default_rng(15)
+    g, reads, introns = _spliced_set(70, 150, glen=800_000)
+    rf, qf, bed = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa"), str(tmp_path / "anno.bed")
+    synth.write_fasta(rf, ["chr0"], [g]); synth.write_fasta(qf, ["tr%d" % i for i in range(len(reads))], reads)
+    _write_bed(bed, introns, rng)
+    assert compare(["-x", "splice", "-c", "--cs", "--junc-bed", bed, rf, qf]) >= 120
+    compare(["-x", "splice", "--junc-bed", bed, "--junc-bonus", "5", "-a", rf, qf], sam=True)
+
+
+def test_splice_kernel_with_junction_table_matches_oracle():
+    """the same check as tests/test_emu_ksw.py::test_emulated_splice_kernel_with_junction_annotation on the device, 200 jobs per model"""
+    import ctypes as C
+    import minimap2_b200 as mb
+    from minimap2_b200._lib import KswJob, KswRes, KswScore, lib
+    import test_emu_ksw as E
+    L = lib()
+    L.mmb_ctx_set_junctions.restype = C.c_int
+    L.mmb_ctx_set_junctions.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    ctx = mb.Context(0)
+    E.check_splice_jobs((L, C.c_void_p(ctx.h), KswJob, KswRes, KswScore), np.random.default_rng(179), (0x400 | 0x800, 0x400, 0), 200, 5, with_junc=True)
+    ctx.close()

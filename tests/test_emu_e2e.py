@@ -129,6 +129,36 @@ def _ava_inputs(d):
     return ["-x", "ava-ont", "-f", "2", qf, qf]
 
 
+def _edge_inputs(d):
+    """FASTQ (gzipped, comments, qualities) with reads that cannot map: shorter than k, all N, lower case, an N stretch"""
+    import gzip
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(1)
+    g = synth.random_genome(6000, 3)[0]
+    r = np.frombuffer(bytes(g), dtype=np.uint8)
+    reads = [("short", b"ACGTACGTAC"), ("allN", b"N" * 300), ("good", bytes(synth.mutate_ascii(r[1000:2200], rng, 0.05))),
+             ("lower", bytes(synth.mutate_ascii(r[3000:3900], rng, 0.02)).lower()), ("withN", bytes(r[4000:4400]) + b"N" * 10 + bytes(r[4410:5000]))]
+    rf, qf = os.path.join(d, "edge_ref.fa"), os.path.join(d, "edge_reads.fq.gz")
+    synth.write_fasta(rf, ["chr0"], [bytes(g)])
+    with gzip.open(qf, "wt") as f:
+        for n, s_ in reads:
+            f.write("@%s some comment\n%s\n+\n%s\n" % (n, s_.decode(), "I" * len(s_)))
+    return ["-a", "-y", "-K", "1k", rf, qf]
+
+
+def _multipart_inputs(d):
+    """-I 4k splits a three-contig reference into several index parts; every part is mapped in turn (main.c:437-511)"""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(2)
+    cs = synth.random_genome(9000, 5, n_contigs=3)
+    reads = [bytes(synth.mutate_ascii(np.frombuffer(bytes(c), dtype=np.uint8)[500:1800], rng, 0.05)) for c in cs]
+    rf, qf = os.path.join(d, "mp_ref.fa"), os.path.join(d, "mp_reads.fa")
+    synth.write_fasta(rf, ["c0", "c1", "c2"], [bytes(c) for c in cs]); synth.write_fasta(qf, ["q0", "q1", "q2"], reads)
+    return ["-c", "-I", "4k", "--paf-no-hit", rf, qf]
+
+
 @pytest.fixture(scope="module")
 def emu_runs(emu_cli, tmp_path_factory):
     """Every emulated CLI run of this module, started together (4 at a time): the emulator spends most of its time in thread
@@ -148,6 +178,8 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["asm20"] = (_asm_inputs(d, "asm20", 0.03), d, True)
         jobs["alt"] = (_alt_inputs(d), d, True)
         jobs["ava"] = (_ava_inputs(d), d, True)
+        jobs["edge"] = (_edge_inputs(d), d, True)
+        jobs["multipart"] = (_multipart_inputs(d), d, True)
 
     def one(item):
         name, (args, cwd, with_ref) = item
@@ -229,6 +261,16 @@ def test_emulated_all_vs_all_overlap_matches_reference(emu_runs):
     r = emu_runs["ava"]
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"] and len(r["ref"]) >= 4
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,n_min", [("edge", 7), ("multipart", 3)])
+def test_emulated_cli_edge_cases_match_reference(emu_runs, name, n_min):
+    """unmappable reads, gzipped FASTQ with comments in SAM (-a -y), several mini-batches; a multi-part index with --paf-no-hit"""
+    r = emu_runs[name]
+    assert r["rc"] == 0, r["err"]
+    strip = lambda ls: [l for l in ls if not l.startswith("@PG")]
+    assert strip(r["out"]) == strip(r["ref"]) and len(r["ref"]) >= n_min
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

@@ -540,7 +540,7 @@ extern "C" mm_idx_t *mm_idx_load(FILE *fp)
 		sum_len += s->len;
 	}
 	{
-		std::vector<uint64_t> keys, pos, p;
+		std::vector<uint64_t> keys, pos, p, kvbuf;
 		std::vector<uint32_t> cnt;
 		const int b = mi->b;
 		for (uint64_t bi = 0; bi < (1ULL << b); ++bi) {
@@ -549,9 +549,10 @@ extern "C" mm_idx_t *mm_idx_load(FILE *fp)
 			p.resize(np);
 			if (np && fread(p.data(), 8, np, fp) != (size_t)np) goto fail;
 			if (fread(&size, 4, 1, fp) != 1) goto fail;
+			kvbuf.resize((size_t)size * 2); // the bucket's (key, value) pairs in one read
+			if (size && fread(kvbuf.data(), 16, size, fp) != size) goto fail;
 			for (uint32_t j = 0; j < size; ++j) {
-				uint64_t kv[2];
-				if (fread(kv, 8, 2, fp) != 2) goto fail;
+				const uint64_t *kv = &kvbuf[(size_t)j * 2];
 				keys.push_back((kv[0] >> 1) << b | bi);
 				if (kv[0] & 1) cnt.push_back(1), pos.push_back(kv[1]);
 				else {
@@ -642,7 +643,7 @@ extern "C" int mm_idx_reader_eof(const mm_idx_reader_t *r) // index.c:639-642
 	return r->is_idx? (feof(r->fp.idx) || ftell(r->fp.idx) == r->idx_size) : r->fp.seq->rd->eof();
 }
 
-// optional annotations: accepted for API compatibility, not supported by this build (out of scope)
+// splice-score annotations: accepted for API compatibility, not supported by this build
 static int unsupported(const char *what)
 {
 	if (mm_verbose >= 1) fprintf(stderr, "[ERROR] %s is not supported by minimap2_b200 (index annotations are out of scope)\n", what);

@@ -62,8 +62,14 @@ struct ReadAlign {          // per-read alignment working set (lives across wave
 	std::vector<mmb_ksw_job_t> want; // jobs requested by the current replay
 	std::vector<int> want_slot;      // their slots in keys[]
 	bool incomplete = false;
-	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); incomplete = false; }
-	int find(const KswKey &k) const { for (size_t i = 0; i < keys.size(); ++i) if (keys[i] == k) return (int)i; return -1; }
+	mutable size_t hint = 0;         // a replay asks for its jobs in the order the previous one did: search from the last hit on
+	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); incomplete = false; hint = 0; }
+	int find(const KswKey &k) const { // keys are unique (a key is added only after a miss)
+		const size_t n = keys.size();
+		for (size_t c = 0, i = hint < n? hint : 0; c < n; ++c, i = i + 1 == n? 0 : i + 1)
+			if (keys[i] == k) { hint = i + 1; return (int)i; }
+		return -1;
+	}
 };
 
 // Runs the whole per-read alignment (mm_align_skeleton semantics) using cached ksw results; missing results are appended

@@ -25,7 +25,8 @@ def libs():
     csrc = os.path.join(ROOT, "minimap2_b200", "csrc")
     src = [os.path.join(csrc, "align.cc"), os.path.join(csrc, "hits.cc"), os.path.join(csrc, "format.cc"), os.path.join(ROOT, "tests", "hostshim", "hostshim.cc"),
            os.path.join(ROOT, "tests", "hostshim", "alignshim.cc")]
-    if not os.path.exists(SHIM) or any(os.path.getmtime(s) > os.path.getmtime(SHIM) for s in src):
+    deps = src + [os.path.join(csrc, h) for h in ("hostlogic.h", "annot.h", "mm_algo.cuh")] + [os.path.join(ROOT, "include", "mm_b200.h")]
+    if not os.path.exists(SHIM) or any(os.path.getmtime(s) > os.path.getmtime(SHIM) for s in deps):
         inc = ["-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-I/usr/local/cuda/include"]
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared"] + inc + src +
                               ["-L" + O.ORACLE_DIR, "-lmm2oracle", "-Wl,-rpath," + O.ORACLE_DIR, "-o", SHIM])

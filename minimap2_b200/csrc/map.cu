@@ -230,7 +230,6 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 {
 	const char *what = nullptr;
 	if (opt->flag & (MM_F_SR | MM_F_SR_RNA)) what = "short-read mode (-x sr / splice:sr)";
-	else if (opt->max_occ > opt->mid_occ) what = "re-chaining with a second occurrence cutoff (-f INT,INT)";
 	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
 	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
 	if (what) {
@@ -242,8 +241,15 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 } // namespace
 
 static double g_batch_t0 = 0;
+// pass: first mapping pass, or the re-chaining pass of map.c:293-316 over the reads the first pass left without a chain
+struct MapPass {
+	int occ_cut;        // max_occ argument of mm_collect_matches (map.c:174): mid_occ, or opt->max_occ when re-chaining
+	bool rescue;        // long-join re-chaining (map.c:283-292) only exists in the first pass
+	uint8_t *no_chain;  // out (optional): 1 for reads that went through chaining and came out with no chain at all
+};
+
 static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
-					 int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
+					 int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads, const MapPass &pass)
 {
 	if (n_reads <= 0) return 0;
 	static const bool timing = getenv("MM_B200_TIMING") != nullptr;
@@ -306,7 +312,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	S.ix = B->view(mi), S.n_reads = n, S.mz = (m128*)bb.mz.p, S.mz_off = d_mz_off, S.qlen = d_qlen;
 	S.n_mz = bb.n_mz.as<int32_t>((size_t)n);
 	S.q_occ_max = opt->mid_occ, S.q_occ_frac = opt->q_occ_frac;
-	S.max_occ = opt->mid_occ, S.max_max_occ = opt->max_max_occ, S.occ_dist = opt->occ_dist, S.flag = opt->flag;
+	S.max_occ = pass.occ_cut, S.max_max_occ = opt->max_max_occ, S.occ_dist = opt->occ_dist, S.flag = opt->flag;
 	const size_t nm = (size_t)total_mz + 4;
 	S.s_n = bb.s_n.as<uint32_t>(nm), S.s_off = bb.s_off.as<uint64_t>(nm), S.k_idx = bb.k_idx.as<uint32_t>(nm), S.k_aoff = bb.k_aoff.as<uint32_t>(nm);
 	S.flt = bb.flt.as<uint8_t>(nm), S.mini_pos = bb.mini_pos.as<uint64_t>(nm);
@@ -376,7 +382,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	int64_t *d_doff = bb.doff.as<int64_t>((size_t)(n + 1) * 3);
 	int64_t *d_uo = d_doff, *d_vo = d_doff + (n + 1), *d_mo = d_doff + 2 * (n + 1);
 	// long-join rescue (map.c:283-292): re-chain on the device with mg_lchain_rmq at bw_long
-	if (opt->bw_long > opt->bw && (opt->flag & (MM_F_SPLICE | MM_F_SR | MM_F_NO_LJOIN)) == 0) {
+	if (pass.rescue && opt->bw_long > opt->bw && (opt->flag & (MM_F_SPLICE | MM_F_SR | MM_F_NO_LJOIN)) == 0) {
 		to_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_n_v, n, d_vo);
 		++ctx->n_launch;
 		const int64_t tv = mmb_exclusive_scan_i64(ctx, d_vo, n, true);
@@ -434,6 +440,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		ReadState &r = rs[live[j]];
 		r.rep_len = h_rep[j];
 		r.n_u = (int)(h_uo[j + 1] - h_uo[j]), r.u = h_du + h_uo[j];
+		if (pass.no_chain) pass.no_chain[live[j]] = r.n_u == 0;
 		r.n_a = (int)(h_vo[j + 1] - h_vo[j]), r.a_src = h_da + h_vo[j];
 		r.n_mini_pos = (int)(h_mo[j + 1] - h_mo[j]), r.mini_pos = h_dm + h_mo[j];
 		uint32_t hash = r.name && !(opt->flag & MM_F_NO_HASH_NAME)? x31_hash_string(r.name) : 0; // map.c:246-248
@@ -646,14 +653,10 @@ static GroupCtx &get_group(int g, int device)
 // The batch is split into NG contiguous groups (balanced by bases) that run the whole pipeline concurrently, each on its
 // own CUDA stream with its own arenas: while one group is in a host phase (hit logic, alignment replay) the others keep
 // the GPU busy. This is the scheduler that replaces kt_pipeline/kt_for (map.c:541-691, kthread.c:54-159).
-extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
-							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
+static int map_batch_pass(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
+						  int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads, const MapPass &pass)
 {
-	if (n_reads <= 0) return 0;
-	static std::mutex batch_mu; // the scheduler groups (streams, arenas) are process-wide: concurrent callers take turns
-	std::lock_guard<std::mutex> batch_lk(batch_mu);
-	g_batch_t0 = realtime();
-	unsupported_check(mi, opt);
+	auto sub = [&](int b) { MapPass p = pass; if (p.no_chain) p.no_chain += b; return p; }; // the pass as a group starting at read b sees it
 	static int ng_env = getenv("MM_B200_GROUPS")? atoi(getenv("MM_B200_GROUPS")) : 12;
 	const bool sequential = g_groups_override < 0; // negative override: same groups, run one after another (clean per-kernel timing)
 	const int ng_req = g_groups_override > 0? g_groups_override : g_groups_override < 0? -g_groups_override : ng_env;
@@ -663,7 +666,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	if (n_reads < 64 * NG || total < 4000000) NG = 1;
 	const int device = mi->B->ctx->device;
 	for (int g = 0; g < NG; ++g) { GroupCtx &gc = get_group(g, device); gc.ctx->profiling = mmb_default_ctx()->profiling; gc.gated = NG > 1 && !sequential; }
-	if (NG == 1) return map_group(get_group(0, device), mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads);
+	if (NG == 1) return map_group(get_group(0, device), mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads, pass);
 	std::vector<int> cut(NG + 1, 0);
 	{
 		// equal shares, except that the last three groups shrink (3/4, 1/2, 1/4 of a share): the end of the batch is then
@@ -682,7 +685,7 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 		for (int g = 0; g < NG; ++g) {
 			const int b = cut[g], m = cut[g + 1] - cut[g];
 			if (m > 0) map_group(get_group(g, device), mi, m, qlens + b, seqs + b, names? names + b : nullptr, n_regs_out + b, regs_out + b,
-								 rep_len_out? rep_len_out + b : nullptr, opt, n_threads);
+								 rep_len_out? rep_len_out + b : nullptr, opt, n_threads, sub(b));
 		}
 		return 0;
 	}
@@ -691,9 +694,50 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 		th.emplace_back([&, g]() {
 			const int b = cut[g], m = cut[g + 1] - cut[g];
 			if (m > 0) map_group(get_group(g, device), mi, m, qlens + b, seqs + b, names? names + b : nullptr, n_regs_out + b, regs_out + b,
-								 rep_len_out? rep_len_out + b : nullptr, opt, n_threads);
+								 rep_len_out? rep_len_out + b : nullptr, opt, n_threads, sub(b));
 		});
 	for (auto &x : th) x.join();
+	return 0;
+}
+
+extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, const char **seqs, const char **names,
+							int *n_regs_out, mm_reg1_t **regs_out, int *rep_len_out, const mm_mapopt_t *opt, int n_threads)
+{
+	if (n_reads <= 0) return 0;
+	static std::mutex batch_mu; // the scheduler groups (streams, arenas) are process-wide: concurrent callers take turns
+	std::lock_guard<std::mutex> batch_lk(batch_mu);
+	g_batch_t0 = realtime();
+	unsupported_check(mi, opt);
+	const bool rechain = opt->max_occ > opt->mid_occ && !(opt->flag & MM_F_RMQ); // map.c:293
+	if (!rechain) {
+		const MapPass first = { opt->mid_occ, true, nullptr };
+		return map_batch_pass(mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads, first);
+	}
+	// Re-chaining with the higher occurrence cutoff (map.c:293-316). For single-segment queries the test "the best chain has all
+	// the segments" always holds, so exactly the reads that came out of chaining with no chain and have rep_len > 0 collect their
+	// seeds again with max_occ = opt->max_occ and are chained again (no long-join pass after it: the two are one if / else if).
+	// Those reads have no hits from the first pass, so the second pass simply supplies their result.
+	std::vector<uint8_t> no_chain((size_t)n_reads, 0);
+	std::vector<int> rep_tmp;
+	if (!rep_len_out) { rep_tmp.assign((size_t)n_reads, 0); rep_len_out = rep_tmp.data(); }
+	const MapPass first = { opt->mid_occ, true, no_chain.data() };
+	map_batch_pass(mi, n_reads, qlens, seqs, names, n_regs_out, regs_out, rep_len_out, opt, n_threads, first);
+	std::vector<int> idx;
+	for (int i = 0; i < n_reads; ++i) if (no_chain[i] && rep_len_out[i] > 0) idx.push_back(i);
+	if (idx.empty()) return 0;
+	const int m = (int)idx.size();
+	std::vector<int> ql(m), nr(m, 0), rl(m, 0);
+	std::vector<const char*> sq(m), nm(m);
+	std::vector<mm_reg1_t*> rg(m, nullptr);
+	for (int k = 0; k < m; ++k) ql[k] = qlens[idx[k]], sq[k] = seqs[idx[k]], nm[k] = names? names[idx[k]] : nullptr;
+	const MapPass second = { opt->max_occ, false, nullptr };
+	map_batch_pass(mi, m, ql.data(), sq.data(), names? nm.data() : nullptr, nr.data(), rg.data(), rl.data(), opt, n_threads, second);
+	for (int k = 0; k < m; ++k) {
+		const int i = idx[k];
+		for (int j = 0; j < n_regs_out[i]; ++j) free(regs_out[i][j].p);
+		free(regs_out[i]);
+		n_regs_out[i] = nr[k], regs_out[i] = rg[k], rep_len_out[i] = rl[k];
+	}
 	return 0;
 }
 

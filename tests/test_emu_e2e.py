@@ -84,6 +84,24 @@ def _high_occ_inputs(d):
     return ["-c", "-f", "3", "-e", "150", "-K", "1500", rf, qf]  # -K: two mini-batches through the overlapped read/map/write steps
 
 
+def _rechain_inputs(d):
+    """-f 3,50 with -e 0: reads that lie inside copies of a repeat lose every seed to the first cutoff (no chain, rep_len > 0) and
+    are chained again with the second one (map.c:293-316); a read with unique flanks keeps its first-pass chains"""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(12)
+    g = np.frombuffer(bytes(synth.random_genome(9_000, 6)[0]), dtype=np.uint8).copy()
+    unit = g[200:700].copy()
+    for k in range(8):
+        s = 1000 + k * 900
+        g[s:s + 500] = unit
+        g[s + rng.integers(0, 500, 2)] = list(b"AC")
+    reads = [synth.mutate_ascii(g[1930:2370], rng, 0.03), synth.mutate_ascii(g[4620:5080], rng, 0.03), synth.mutate_ascii(g[5000:6500], rng, 0.04)]
+    rf, qf = os.path.join(d, "rc_ref.fa"), os.path.join(d, "rc_reads.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["in0", "in1", "span"], reads)
+    return ["-c", "-f", "3,50", "-e", "0", rf, qf]
+
+
 def _asm_inputs(d, preset, div):
     import numpy as np
     import synth
@@ -179,6 +197,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["alt"] = (_alt_inputs(d), d, True)
         jobs["ava"] = (_ava_inputs(d), d, True)
         jobs["edge"] = (_edge_inputs(d), d, True)
+        jobs["rechain"] = (_rechain_inputs(d), d, True)
         jobs["multipart"] = (_multipart_inputs(d), d, True)
 
     def one(item):
@@ -241,6 +260,15 @@ def test_emulated_assembly_presets_match_reference(emu_runs, preset):
     r = emu_runs[preset]
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"] and len(r["ref"]) >= 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_second_occurrence_cutoff_matches_reference(emu_runs):
+    """-f INT,INT: the re-chaining pass of map.c:293-316 (seeds collected again with max_occ for reads left without a chain)"""
+    r = emu_runs["rechain"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"]
+    assert any(l.startswith("in0\t") for l in r["ref"]) and any(l.startswith("in1\t") for l in r["ref"])  # mapped thanks to the second pass
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

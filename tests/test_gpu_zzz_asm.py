@@ -90,3 +90,15 @@ def test_splice_kernel_with_junction_table_matches_oracle():
     ctx = mb.Context(0)
     E.check_splice_jobs((L, C.c_void_p(ctx.h), KswJob, KswRes, KswScore), np.random.default_rng(179), (0x400 | 0x800, 0x400, 0), 200, 5, with_junc=True)
     ctx.close()
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("extra", [["-f", "4,400", "-e", "0"], ["-f", "8,2000"]])
+def test_second_occurrence_cutoff(tmp_path, extra):
+    """-f INT,INT (map.c:293-316): reads left without a chain by the first cutoff collect their seeds again with the second one"""
+    contigs = synth.random_genome(400_000, 61, n_contigs=2, repeat_frac=0.6)
+    reads = synth.make_reads(contigs, 500, 1500, 0.06, 161, chimeric_frac=0.0)
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    compare(["-c"] + extra + [rf, qf])

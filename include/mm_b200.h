@@ -110,6 +110,12 @@ int64_t mmb_sketch_batch_host(mmb_ctx_t *ctx, int n_seq, const char *seqs, const
  * mm_idx_bed_junc does for the window mm_align1 passes. n = 0 clears it. Returns -1 if st[] is not sorted. */
 int mmb_ctx_set_junctions(mmb_ctx_t *ctx, int64_t n, const int64_t *st, const int64_t *en, const int8_t *strand);
 
+/* Splice scores for MMB_JOB_SPLICE | MMB_KSW_SPLICE_SCORE jobs (the junc[] bytes mm_idx_spsc_get, index.c:1055-1075, hands to
+ * ksw_exts2_sse, ksw2_exts2_sse.c:213-219): per strand (0: jobs without MMB_KSW_SPLICE_REV, 1: with) n positions in strictly
+ * ascending order, in the coordinates of the target array, with their bytes (score+64)<<1 | acceptor. A job sees the entries strictly
+ * inside its target window. n = 0 clears the strand's table. Returns -1 on unsorted input. */
+int mmb_ctx_set_splice_scores(mmb_ctx_t *ctx, int strand, int64_t n, const int64_t *pos, const uint8_t *val);
+
 /* ---------------------------------------------------------------------------------------------------------
  * K2c: chaining   (replaces mg_lchain_dp lchain.c:148-217 incl. mg_chain_backtrack/compact_a, and mg_lchain_rmq :250-368)
  * --------------------------------------------------------------------------------------------------------- */

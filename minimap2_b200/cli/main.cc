@@ -41,7 +41,7 @@ static struct option long_options[] = {
 	{ "score-N", required_argument, 0, 331 }, { "eqx", no_argument, 0, 332 }, { "paf-no-hit", no_argument, 0, 333 },
 	{ "no-end-flt", no_argument, 0, 335 }, { "hard-mask-level", no_argument, 0, 336 }, { "cap-sw-mem", required_argument, 0, 337 },
 	{ "max-qlen", required_argument, 0, 338 }, { "max-chain-iter", required_argument, 0, 339 }, { "sam-hit-only", no_argument, 0, 342 },
-	{ "chain-gap-scale", required_argument, 0, 343 }, { "junc-bed", required_argument, 0, 340 }, { "junc-bonus", required_argument, 0, 341 }, { "junc-pen", required_argument, 0, 358 }, { "alt", required_argument, 0, 344 }, { "alt-drop", required_argument, 0, 345 }, { "mask-len", required_argument, 0, 346 },
+	{ "chain-gap-scale", required_argument, 0, 343 }, { "junc-bed", required_argument, 0, 340 }, { "junc-bonus", required_argument, 0, 341 }, { "junc-pen", required_argument, 0, 358 }, { "spsc", required_argument, 0, 357 }, { "spsc-scale", required_argument, 0, 363 }, { "spsc0", required_argument, 0, 364 }, { "alt", required_argument, 0, 344 }, { "alt-drop", required_argument, 0, 345 }, { "mask-len", required_argument, 0, 346 },
 	{ "rmq", optional_argument, 0, 347 }, { "q-occ-frac", required_argument, 0, 350 }, { "chain-skip-scale", required_argument, 0, 351 },
 	{ "no-hash-name", no_argument, 0, 353 }, { "secondary-seq", no_argument, 0, 354 }, { "ds", no_argument, 0, 355 },
 	{ "rmq-inner", required_argument, 0, 356 }, { "help", no_argument, 0, 'h' }, { "version", no_argument, 0, 'V' },
@@ -55,7 +55,8 @@ int main(int argc, char *argv[])
 	mm_mapopt_t opt;
 	mm_idxopt_t ipt;
 	int c, n_threads = 3, old_best_n = -1, li = 0;
-	char *fnw = 0, *s, *alt_list = 0, *fn_bed_junc = 0;
+	char *fnw = 0, *s, *alt_list = 0, *fn_bed_junc = 0, *fn_spsc = 0;
+	float spsc_scale = 0.7f;
 	mm_verbose = 3;
 	mm_realtime0 = realtime();
 	mm_set_opt(0, &ipt, &opt);
@@ -138,7 +139,9 @@ int main(int argc, char *argv[])
 		else if (c == 351) opt.chain_skip_scale = atof(optarg);
 		else if (c == 340) fn_bed_junc = optarg;
 		else if (c == 341) opt.junc_bonus = atoi(optarg);
-		else if (c == 358) opt.junc_pen = atoi(optarg);
+		else if (c == 358 || c == 364) opt.junc_pen = atoi(optarg);
+		else if (c == 357) fn_spsc = optarg;
+		else if (c == 363) spsc_scale = (float)atof(optarg);
 		else if (c == 344) alt_list = optarg;
 		else if (c == 345) opt.alt_drop = atof(optarg);
 		else if (c == 346) opt.mask_len = (int)parse_num(optarg);
@@ -204,6 +207,10 @@ int main(int argc, char *argv[])
 		if (fn_bed_junc) { // main.c:467-471
 			mm_idx_bed_read(mi, fn_bed_junc, 1);
 			if (mi->I == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] failed to load the junction BED file\n");
+		}
+		if (fn_spsc) { // main.c:482-486
+			mm_idx_spsc_read2(mi, fn_spsc, mm_max_spsc_bonus(&opt), spsc_scale);
+			if (mi->spsc == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] failed to load the splice score file\n");
 		}
 		if (alt_list) mm_idx_alt_read(mi, alt_list); // main.c:487
 		if ((opt.flag & MM_F_OUT_SAM) && idx_rdr->n_parts == 1) { // SAM header (format.c:128-148)

@@ -607,6 +607,7 @@ struct Driver {
 			if (splice_flag & MM_F_SPLICE_FOR) sflag |= rev? MMB_KSW_SPLICE_REV : MMB_KSW_SPLICE_FOR;
 			if (splice_flag & MM_F_SPLICE_REV) sflag |= rev? MMB_KSW_SPLICE_FOR : MMB_KSW_SPLICE_REV;
 			if (opt->flag & MM_F_SPLICE_FLANK) sflag |= MMB_KSW_SPLICE_FLANK;
+			if (mi->spsc) sflag |= MMB_KSW_SPLICE_SCORE; // align.c:688: junc[] carries splice scores (mm_idx_spsc_get)
 		}
 		filter_bad_seeds(as1, cnt1, a, 10, 40, opt->max_gap >> 1, 10);
 		filter_bad_seeds_alt(as1, cnt1, a, 30, opt->max_gap >> 1);

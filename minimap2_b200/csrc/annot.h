@@ -130,3 +130,97 @@ static inline int mmx_bed_junc(const mm_idx_intv_s *I, int32_t n_seq, int32_t ct
 	}
 	return left;
 }
+
+// ---- splice scores (mm_idx_t::spsc; index.c:963-1075) ----
+struct mm_idx_spsc_s { // index.c:963-966; one entry per (contig, strand): a[] = pos<<8 | (score+64)<<1 | acceptor, sorted
+	uint32_t n, m;
+	uint64_t *a;
+};
+
+// index.c:968-1040. Line format: contig, position, strand (+/-), type (D/A), score. Returns NULL if the file cannot be opened.
+template<class Name2Id, class SeqLen> static inline mm_idx_spsc_s *mmx_spsc_read(const char *fn, uint32_t n_seq, int32_t max_sc, float scale, Name2Id name2id, SeqLen seq_len, long *n_read_)
+{
+	gzFile fp = fn && strcmp(fn, "-") != 0? gzopen(fn, "rb") : gzdopen(0, "rb");
+	if (fp == 0) return 0;
+	if (max_sc > 63) max_sc = 63;
+	mm_idx_spsc_s *S = (mm_idx_spsc_s*)calloc((size_t)n_seq * 2, sizeof(mm_idx_spsc_s));
+	long n_read = 0;
+	std::string line;
+	int c;
+	bool any = false;
+	auto flush = [&]() {
+		std::vector<char> buf(line.begin(), line.end()); buf.push_back(0);
+		line.clear(), any = false;
+		char *p, *q, *name = 0;
+		int32_t i, type = -1, strand = 0, cid = -1, score = -1;
+		int64_t pos = -1;
+		for (i = 0, p = q = buf.data();; ++p) {
+			if (*p == '\t' || *p == 0) {
+				const int ch = *p;
+				*p = 0;
+				if (i == 0) name = q;
+				else if (i == 1) pos = atol(q);
+				else if (i == 2) strand = *q == '+'? 1 : -1; // index.c:1001 as written: anything but '+' counts as the minus strand
+				else if (i == 3) type = *q == 'D'? 0 : *q == 'A'? 1 : -1;
+				else if (i == 4) { score = atoi(q); break; }
+				if (ch == 0) break;
+				q = p + 1, ++i;
+			}
+		}
+		if (i < 4) return;
+		if (scale > 0.0f && scale < 1.0f) score = score > 0.0f? (int)(score * scale + .499) : (int)(score * scale - .499);
+		if (score > max_sc) score = max_sc;
+		if (score < -max_sc) score = -max_sc;
+		cid = name2id(name);
+		if (cid < 0 || type < 0 || strand == 0 || pos < 0) return;
+		mm_idx_spsc_s *s = &S[cid << 1 | (strand > 0? 0 : 1)];
+		if (s->n == s->m) { s->m = s->m? s->m + (s->m >> 1) + 1 : 16; s->a = (uint64_t*)realloc(s->a, sizeof(uint64_t) * s->m); }
+		if (pos > 0 && pos < (int64_t)seq_len(cid)) { // scores at the ends are ignored
+			s->a[s->n++] = (uint64_t)pos << 8 | (uint64_t)(score + 64) << 1 | (uint64_t)type;
+			++n_read;
+		}
+	};
+	while ((c = gzgetc(fp)) >= 0) {
+		if (c == '\n') flush();
+		else line += (char)c, any = true;
+	}
+	if (any) flush();
+	gzclose(fp);
+	for (uint32_t j = 0; j < n_seq * 2; ++j) if (S[j].n > 0) std::sort(S[j].a, S[j].a + S[j].n); // radix_sort_64: plain ascending order of distinct-or-equal keys
+	if (n_read_) *n_read_ = n_read;
+	return S;
+}
+
+// index.c:1042-1053
+static inline int32_t mmx_spsc_find(int32_t n, const uint64_t *a, int64_t x)
+{
+	int32_t s = 0, e = n;
+	if (n == 0) return -1;
+	if (x < (int64_t)(a[0] >> 8)) return -1;
+	while (s < e) {
+		const int32_t mid = s + (e - s) / 2;
+		if (x >= (int64_t)(a[mid] >> 8) && (mid + 1 >= n || x < (int64_t)(a[mid + 1] >> 8))) return mid;
+		else if (x < (int64_t)(a[mid] >> 8)) e = mid;
+		else s = mid + 1;
+	}
+	return n - 1;
+}
+
+// index.c:1055-1075: per-position score bytes of (st, en) on one strand, 0xff where there is none; the largest byte wins
+static inline int64_t mmx_spsc_get(const mm_idx_spsc_s *S, int32_t n_seq, int32_t cid, int64_t seq_len, int64_t st, int64_t en, int32_t rev, uint8_t *sc)
+{
+	if (cid >= n_seq || cid < 0 || S == 0) return -1;
+	if (en < 0 || en > seq_len) en = seq_len;
+	memset(sc, 0xff, en - st);
+	const mm_idx_spsc_s *s = &S[cid << 1 | (!!rev)];
+	if (s->n > 0) {
+		const int32_t l = mmx_spsc_find((int32_t)s->n, s->a, st), r = mmx_spsc_find((int32_t)s->n, s->a, en);
+		for (int32_t j = l + 1; j <= r; ++j) {
+			const int64_t x = (int64_t)(s->a[j] >> 8) - st;
+			const uint8_t score = s->a[j] & 0xff;
+			if (x == en - st) continue;
+			if (sc[x] == 0xff || sc[x] < score) sc[x] = score;
+		}
+	}
+	return en - st;
+}

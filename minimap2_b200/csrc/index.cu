@@ -283,10 +283,12 @@ extern "C" void mm_idx_destroy(mm_idx_t *mi) // index.c:62-91
 		if (B->ctx) cudaSetDevice(B->ctx->device);
 		if (!B->external) { cudaFree(B->d_tab); cudaFree(B->d_pos); cudaFree(B->d_S); cudaFree(B->d_seq_off); cudaFree(B->d_seq_len); cudaFree(B->d_cnt_sorted); } cudaFree(B->d_name_rank); cudaFree(B->d_ukeys); cudaFree(B->d_ucnt); cudaFree(B->d_uoff);
 		if (B->d_junc) cudaFree(B->d_junc);
+		for (int t = 0; t < 2; ++t) if (B->d_spsc[t]) cudaFree(B->d_spsc[t]);
 		delete B->h_map;
 		delete B;
 	}
 	if (mi->I) { for (uint32_t i = 0; i < mi->n_seq; ++i) free(mi->I[i].a); free(mi->I); }
+	if (mi->spsc) { for (uint32_t i = 0; i < mi->n_seq * 2; ++i) free(mi->spsc[i].a); free(mi->spsc); }
 	for (uint32_t i = 0; i < mi->n_seq; ++i) free(mi->seq[i].name);
 	free(mi->seq); free(mi->S); free(mi);
 }
@@ -643,12 +645,6 @@ extern "C" int mm_idx_reader_eof(const mm_idx_reader_t *r) // index.c:639-642
 	return r->is_idx? (feof(r->fp.idx) || ftell(r->fp.idx) == r->idx_size) : r->fp.seq->rd->eof();
 }
 
-// splice-score annotations: accepted for API compatibility, not supported by this build
-static int unsupported(const char *what)
-{
-	if (mm_verbose >= 1) fprintf(stderr, "[ERROR] %s is not supported by minimap2_b200 (index annotations are out of scope)\n", what);
-	return -1;
-}
 extern "C" int mm_idx_alt_read(mm_idx_t *mi, const char *fn) // index.c:648-670: one contig name per line (first token), plain or gzipped
 {
 	gzFile fp = fn && strcmp(fn, "-")? gzopen(fn, "r") : gzdopen(0, "r");
@@ -705,9 +701,46 @@ extern "C" int mm_idx_bed_read(mm_idx_t *mi, const char *fn, int read_junc)
 	return 0;
 }
 extern "C" int mm_idx_bed_junc(const mm_idx_t *mi, int32_t ctg, int32_t st, int32_t en, uint8_t *s) { return mmx_bed_junc(mi->I, (int32_t)mi->n_seq, ctg, st, en, s); }
-extern "C" int32_t mm_idx_spsc_read(mm_idx_t *, const char *, int32_t) { return unsupported("--spsc"); }
-extern "C" int32_t mm_idx_spsc_read2(mm_idx_t *, const char *, int32_t, float) { return unsupported("--spsc"); }
-extern "C" int64_t mm_idx_spsc_get(const mm_idx_t *, int32_t, int64_t st0, int64_t en0, int32_t, uint8_t *sc) { memset(sc, 0, en0 - st0); return 0; }
+// index.c:968-1040 + the device copy the spliced kernel reads: per strand, one entry per position (the largest byte, which is what
+// the reference's in-window scan keeps), in global S coordinates
+extern "C" int32_t mm_idx_spsc_read2(mm_idx_t *mi, const char *fn, int32_t max_sc, float scale)
+{
+	if (mi->h == 0) mm_idx_index_name(mi);
+	if (mi->spsc) { for (uint32_t i = 0; i < mi->n_seq * 2; ++i) free(mi->spsc[i].a); free(mi->spsc); mi->spsc = 0; }
+	long n_read = 0;
+	mi->spsc = mmx_spsc_read(fn, mi->n_seq, max_sc, scale, [&](const char *name) { return mm_idx_name2id(mi, name); }, [&](int cid) { return mi->seq[cid].len; }, &n_read);
+	mm_idx_bucket_s *B = mi->B;
+	if (B) {
+		if (B->ctx) MMB_CUDA_CHECK(cudaSetDevice(B->ctx->device));
+		for (int t = 0; t < 2; ++t) { if (B->d_spsc[t]) MMB_CUDA_CHECK(cudaFree(B->d_spsc[t])); B->d_spsc[t] = nullptr, B->n_spsc[t] = 0; }
+	}
+	if (mi->spsc == 0) return -1;
+	if (mm_verbose >= 3) fprintf(stderr, "[M::%s] read %ld splice scores\n", __func__, n_read);
+	for (int t = 0; B && t < 2; ++t) {
+		std::vector<int64_t> pos; std::vector<uint8_t> val;
+		for (uint32_t i = 0; i < mi->n_seq; ++i) {
+			const mm_idx_spsc_s *s = &mi->spsc[i << 1 | t];
+			for (uint32_t j = 0; j < s->n; ++j) {
+				const int64_t p = (int64_t)mi->seq[i].offset + (int64_t)(s->a[j] >> 8);
+				const uint8_t v = (uint8_t)(s->a[j] & 0xff);
+				if (!pos.empty() && pos.back() == p) { if (val.back() == 0xff || val.back() < v) val.back() = v; } // index.c:1070
+				else pos.push_back(p), val.push_back(v);
+			}
+		}
+		if (pos.empty()) continue;
+		const size_t n = pos.size();
+		MMB_CUDA_CHECK(cudaMalloc((void**)&B->d_spsc[t], n * 9 + 64));
+		MMB_CUDA_CHECK(cudaMemcpy(B->d_spsc[t], pos.data(), n * 8, cudaMemcpyHostToDevice));
+		MMB_CUDA_CHECK(cudaMemcpy(B->d_spsc[t] + n * 8, val.data(), n, cudaMemcpyHostToDevice));
+		B->n_spsc[t] = (int64_t)n;
+	}
+	return 0;
+}
+extern "C" int32_t mm_idx_spsc_read(mm_idx_t *mi, const char *fn, int32_t max_sc) { return mm_idx_spsc_read2(mi, fn, max_sc, 1.0f); }
+extern "C" int64_t mm_idx_spsc_get(const mm_idx_t *mi, int32_t cid, int64_t st0, int64_t en0, int32_t rev, uint8_t *sc) // index.c:1055-1075
+{
+	return mmx_spsc_get(mi->spsc, (int32_t)mi->n_seq, cid, cid >= 0 && cid < (int32_t)mi->n_seq? (int64_t)mi->seq[cid].len : 0, st0, en0, rev, sc);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Multi-GPU: the device index is replicated, not sharded (reads shard). Rank 0 exports the device arrays,

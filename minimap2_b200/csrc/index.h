@@ -44,6 +44,7 @@ struct mm_idx_bucket_s {  // the opaque "B" of mm_idx_t
 	uint32_t *d_name_rank = nullptr;    // rank of every sequence name in the sorted name list (skip_seed, map.c:78-100); lazy
 	std::vector<uint32_t> name_order;   // sequence ids in name order (host side of the same)
 	uint64_t *d_ukeys = nullptr; uint32_t *d_ucnt = nullptr; int64_t *d_uoff = nullptr; // key list kept for the lazy host mirror
+	uint8_t *d_spsc[2] = {nullptr, nullptr}; int64_t n_spsc[2] = {0, 0}; // splice scores per strand (mm_idx_spsc_read): n positions (int64, global S coordinates) | n bytes
 	int64_t *d_junc = nullptr; int64_t n_junc = 0; // annotated introns (mm_idx_bed_read): n_junc starts | n_junc ends (global S coordinates, int64) | n_junc strands (int8)
 	// host (lazy)
 	std::mutex mu;

@@ -53,6 +53,8 @@ struct KswArgs {
 	const long long *jst, *jen; // annotated introns sorted by jst, [jst,jen) in target coordinates (mm_idx_bed_junc, index.c:802-826); spliced variant
 	const int8_t *jstrand;
 	int n_junc;            // 0: no annotation
+	const long long *sps_pos[2]; const uint8_t *sps_val[2]; int n_sps[2]; // splice scores per strand (mm_idx_spsc_get, index.c:1055-1075)
+	int8_t junc_pen;
 	int8_t junc_bonus;
 	uint8_t *gws;          // per-worker DP state in HBM for targets that do not fit shared memory (null: shared memory)
 	size_t gws_stride;
@@ -260,7 +262,24 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 		gsync<G>();
 		if (SP) { // donor / acceptor arrays (ksw2_exts2_sse.c:111-190) + annotated junctions (:220-241)
 			const bool fo = (flag & MMB_KSW_SPLICE_FOR) != 0, re = (flag & MMB_KSW_SPLICE_REV) != 0, rc = (flag & MMB_KSW_REV_CIGAR) != 0;
-			const bool with_junc = A.n_junc > 0 && (fo || re);
+			const bool with_score = (flag & MMB_KSW_SPLICE_SCORE) != 0; // junc[] carries per-site scores (ksw2_exts2_sse.c:213-219)
+			const bool with_junc = !with_score && A.n_junc > 0 && (fo || re);
+			if (with_score) {
+				// junc[] = mm_idx_spsc_get over the job's window on the strand SPLICE_REV selects (align.c:638-640): 0xff, or the
+				// score byte of the positions strictly inside the window; staged in s[] and cleared again below
+				for (int i = g * 4; i < tlen16; i += G * 4) *(uint32_t*)(s + i) = 0xffffffffu;
+				gsync<G>();
+				const int sd = re? 1 : 0;
+				const long long wlo = jb.t_step > 0? jb.t_start : jb.t_start - (tlen - 1), whi = wlo + tlen;
+				int lo = 0, hi = A.n_sps[sd];
+				while (hi > lo) { const int mid = lo + ((hi - lo) >> 1); if (A.sps_pos[sd][mid] > wlo) hi = mid; else lo = mid + 1; }
+				for (int k = lo + g; k < A.n_sps[sd]; k += G) {
+					const long long pos = A.sps_pos[sd][k];
+					if (pos >= whi) break;
+					s[jb.t_step > 0? pos - jb.t_start : jb.t_start - pos] = A.sps_val[sd][k];
+				}
+				gsync<G>();
+			}
 			if (with_junc) {
 				// junc[] of this call = mm_idx_bed_junc over the job's target window, reversed with the target for a reversed job
 				// (align.c:787-790): flags of the introns lying entirely inside the window, OR-ed into s[] (all zero here) and
@@ -318,10 +337,15 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 						if (ja & am) a = (int8_t)(a + A.junc_bonus);
 					}
 				}
+				if (with_score && i < tlen - 1) { // :213-219
+					const int donor_val = fo == !rc? 0 : 1, jv = s[i + 1];
+					d = (int8_t)(d + (jv == 0xff || (jv & 1) != donor_val? -A.junc_pen : (int8_t)(jv >> 1) - (int8_t)64));
+					a = (int8_t)(a + (jv == 0xff || (jv & 1) != !donor_val? -A.junc_pen : (int8_t)(jv >> 1) - (int8_t)64));
+				}
 				y2[i] = (uint8_t)d, acc[i] = (uint8_t)a;
 			}
 			gsync<G>();
-			if (with_junc) {
+			if (with_junc || with_score) {
 				for (int i = g * 4; i < tlen16; i += G * 4) *(uint32_t*)(s + i) = 0;
 				gsync<G>();
 			}
@@ -697,7 +721,8 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		static const int sp0[4] = { 8, 15, 21, 30 };
 		for (int t = 0; t < 4; ++t) A.sp[t] = cmplx? (int8_t)((double)sp0[t] / 3. + .499) : (int8_t)(t == 0? (flank? sc->noncan / 2 : 0) : sc->noncan);
 		A.jst = (const long long*)ctx->junc_st, A.jen = (const long long*)ctx->junc_en, A.jstrand = ctx->junc_strand;
-		A.n_junc = (int)ctx->n_junc, A.junc_bonus = sc->junc_bonus;
+		A.n_junc = (int)ctx->n_junc, A.junc_bonus = sc->junc_bonus, A.junc_pen = sc->junc_pen;
+		for (int t = 0; t < 2; ++t) A.sps_pos[t] = (const long long*)ctx->spsc_pos[t], A.sps_val[t] = ctx->spsc_val[t], A.n_sps[t] = (int)ctx->n_spsc[t];
 	}
 
 	// tiers: {max len16, group size, workers per CTA}; the last tier keeps the DP state in HBM instead of shared memory

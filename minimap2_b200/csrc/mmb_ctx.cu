@@ -46,13 +46,30 @@ extern "C" void mmb_ctx_destroy(mmb_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->d_a.release(); c->d_b.release(); c->d_c.release(); c->d_d.release();
-	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release(); c->d_junc.release();
+	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release(); c->d_junc.release(); c->d_spsc[0].release(); c->d_spsc[1].release();
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
 	delete c;
 }
 
 extern "C" void *mmb_ctx_stream(mmb_ctx_t *c) { return (void*)c->stream; }
+
+// Splice scores for MMB_JOB_SPLICE jobs carrying MMB_KSW_SPLICE_SCORE (host arrays; pos strictly ascending, in the coordinates of
+// the target array; val = (score+64)<<1 | acceptor). strand 0: jobs without MMB_KSW_SPLICE_REV, 1: with. n = 0 clears the table.
+extern "C" int mmb_ctx_set_splice_scores(mmb_ctx_t *c, int strand, int64_t n, const int64_t *pos, const uint8_t *val)
+{
+	if (strand < 0 || strand > 1) return -1;
+	MMB_CUDA_CHECK(cudaSetDevice(c->device));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+	c->spsc_pos[strand] = nullptr, c->spsc_val[strand] = nullptr, c->n_spsc[strand] = 0;
+	if (n <= 0) return 0;
+	for (int64_t i = 1; i < n; ++i) if (pos[i] <= pos[i - 1]) return -1;
+	uint8_t *d = (uint8_t*)c->d_spsc[strand].reserve((size_t)n * 9 + 64);
+	MMB_CUDA_CHECK(cudaMemcpy(d, pos, (size_t)n * 8, cudaMemcpyHostToDevice));
+	MMB_CUDA_CHECK(cudaMemcpy(d + (size_t)n * 8, val, (size_t)n, cudaMemcpyHostToDevice));
+	c->spsc_pos[strand] = (const int64_t*)d, c->spsc_val[strand] = d + (size_t)n * 8, c->n_spsc[strand] = n;
+	return 0;
+}
 
 // Annotated introns for MMB_JOB_SPLICE jobs of the kernel-level entry points (host arrays, sorted by st; coordinates index the
 // target array passed to mmb_ksw_batch_host). n = 0 removes the annotation.

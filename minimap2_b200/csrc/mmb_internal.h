@@ -74,6 +74,10 @@ struct mmb_ctx_s {
 	// of the target array the jobs address: first base, one past the last base, strand (+1/-1). Null: no annotation.
 	const int64_t *junc_st = nullptr, *junc_en = nullptr; const int8_t *junc_strand = nullptr; int64_t n_junc = 0;
 	DevBuf d_junc;                            // backing store when set through mmb_ctx_set_junctions
+	// splice scores (mm_idx_spsc_get semantics, index.c:1055-1075), one table per strand [0: '+', 1: '-']: positions (sorted, one
+	// entry per position: the largest byte) in target coordinates and their bytes (score+64)<<1 | acceptor
+	const int64_t *spsc_pos[2] = {nullptr, nullptr}; const uint8_t *spsc_val[2] = {nullptr, nullptr}; int64_t n_spsc[2] = {0, 0};
+	DevBuf d_spsc[2];
 };
 
 // Timing of one kernel family on the ctx stream with CUDA events (only when profiling is enabled). Asynchronous: the event

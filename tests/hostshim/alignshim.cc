@@ -51,13 +51,14 @@ static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t 
 	memset(&ez, 0, sizeof(ez));
 	if (j.flag & MMB_JOB_SPLICE) { // ksw_exts2 as mm_align_pair calls it (align.c:352-355), junc[] as mm_get_junc fills it (align.c:638-643,787-790)
 		std::vector<uint8_t> junc;
-		if (mi->I && j.tlen > 0) {
+		if ((mi->I || mi->spsc) && j.tlen > 0) { // mm_get_junc (align.c:638-643): splice scores take precedence over the BED annotation
 			const int64_t lo = j.t_step > 0? j.t_start : j.t_start - (j.tlen - 1);
 			int32_t rid = 0;
 			while (rid + 1 < (int32_t)mi->n_seq && (int64_t)mi->seq[rid + 1].offset <= lo) ++rid;
 			const int32_t st = (int32_t)(lo - (int64_t)mi->seq[rid].offset);
 			junc.resize(j.tlen);
-			mmx_bed_junc((const mm_idx_intv_s*)mi->I, (int32_t)mi->n_seq, rid, st, st + j.tlen, junc.data());
+			if (mi->spsc) mmx_spsc_get((const mm_idx_spsc_s*)mi->spsc, (int32_t)mi->n_seq, rid, mi->seq[rid].len, st, st + j.tlen, !!(j.flag & MMB_KSW_SPLICE_REV), junc.data());
+			else mmx_bed_junc((const mm_idx_intv_s*)mi->I, (int32_t)mi->n_seq, rid, st, st + j.tlen, junc.data());
 			if (j.t_step < 0) std::reverse(junc.begin(), junc.end());
 		}
 		mm2o_exts2(j.qlen, q.data(), j.tlen, t.data(), 5, mat, opt->q, opt->e, opt->q2, opt->noncan, j.zdrop, j.end_bonus, opt->junc_bonus, opt->junc_pen,
@@ -170,4 +171,16 @@ int hs_bed_n(const void *I, int ctg) { return ((const mm_idx_intv_s*)I)[ctg].n; 
 void hs_bed_get(const void *I, int ctg, int k, int32_t *out) { const mm_idx_intv1_t &t = ((const mm_idx_intv_s*)I)[ctg].a[k]; out[0] = t.st, out[1] = t.en, out[2] = t.cnt, out[3] = t.strand; }
 int hs_bed_junc(const void *I, int n_seq, int ctg, int st, int en, uint8_t *s) { return mmx_bed_junc((const mm_idx_intv_s*)I, n_seq, ctg, st, en, s); }
 void hs_bed_free(void *I, int n_seq) { for (int i = 0; i < n_seq; ++i) free(((mm_idx_intv_s*)I)[i].a); free(I); }
+void *hs_spsc_read(const mm_idx_t *mi, const char *fn, int max_sc, float scale)
+{
+	std::unordered_map<std::string, int> ids;
+	for (uint32_t i = 0; i < mi->n_seq; ++i) ids[mi->seq[i].name] = (int)i;
+	return mmx_spsc_read(fn, mi->n_seq, max_sc, scale, [&](const char *name) { auto it = ids.find(name); return it == ids.end()? -1 : it->second; },
+						 [&](int cid) { return mi->seq[cid].len; }, nullptr);
+}
+int64_t hs_spsc_get(const void *S, const mm_idx_t *mi, int cid, int64_t st, int64_t en, int rev, uint8_t *sc)
+{
+	return mmx_spsc_get((const mm_idx_spsc_s*)S, (int32_t)mi->n_seq, cid, mi->seq[cid].len, st, en, rev, sc);
+}
+void hs_spsc_free(void *S, int n_seq) { for (int i = 0; i < n_seq * 2; ++i) free(((mm_idx_spsc_s*)S)[i].a); free(S); }
 }

@@ -92,10 +92,13 @@ def compare_formats(H, R, api, mi, qname, qstr, n, pm, pr, rep_len, flag):
         assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, ref_line[:300], buf.raw[:min(ln, 300)])
 
 
-def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0, k=15, tweak=None, bed=None):
+def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0, k=15, tweak=None, bed=None, spsc=None):
     mi, keep = build_ref_index(R, contigs, names, w=w, k=k)
     if bed:  # junction annotation (main.c:467-471): both drivers read it from mi->I
         R.mm_idx_bed_read(mi, bed.encode(), 1)
+    if spsc:  # splice scores (main.c:482-486): mi->spsc, max bonus as main.c computes it for the splice preset (q2=32, q=2)
+        R.mm_idx_spsc_read2.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_float]
+        R.mm_idx_spsc_read2(mi, spsc.encode(), 30, 0.7)
     io, mo = api.IdxOpt(), api.MapOpt()
     R.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
     R.mm_set_opt(None, C.byref(io), C.byref(mo)); R.mm_set_opt(preset.encode(), C.byref(io), C.byref(mo))
@@ -299,6 +302,58 @@ def test_driver_with_junction_annotation(libs, tmp_path):
     g, reads, introns = _spliced_set(60, 36)
     bed = str(tmp_path / "anno.bed"); _write_bed(bed, introns, rng)
     n, _ = run_case(H, R, api, [g], ["chr0"], reads, preset="splice", w=5, is_cdna=1, bed=bed)
+    assert n >= 30
+
+
+def _write_spsc(path, g, introns, rng):
+    """splice-score lines (contig, position, strand, D/A, score) at the true sites, at decoys and at random places, with duplicates"""
+    lines = []
+    for st, en, sd in introns:
+        s_ = "+" if sd > 0 else "-"
+        d_pos, a_pos = (st, en - 1) if sd > 0 else (en - 1, st)  # first/last intron base in transcript order
+        lines.append("chr0\t%d\t%s\tD\t%d" % (d_pos, s_, int(rng.integers(3, 14))))
+        lines.append("chr0\t%d\t%s\tA\t%d" % (a_pos, s_, int(rng.integers(3, 14))))
+        if rng.random() < 0.3:
+            lines.append("chr0\t%d\t%s\tD\t%d" % (d_pos, s_, int(rng.integers(-8, 20))))
+    for _ in range(len(introns) * 4):
+        lines.append("chr0\t%d\t%s\t%s\t%d" % (int(rng.integers(0, len(g))), "+-"[int(rng.integers(0, 2))], "DA"[int(rng.integers(0, 2))], int(rng.integers(-12, 12))))
+    lines += ["chr0\t0\t+\tD\t5", "chrUn\t50\t+\tD\t5", "chr0\t77\t+\tX\t5", "chr0\t88\t+"]
+    order = rng.permutation(len(lines))
+    open(path, "w").write("".join(lines[i] + "\n" for i in order))
+
+
+def test_splice_score_reader_matches_reference(libs, tmp_path):
+    """mm_idx_spsc_read2 / mm_idx_spsc_get (index.c:963-1075) restated in csrc/annot.h vs the reference library on random windows"""
+    H, R, api = libs
+    rng = np.random.default_rng(4)
+    g, reads, introns = _spliced_set(50, 40)
+    fn = str(tmp_path / "sc.txt"); _write_spsc(fn, g, introns, rng)
+    mi, keep = build_ref_index(R, [g], ["chr0"], w=5)
+    R.mm_idx_spsc_read2.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_float]
+    R.mm_idx_spsc_get.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    R.mm_idx_spsc_get.restype = C.c_int64
+    H.hs_spsc_read.restype = C.c_void_p; H.hs_spsc_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_float]
+    H.hs_spsc_get.restype = C.c_int64; H.hs_spsc_get.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_void_p]
+    for scale in (0.7, 1.0):
+        R.mm_idx_spsc_read2(mi, fn.encode(), 30, scale)
+        S = H.hs_spsc_read(mi, fn.encode(), 30, scale)
+        for _ in range(300):
+            st = int(rng.integers(0, len(g) - 10)); en = min(len(g), st + int(rng.integers(1, 20000))); rev = int(rng.integers(0, 2))
+            a = np.zeros(en - st, dtype=np.uint8); b = np.zeros(en - st, dtype=np.uint8)
+            ra = R.mm_idx_spsc_get(mi, 0, st, en, rev, a.ctypes.data_as(C.c_void_p))
+            rb = H.hs_spsc_get(S, mi, 0, st, en, rev, b.ctypes.data_as(C.c_void_p))
+            assert ra == rb and np.array_equal(a, b), (st, en, rev)
+        H.hs_spsc_free(C.c_void_p(S), 1)
+
+
+def test_driver_with_splice_scores(libs, tmp_path):
+    """-x splice --spsc: KSW_EZ_SPLICE_SCORE on every spliced call (align.c:688) and junc[] bytes from mm_idx_spsc_get on the strand
+    SPLICE_REV selects (align.c:638-640), reversed for the left extension"""
+    H, R, api = libs
+    rng = np.random.default_rng(6)
+    g, reads, introns = _spliced_set(61, 36)
+    fn = str(tmp_path / "sc.txt"); _write_spsc(fn, g, introns, rng)
+    n, _ = run_case(H, R, api, [g], ["chr0"], reads, preset="splice", w=5, is_cdna=1, spsc=fn)
     assert n >= 30
 
 

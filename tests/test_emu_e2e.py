@@ -36,7 +36,7 @@ HAVE_REF = os.path.exists(O.REF_BIN)
 GOLDEN = ["inv_paf_cigar", "x3s_paf_cigar", "t2_paf_cigar"]  # MT-human/MT-orang goes through the .mmi test below
 
 
-def _splice_inputs(d, junc=False):
+def _splice_inputs(d, junc=False, spsc=False):
     """two cDNA reads, one per transcript strand; junc: no canonical signals in the genome, the introns come from a BED file instead"""
     import numpy as np
     import synth
@@ -51,16 +51,25 @@ def _splice_inputs(d, junc=False):
         for k in range(3):
             el = int(rng.integers(90, 200)); exons.append((pos, pos + el)); il = int(rng.integers(150, 500))
             d_, a_ = (b"GT", b"AG") if not rev else (b"CT", b"AC")
-            if not junc:
+            if not junc and not spsc:
                 g[pos + el:pos + el + 2] = list(d_); g[pos + el + il - 2:pos + el + il] = list(a_)
             if k < 2:
                 introns.append((pos + el, pos + el + il, "-" if rev else "+"))
             pos += el + il
         tr = np.concatenate([g[s:e] for s, e in exons])
         reads.append(synth.mutate_ascii(comp[tr[::-1]] if rev else tr, rng, 0.03))
-    tag = "spj" if junc else "sp"
+    tag = "spj" if junc else "sps" if spsc else "sp"
     rf, qf = os.path.join(d, tag + "_ref.fa"), os.path.join(d, tag + "_reads.fa")
     synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["tr0", "tr1"], reads)
+    if spsc:  # splice-score file: contig, position, strand, D/A, score -- the true sites plus noise on both strands
+        fn = os.path.join(d, "sps.txt")
+        with open(fn, "w") as f:
+            for st, en, sd in introns:
+                dp, ap = (st, en - 1) if sd == "+" else (en - 1, st)
+                f.write("chr0\t%d\t%s\tD\t%d\nchr0\t%d\t%s\tA\t%d\n" % (dp, sd, int(rng.integers(5, 15)), ap, sd, int(rng.integers(5, 15))))
+            for _ in range(400):
+                f.write("chr0\t%d\t%s\t%s\t%d\n" % (int(rng.integers(1, len(g) - 1)), "+-"[int(rng.integers(0, 2))], "DA"[int(rng.integers(0, 2))], int(rng.integers(-10, 8))))
+        return ["-x", "splice", "-c", "--cs", "--spsc", fn, rf, qf]
     if junc:
         bed = os.path.join(d, "spj.bed")
         open(bed, "w").write("".join("chr0\t%d\t%d\tj%d\t0\t%s\n" % (st, en, i, sd) for i, (st, en, sd) in enumerate(introns)))
@@ -191,6 +200,7 @@ def emu_runs(emu_cli, tmp_path_factory):
     if HAVE_REF:
         jobs["splice"] = (_splice_inputs(d), d, True)
         jobs["splice_junc"] = (_splice_inputs(d, junc=True), d, True)
+        jobs["splice_spsc"] = (_splice_inputs(d, spsc=True), d, True)
         jobs["high_occ"] = (_high_occ_inputs(d), d, True)
         jobs["asm5"] = (_asm_inputs(d, "asm5", 0.004), d, True)
         jobs["asm20"] = (_asm_inputs(d, "asm20", 0.03), d, True)
@@ -208,7 +218,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         p = subprocess.run([emu_cli, "-t", "4"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=env)
         return name, dict(rc=p.returncode, err=p.stderr.decode()[-2000:], out=p.stdout.decode().splitlines(), ref=ref)
 
-    order = sorted(jobs.items(), key=lambda kv: {"splice": 0, "splice_junc": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
+    order = sorted(jobs.items(), key=lambda kv: {"splice": 0, "splice_junc": 0, "splice_spsc": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
     with ThreadPoolExecutor(4) as ex:
         return dict(ex.map(one, order))
 
@@ -236,6 +246,15 @@ def test_emulated_junction_annotation_matches_reference(emu_runs):
     """-x splice --junc-bed: mm_idx_bed_read on the index, the intron table on the device, junction flags derived per ksw_exts2 job
     in the kernel (mm_idx_bed_junc's window rule), for a genome without canonical splice signals"""
     r = emu_runs["splice_junc"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) == 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_splice_scores_match_reference(emu_runs):
+    """-x splice --spsc: mm_idx_spsc_read2 on the index, per-strand score tables on the device, junc[] bytes assembled per ksw_exts2
+    job in the kernel (mm_idx_spsc_get's window rule), KSW_EZ_SPLICE_SCORE on every spliced call"""
+    r = emu_runs["splice_spsc"]
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"] and len(r["ref"]) == 2
 

@@ -139,7 +139,7 @@ def small_spliced_pair(rng, n_exon, err, introns_out=None):
     return (q if len(q) else np.array([0], dtype=np.uint8)), np.concatenate(parts)
 
 
-def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False):
+def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False, with_score=False):
     L, ctx, KswJob, KswRes, KswScore = emu
     SPF, SPR, JOB_SPLICE = 0x100, 0x200, 0x80000
     mat = O.simple_mat(1, 2, 1)
@@ -156,10 +156,35 @@ def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False):
         qcat = np.concatenate([p[0] for p in pairs]); tcat = np.concatenate([p[1] for p in pairs])
         jobs = (KswJob * n)(); qo = to = tot = 0
         introns, juncs = [], [None] * n
+        score_tabs = [{}, {}]
         for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
             j = jobs[i]
             j.q_start, j.t_start, j.q_step, j.t_step, j.qlen, j.tlen = qo, to, 1, 1, len(qq), len(tt)
             j.w, j.zdrop, j.end_bonus, j.flag = pr["w"], pr["zdrop"], pr["end_bonus"], pr["flag"]
+            if with_score:
+                # splice-score tables per strand in the coordinates of the concatenated target (mmb_ctx_set_splice_scores): scores at the
+                # true intron ends, at shifted decoys and at random places; a job sees the entries strictly inside its window
+                lt = len(tt); sd = 1 if pr["flag"] & SPR else 0
+                j.flag = pr["flag"] = pr["flag"] | 0x1000
+                for tab in (0, 1):
+                    cand = {}
+                    for st, en in true_introns[i]:
+                        for pos_, typ in ((st, 0), (en - 1, 1)) if rng.random() < 0.5 else ((en - 1, 0), (st, 1)):
+                            cand[to + pos_ + int(rng.choice([0, 0, 0, 1, -2]))] = (int(rng.integers(60, 80)) << 1) | typ
+                    for _ in range(max(1, lt // 25)):
+                        cand[to + int(rng.integers(0, lt))] = (int(rng.integers(50, 78)) << 1) | int(rng.integers(0, 2))
+                    cand[to] = (70 << 1) | 1  # on the window edge: not strictly inside, must be ignored
+                    for pos_, v in cand.items():
+                        if to <= pos_ < to + lt:
+                            score_tabs[tab][pos_] = v
+                flags = np.full(lt, 0xff, dtype=np.uint8)
+                for pos_, v in score_tabs[sd].items():
+                    if to < pos_ < to + lt:
+                        flags[pos_ - to] = v
+                if i % 2:
+                    j.t_start, j.t_step = to + lt - 1, -1
+                    pairs[i] = (qq, tt[::-1].copy()); flags = flags[::-1].copy()
+                juncs[i] = flags
             if with_junc:
                 # annotated introns in the coordinates of the concatenated target: inside this job's window, or sticking out of it
                 # (those must be ignored, index.c:816); every other job reads its target backwards (t_step = -1, reversed junc[])
@@ -184,6 +209,10 @@ def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False):
             introns.sort(key=lambda x: x[0])
             st = np.array([x[0] for x in introns], dtype=np.int64); en = np.array([x[1] for x in introns], dtype=np.int64); sd = np.array([x[2] for x in introns], dtype=np.int8)
             assert L.mmb_ctx_set_junctions(ctx, C.c_int64(len(introns)), st.ctypes.data_as(C.c_void_p), en.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p)) == 0
+        if with_score:
+            for tab in (0, 1):
+                ps = np.array(sorted(score_tabs[tab]), dtype=np.int64); vs = np.array([score_tabs[tab][x] for x in ps], dtype=np.uint8)
+                assert L.mmb_ctx_set_splice_scores(ctx, tab, C.c_int64(len(ps)), ps.ctypes.data_as(C.c_void_p), vs.ctypes.data_as(C.c_void_p)) == 0
         sc = KswScore()
         for i in range(25):
             sc.mat[i] = int(mat[i])
@@ -193,16 +222,19 @@ def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False):
         assert used >= 0
         if with_junc:
             L.mmb_ctx_set_junctions(ctx, C.c_int64(0), None, None, None)
+        if with_score:
+            for tab in (0, 1):
+                L.mmb_ctx_set_splice_scores(ctx, tab, C.c_int64(0), None, None)
         n_changed = 0
         for i, ((qq, tt), pr) in enumerate(zip(pairs, params)):
             r = res[i]
             g = dict(max=r.max, zdropped=r.zdropped, max_q=r.max_q, max_t=r.max_t, mqe=r.mqe, mqe_t=r.mqe_t, mte=r.mte, mte_q=r.mte_q, score=r.score,
                      n_cigar=r.n_cigar, reach_end=r.reach_end, cigar=[int(x) for x in cig[r.cigar_off:r.cigar_off + r.n_cigar]])
             exp = O.oracle_exts2(qq, tt, mat, 2, 1, 32, 9, pr["zdrop"], pr["end_bonus"], 9, 5, pr["flag"] & 0x1fff, juncs[i])
-            if with_junc:
+            if with_junc or with_score:
                 n_changed += exp != O.oracle_exts2(qq, tt, mat, 2, 1, 32, 9, pr["zdrop"], pr["end_bonus"], 9, 5, pr["flag"] & 0x1fff)
             assert g == exp, (hex(model), i, len(qq), len(tt), hex(pr["flag"]), {k: (g[k], exp[k]) for k in exp if g[k] != exp[k] and k != "cigar"}, g["cigar"][:8], exp["cigar"][:8])
-        assert not with_junc or n_changed >= 3, n_changed  # the annotation really changed some of the expected results
+        assert not (with_junc or with_score) or n_changed >= 3, n_changed  # the annotation really changed some of the expected results
 
 
 def test_emulated_splice_kernel_with_junction_annotation(emu):
@@ -210,6 +242,13 @@ def test_emulated_splice_kernel_with_junction_annotation(emu):
     sorted intron table (mmb_ctx_set_junctions) with mm_idx_bed_junc's window rule, for forward and reversed targets"""
     FLANK, CMPLX = 0x400, 0x800
     check_splice_jobs(emu, np.random.default_rng(78), (FLANK | CMPLX, 0), 24, 3, with_junc=True)
+
+
+def test_emulated_splice_kernel_with_splice_scores(emu):
+    """the splice-score branch of ksw_exts2_sse (:213-219): junc[] bytes assembled on the device from per-strand position tables
+    (mmb_ctx_set_splice_scores) with mm_idx_spsc_get's window rule, forward and reversed targets"""
+    FLANK, CMPLX = 0x400, 0x800
+    check_splice_jobs(emu, np.random.default_rng(79), (FLANK | CMPLX, 0), 24, 3, with_score=True)
 
 
 def test_emulated_splice_kernel_matches_oracle(emu):

@@ -102,3 +102,30 @@ def test_second_occurrence_cutoff(tmp_path, extra):
     synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
     synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
     compare(["-c"] + extra + [rf, qf])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_splice_scores_vs_reference(tmp_path):
+    """-x splice --spsc (mm_idx_spsc_read2 / mm_idx_spsc_get, index.c:963-1075; KSW_EZ_SPLICE_SCORE, align.c:688)"""
+    from test_aligndriver_vs_ref import _spliced_set, _write_spsc
+    rng = np.random.default_rng(16)
+    g, reads, introns = _spliced_set(71, 150, glen=800_000)
+    rf, qf, fn = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa"), str(tmp_path / "sc.txt")
+    synth.write_fasta(rf, ["chr0"], [g]); synth.write_fasta(qf, ["tr%d" % i for i in range(len(reads))], reads)
+    _write_spsc(fn, g, introns, rng)
+    assert compare(["-x", "splice", "-c", "--cs", "--spsc", fn, rf, qf]) >= 120
+    compare(["-x", "splice", "--spsc", fn, "--spsc-scale", "1", "--spsc0", "3", "-a", rf, qf], sam=True)
+
+
+def test_splice_kernel_with_score_tables_matches_oracle():
+    """tests/test_emu_ksw.py::test_emulated_splice_kernel_with_splice_scores on the device, 200 jobs per model"""
+    import ctypes as C
+    import minimap2_b200 as mb
+    from minimap2_b200._lib import KswJob, KswRes, KswScore, lib
+    import test_emu_ksw as E
+    L = lib()
+    L.mmb_ctx_set_splice_scores.restype = C.c_int
+    L.mmb_ctx_set_splice_scores.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+    ctx = mb.Context(0)
+    E.check_splice_jobs((L, C.c_void_p(ctx.h), KswJob, KswRes, KswScore), np.random.default_rng(181), (0x400 | 0x800, 0x400, 0), 200, 5, with_score=True)
+    ctx.close()

@@ -225,10 +225,14 @@ __global__ void __launch_bounds__(128) chain_fill_kernel(ChainArgs A)
 	}
 }
 
-// mg_chain_backtrack + compact_a (lchain.c:27-111), one WARP per read: collecting the candidate ends (f >= min_sc), clearing t[] and
-// every bulk copy of compact_a are done by all lanes with coalesced accesses; the two unstable sorts and the peeling of chains
-// (a pointer chase through p[] whose order is part of the contract) stay sequential on lane 0.
-__global__ void __launch_bounds__(128) chain_bt_kernel(ChainArgs A)
+// Backtrack + compaction (mg_chain_backtrack lchain.c:27-76, compact_a :78-111) in three launches, each shaped after its part:
+//   chain_bt_collect_kernel  warp per read   candidate chain ends (f >= min_sc) gathered in anchor order with ballots, t[] cleared:
+//                                            coalesced streaming over the read's anchors
+//   chain_bt_peel_kernel     thread per read the unstable sort of the candidates (exact tie order) and the best-first peeling are
+//                                            chains of dependent loads; one thread per read keeps every read of the batch in flight
+//                                            at once, which is what hides that latency
+//   chain_bt_compact_kernel  warp per read   chains copied into b[] and, ordered by first target position, into a_out by all lanes
+__global__ void __launch_bounds__(128) chain_bt_collect_kernel(ChainArgs A)
 {
 	const int lane = threadIdx.x & 31;
 	const int rd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -236,17 +240,11 @@ __global__ void __launch_bounds__(128) chain_bt_kernel(ChainArgs A)
 	const unsigned full = 0xffffffffu;
 	const int64_t off = A.a_off[rd];
 	const int32_t n = (int32_t)(A.a_off[rd + 1] - off);
-	if (lane == 0) A.n_u[rd] = 0, A.n_v[rd] = 0;
-	if (n <= 0) return;
-	const mmb_chain_par_t &P = A.par;
-	const int32_t max_drop = P.is_cdna? INT32_MAX : P.bw, min_sc = P.min_sc, min_cnt = P.min_cnt;
-	const m128 *a = A.a + off;
-	const int32_t *f = A.f + off, *p = A.p + off;
-	int32_t *v = A.v + off, *t = A.t + off, *stk = A.stk + A.stk_off[rd];
-	m128 *z = A.z + off, *b = A.b + off, *ao = A.a_out + off;
-	uint64_t *u = A.u + off;
-	// candidate chain ends in anchor order (lchain.c:35-37), t[] cleared on the way
-	int32_t n_z = 0;
+	const int32_t min_sc = A.par.min_sc;
+	const int32_t *f = A.f + off;
+	int32_t *t = A.t + off;
+	m128 *z = A.z + off;
+	int32_t n_z = 0; // candidate chain ends in anchor order (lchain.c:35-37), t[] cleared on the way
 	for (int32_t i0 = 0; i0 < n; i0 += 32) {
 		const int32_t i = i0 + lane;
 		const int32_t fi = i < n? f[i] : INT32_MIN;
@@ -256,26 +254,51 @@ __global__ void __launch_bounds__(128) chain_bt_kernel(ChainArgs A)
 		n_z += __popc(m);
 		if (i < n) t[i] = 0;
 	}
-	__syncwarp();
-	if (n_z == 0) return;
+	if (lane == 0) A.n_u[rd] = n_z, A.n_v[rd] = 0; // n_u carries the candidate count to the next launch
+}
+
+__global__ void __launch_bounds__(128) chain_bt_peel_kernel(ChainArgs A)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= A.n_reads) return;
+	const int32_t n_z = A.n_u[rd];
+	if (n_z == 0) return; // n_u = n_v = 0 already
+	const int64_t off = A.a_off[rd];
+	const mmb_chain_par_t &P = A.par;
+	const int32_t max_drop = P.is_cdna? INT32_MAX : P.bw, min_sc = P.min_sc, min_cnt = P.min_cnt;
+	const int32_t *f = A.f + off, *p = A.p + off;
+	int32_t *v = A.v + off, *t = A.t + off, *stk = A.stk + A.stk_off[rd];
+	m128 *z = A.z + off;
+	uint64_t *u = A.u + off;
 	int32_t n_u = 0, n_v = 0;
-	if (lane == 0) { // lchain.c:38-66: best end first; one filling pass suffices (v[] and u[] have capacity n)
-		mmx_rs_sort(z, (int64_t)n_z, stk, KeyX128());
-		for (int32_t k = n_z - 1; k >= 0; --k) {
-			if (t[z[k].y] == 0) {
-				const int32_t n_v0 = n_v, end_i = bk_end(max_drop, z, f, p, t, k);
-				int32_t i, sc;
-				for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
-				sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
-				if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
-				else n_v = n_v0;
-			}
+	// lchain.c:38-66: best end first; one filling pass suffices (v[] and u[] have capacity n)
+	mmx_rs_sort(z, (int64_t)n_z, stk, KeyX128());
+	for (int32_t k = n_z - 1; k >= 0; --k) {
+		if (t[z[k].y] == 0) {
+			const int32_t n_v0 = n_v, end_i = bk_end(max_drop, z, f, p, t, k);
+			int32_t i, sc;
+			for (i = (int32_t)z[k].y; i != end_i; i = p[i]) v[n_v++] = i, t[i] = 1;
+			sc = i < 0? (int32_t)z[k].x : (int32_t)z[k].x - f[i];
+			if (sc >= min_sc && n_v > n_v0 && n_v - n_v0 >= min_cnt) u[n_u++] = (uint64_t)sc << 32 | (uint64_t)(n_v - n_v0);
+			else n_v = n_v0;
 		}
-		A.n_u[rd] = n_u, A.n_v[rd] = n_v;
 	}
-	n_u = __shfl_sync(full, n_u, 0), n_v = __shfl_sync(full, n_v, 0);
-	__syncwarp();
+	A.n_u[rd] = n_u, A.n_v[rd] = n_v;
+}
+
+__global__ void __launch_bounds__(128) chain_bt_compact_kernel(ChainArgs A)
+{
+	const int lane = threadIdx.x & 31;
+	const int rd = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (rd >= A.n_reads) return;
+	const int32_t n_u = A.n_u[rd];
 	if (n_u == 0) return;
+	const int64_t off = A.a_off[rd];
+	const m128 *a = A.a + off;
+	const int32_t *v = A.v + off;
+	int32_t *stk = A.stk + A.stk_off[rd];
+	m128 *z = A.z + off, *b = A.b + off, *ao = A.a_out + off;
+	uint64_t *u = A.u + off;
 	// compact_a (lchain.c:78-111): chains laid out in b[] with their anchors in ascending order, then ordered by first target position
 	m128 *w = z; // z is free now; n_u <= n_z
 	int32_t k = 0;
@@ -452,9 +475,11 @@ void mmb_chain_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, c
 	chain_scratch_setup(ctx, A, n_reads, d_a, d_a_off, n_tot, d_n_u, d_n_v, d_u, d_a_out, scratch, scratch2);
 	ProfScope prof(ctx, MMB_PROF_CHAIN, (uint64_t)n_tot);
 	chain_fill_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
-	chain_bt_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
+	chain_bt_collect_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
+	chain_bt_peel_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(A);
+	chain_bt_compact_kernel<<<(unsigned)(((int64_t)n_reads * 32 + 127) / 128), 128, 0, ctx->stream>>>(A);
 	MMB_CUDA_CHECK(cudaGetLastError());
-	ctx->n_launch += 2;
+	ctx->n_launch += 4;
 }
 
 extern "C" int mmb_chain_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_reads, const uint64_t *anchors_xy, const int64_t *a_off,

@@ -56,6 +56,7 @@ uint64_t mmb_profile_units(mmb_ctx_t *ctx, int which, int reset); /* algorithmic
 #define MMB_JOB_Q_COMP       0x10000 /* complement query bases (3-c, N stays 4): reverse strand (align.c:1056-1061) */
 #define MMB_JOB_LL           0x20000 /* run ksw_ll_i16 (local score) instead of extd2 */
 #define MMB_JOB_SPLICE       0x80000 /* the job is a ksw_exts2 call (align.c:352-355): q/e = gap open/extend, q2 = intron open, MMB_KSW_SPLICE_* select the model */
+#define MMB_JOB_T_COMP       0x100000 /* the target is read complemented (query-strand mode, mm_idx_getseq_rev index.c:176-190: with t_step = -1 the job sees the reverse complement) */
 #define MMB_JOB_ZDROP        0x40000 /* also run mm_test_zdrop's scan over the resulting CIGAR (align.c:61-89); see zd_* below */
 
 typedef struct {

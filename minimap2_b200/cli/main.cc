@@ -35,7 +35,7 @@ static struct option long_options[] = {
 	{ "bucket-bits", required_argument, 0, 300 }, { "mb-size", required_argument, 0, 'K' }, { "seed", required_argument, 0, 302 },
 	{ "no-self", no_argument, 0, 'D' }, { "max-chain-skip", required_argument, 0, 307 }, { "min-dp-len", required_argument, 0, 308 },
 	{ "splice", no_argument, 0, 310 }, { "no-long-join", no_argument, 0, 312 }, { "secondary", required_argument, 0, 315 },
-	{ "cs", optional_argument, 0, 316 }, { "end-bonus", required_argument, 0, 317 }, { "for-only", no_argument, 0, 322 },
+	{ "cs", optional_argument, 0, 316 }, { "end-bonus", required_argument, 0, 317 }, { "for-only", no_argument, 0, 322 }, { "qstrand", no_argument, 0, 348 },
 	{ "rev-only", no_argument, 0, 323 }, { "all-chain", no_argument, 0, 'P' }, { "dual", required_argument, 0, 326 },
 	{ "max-clip-ratio", required_argument, 0, 327 }, { "min-occ-floor", required_argument, 0, 328 }, { "MD", no_argument, 0, 329 },
 	{ "score-N", required_argument, 0, 331 }, { "eqx", no_argument, 0, 332 }, { "paf-no-hit", no_argument, 0, 333 },
@@ -123,6 +123,7 @@ int main(int argc, char *argv[])
 		else if (c == 312) opt.flag |= MM_F_NO_LJOIN;
 		else if (c == 317) opt.end_bonus = atoi(optarg);
 		else if (c == 322) opt.flag |= MM_F_FOR_ONLY;
+		else if (c == 348) opt.flag |= MM_F_QSTRAND | MM_F_NO_INV; // main.c:252
 		else if (c == 323) opt.flag |= MM_F_REV_ONLY;
 		else if (c == 327) opt.max_clip_ratio = atof(optarg);
 		else if (c == 328) opt.min_mid_occ = atoi(optarg);

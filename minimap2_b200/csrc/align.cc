@@ -34,6 +34,7 @@ inline void ez_reset(Ez *ez) // ksw2.h:164-169
 struct Seg { // a piece of the query (on strand `rev`, strand coordinates) and of the target
 	int rev, qs, qlen, q_reversed;
 	uint32_t rid; int rs, tlen, t_reversed;
+	int t_rc = 0; // query-strand mode, reverse hit: rs counts on the reverse-complement strand of the target (mm_idx_getseq_rev, index.c:176-190)
 };
 
 inline uint32_t roundup32(uint32_t x) { --x; x |= x >> 1; x |= x >> 2; x |= x >> 4; x |= x >> 8; x |= x >> 16; return ++x; }
@@ -74,9 +75,16 @@ struct Driver {
 			if (!s.q_reversed) k.q_start = ra.q_dev_off + qlen - 1 - s.qs, k.q_step = -1;
 			else k.q_start = ra.q_dev_off + qlen - s.qs - s.qlen, k.q_step = 1;
 		}
-		const int64_t toff = (int64_t)mi->seq[s.rid].offset + s.rs;
-		if (!s.t_reversed) k.t_start = toff, k.t_step = 1;
-		else k.t_start = toff + s.tlen - 1, k.t_step = -1;
+		if (!s.t_rc) {
+			const int64_t toff = (int64_t)mi->seq[s.rid].offset + s.rs;
+			if (!s.t_reversed) k.t_start = toff, k.t_step = 1;
+			else k.t_start = toff + s.tlen - 1, k.t_step = -1;
+		} else { // element i of the piece is reverse-strand position rs+i = forward position len-1-rs-i, complemented
+			const int64_t off = (int64_t)mi->seq[s.rid].offset, len = (int64_t)mi->seq[s.rid].len;
+			flag |= MMB_JOB_T_COMP;
+			if (!s.t_reversed) k.t_start = off + len - 1 - s.rs, k.t_step = -1;
+			else k.t_start = off + len - s.rs - s.tlen, k.t_step = 1;
+		}
 		k.qlen = s.qlen, k.tlen = s.tlen, k.w = w, k.zdrop = zdrop, k.end_bonus = end_bonus, k.flag = flag;
 		return k;
 	}
@@ -132,10 +140,18 @@ struct Driver {
 	}
 
 	const uint8_t *qptr(int rev, int qs) const { return ra.qseq[rev] + qs; }
-	void get_tseq(uint32_t rid, int st, int en, std::vector<uint8_t> &buf) const {
+	void get_tseq(uint32_t rid, int st, int en, std::vector<uint8_t> &buf, int t_rc = 0) const { // mm_idx_getseq2 (index.c:192-196)
 		HpScope hp_(HP_TSEQ);
 		buf.resize((en > st? en - st : 0) + 16); // 16 bytes of slack: update_extra compares 16-byte blocks
-		if (en > st) mm_idx_getseq(mi, rid, st, en, buf.data());
+		if (en <= st) return;
+		if (!t_rc) { mm_idx_getseq(mi, rid, st, en, buf.data()); return; }
+		const int len = (int)mi->seq[rid].len; // mm_idx_getseq_rev: reverse complement of [len-en, len-st)
+		if (en > len) en = len;
+		mm_idx_getseq(mi, rid, len - en, len - st, buf.data());
+		for (int i = 0, j = en - st - 1; i <= j; ++i, --j) {
+			const uint8_t x = buf[i], y = buf[j];
+			buf[i] = y < 4? 3 - y : y, buf[j] = x < 4? 3 - x : x;
+		}
 	}
 
 	static void update_max_zdrop(int32_t score, int i, int j, int32_t *max, int *max_i, int *max_j, int e, int *max_zdrop, int pos[2][2]) { // align.c:46-59
@@ -179,7 +195,7 @@ struct Driver {
 			v.rev = 1 - s.rev, v.q_reversed = 0, v.qlen = q_len;
 			// strand position of piece element 0: qlen - (s.qs' + pos11) where s.qs' is the forward-orientation start on strand s.rev
 			v.qs = qlen - s.qs - pos[1][1]; // test_zdrop is only applied to (non-reversed) gap fills
-			v.rid = s.rid, v.rs = s.rs + pos[0][0], v.tlen = t_len, v.t_reversed = 0;
+			v.rid = s.rid, v.rs = s.rs + pos[0][0], v.tlen = t_len, v.t_reversed = 0, v.t_rc = s.t_rc;
 			int sc, qo, to;
 			if (q_len <= 0 || t_len <= 0) sc = 0; // ksw_ll_i16 on an empty query/target yields 0
 			else if (!ll_i16(v, &sc, &qo, &to)) return -1;
@@ -587,6 +603,9 @@ struct Driver {
 	// splice_flag: which transcript strand(s) to assume (MM_F_SPLICE_FOR / MM_F_SPLICE_REV), as in align.c:684-689.
 	bool align1(mm_reg1_t *r, mm_reg1_t *r2, int n_a, m128 *a, int64_t splice_flag) {
 		const int32_t rid = (int32_t)(a[r->as].x << 1 >> 33), rev = (int32_t)(a[r->as].x >> 63);
+		// query-strand mode (align.c:780-783,815-818,875-878,899-901): the query stays forward, a reverse hit reads the target's other strand
+		const bool qst = (opt->flag & MM_F_QSTRAND) != 0;
+		const int qrev = qst? 0 : rev, trc = qst && rev? 1 : 0;
 		int32_t as1, cnt1, i, l, bw, bw_long, dropped = 0, rs0, re0, qs0, qe0, rs, re, qs, qe, rs1, qs1, re1, qe1;
 		const int32_t ref_len = (int32_t)mi->seq[rid].len;
 		std::vector<uint8_t> tseq;
@@ -679,7 +698,7 @@ struct Driver {
 
 		// left extension (align.c:779-799)
 		if (qs > 0 && rs > 0) {
-			Seg s; s.rev = rev, s.qs = qs0, s.qlen = qs - qs0, s.q_reversed = 1, s.rid = rid, s.rs = rs0, s.tlen = rs - rs0, s.t_reversed = 1;
+			Seg s; s.rev = qrev, s.qs = qs0, s.qlen = qs - qs0, s.q_reversed = 1, s.rid = rid, s.rs = rs0, s.tlen = rs - rs0, s.t_reversed = 1, s.t_rc = trc;
 			bool ok = align_pair(s, bw, opt->end_bonus, r->split_inv? opt->zdrop_inv : opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY | MMB_KSW_RIGHT | MMB_KSW_REV_CIGAR, &ez);
 			if (ok) {
 				if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
@@ -698,12 +717,12 @@ struct Driver {
 			if (i == cnt1 - 1 || (a[as1 + i].y & MMX_SEED_LONG_JOIN) || (qe - qs >= opt->min_ksw_len && re - rs >= opt->min_ksw_len)) {
 				int j, bw1 = bw_long, zdrop_code;
 				if (a[as1 + i].y & MMX_SEED_LONG_JOIN) bw1 = qe - qs > re - rs? qe - qs : re - rs;
-				Seg s; s.rev = rev, s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0;
+				Seg s; s.rev = qrev, s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0, s.t_rc = trc;
 				bool ok = align_pair(s, bw1, -1, opt->zdrop, sflag | MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez); // first pass
 				if (ok) { // results that are available are consumed even if an earlier call is pending: this surfaces second-pass jobs one wave earlier
-					const uint8_t *qseq = qptr(rev, qs);
+					const uint8_t *qseq = qptr(qrev, qs);
 					const bool have_zd = ez.zd_max >= 0 && !ez.zdropped;
-					if (!have_zd) get_tseq(rid, rs, re, tseq);
+					if (!have_zd) get_tseq(rid, rs, re, tseq, trc);
 					zdrop_code = test_zdrop(s, qseq, tseq.data(), ez.n_cigar, ez.cigar, have_zd? &ez : nullptr);
 					if (zdrop_code > 0) ok = align_pair(s, bw1, -1, zdrop_code == 2? opt->zdrop_inv : opt->zdrop, sflag, &ez); // second pass
 					else if (zdrop_code < 0) ok = false;
@@ -735,7 +754,7 @@ struct Driver {
 
 		// right extension (align.c:874-890)
 		if (!dropped && qe < qe0 && re < re0) {
-			Seg s; s.rev = rev, s.qs = qe, s.qlen = qe0 - qe, s.q_reversed = 0, s.rid = rid, s.rs = re, s.tlen = re0 - re, s.t_reversed = 0;
+			Seg s; s.rev = qrev, s.qs = qe, s.qlen = qe0 - qe, s.q_reversed = 0, s.rid = rid, s.rs = re, s.tlen = re0 - re, s.t_reversed = 0, s.t_rc = trc;
 			bool ok = align_pair(s, bw, opt->end_bonus, opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY, &ez);
 			if (ok) {
 				if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
@@ -750,8 +769,8 @@ struct Driver {
 		else r->qs = qlen - qe1, r->qe = qlen - qs1;
 		assert(re1 - rs1 <= re0 - rs0);
 		if (r->p) {
-			get_tseq(rid, rs1, re1, tseq);
-			update_extra(r, qptr(r->rev, qs1), tseq.data(), opt->q, opt->e, opt->flag & MM_F_EQX, 1);
+			get_tseq(rid, rs1, re1, tseq, trc);
+			update_extra(r, qptr(qst? 0 : r->rev, qs1), tseq.data(), opt->q, opt->e, opt->flag & MM_F_EQX, 1);
 			if (rev && r->p->trans_strand) r->p->trans_strand ^= 3;
 		}
 		return true;

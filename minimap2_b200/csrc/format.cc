@@ -135,12 +135,16 @@ static void write_MD_core(std::string &s, const uint8_t *tseq, const uint8_t *qs
 	if (l_MD > 0) put_int(s, l_MD);
 }
 
-static void write_cs_ds_or_MD(std::string &s, const mm_idx_t *mi, const char *seq, const mm_reg1_t *r, int no_iden, int is_MD, int is_ds, int write_tag)
+static void write_cs_ds_or_MD(std::string &s, const mm_idx_t *mi, const char *seq, const mm_reg1_t *r, int no_iden, int is_MD, int is_ds, int write_tag, int is_qstrand = 0)
 {
 	if (r->p == 0) return;
 	std::vector<uint8_t> qseq(r->qe - r->qs + 1), tseq(r->re - r->rs + 1);
-	mm_idx_getseq(mi, r->rid, r->rs, r->re, tseq.data());
-	if (!r->rev) for (int i = r->qs; i < r->qe; ++i) qseq[i - r->qs] = mmx_nt4((uint8_t)seq[i]);
+	if (is_qstrand && r->rev) { // mm_idx_getseq2 / mm_idx_getseq_rev (index.c:176-196): the other strand of the target, forward query (format.c:343-346)
+		const int len = (int)mi->seq[r->rid].len, n = r->re - r->rs;
+		mm_idx_getseq(mi, r->rid, len - r->re, len - r->rs, tseq.data());
+		for (int i = 0, j = n - 1; i <= j; ++i, --j) { const uint8_t x = tseq[i], y = tseq[j]; tseq[i] = y < 4? 3 - y : y, tseq[j] = x < 4? 3 - x : x; }
+	} else mm_idx_getseq(mi, r->rid, r->rs, r->re, tseq.data());
+	if (!r->rev || is_qstrand) for (int i = r->qs; i < r->qe; ++i) qseq[i - r->qs] = mmx_nt4((uint8_t)seq[i]);
 	else for (int i = r->qs; i < r->qe; ++i) { uint8_t c = mmx_nt4((uint8_t)seq[i]); qseq[r->qe - i - 1] = c >= 4? 4 : 3 - c; }
 	if (is_MD) write_MD_core(s, tseq.data(), qseq.data(), r, write_tag);
 	else write_cs_ds_core(s, tseq.data(), qseq.data(), r, no_iden, is_ds, write_tag);
@@ -178,7 +182,8 @@ void hl_write_paf(std::string &s, const mm_idx_t *mi, const char *qname, int qle
 	s += '\t'; put_int(s, qlen); s += '\t'; put_int(s, r->qs); s += '\t'; put_int(s, r->qe); s += '\t'; s += "+-"[r->rev]; s += '\t';
 	if (mi->seq[r->rid].name) s += mi->seq[r->rid].name; else put_int(s, r->rid);
 	s += '\t'; put_int(s, mi->seq[r->rid].len);
-	s += '\t'; put_int(s, r->rs); s += '\t'; put_int(s, r->re);
+	if ((opt_flag & MM_F_QSTRAND) && r->rev) { s += '\t'; put_int(s, (int64_t)mi->seq[r->rid].len - r->re); s += '\t'; put_int(s, (int64_t)mi->seq[r->rid].len - r->rs); } // format.c:440-443
+	else { s += '\t'; put_int(s, r->rs); s += '\t'; put_int(s, r->re); }
 	s += '\t'; put_int(s, r->mlen); s += '\t'; put_int(s, r->blen);
 	s += '\t'; put_int(s, r->mapq);
 	write_tags(s, r);
@@ -188,7 +193,7 @@ void hl_write_paf(std::string &s, const mm_idx_t *mi, const char *qname, int qle
 		for (uint32_t k = 0; k < r->p->n_cigar; ++k) { put_int(s, r->p->cigar[k] >> 4); s += MM_CIGAR_STR[r->p->cigar[k] & 0xf]; }
 	}
 	if (r->p && (opt_flag & (MM_F_OUT_CS | MM_F_OUT_DS | MM_F_OUT_MD)) && tl_seq)
-		write_cs_ds_or_MD(s, mi, tl_seq, r, !(opt_flag & MM_F_OUT_CS_LONG), !!(opt_flag & MM_F_OUT_MD), !!(opt_flag & MM_F_OUT_DS), 1);
+		write_cs_ds_or_MD(s, mi, tl_seq, r, !(opt_flag & MM_F_OUT_CS_LONG), !!(opt_flag & MM_F_OUT_MD), !!(opt_flag & MM_F_OUT_DS), 1, !!(opt_flag & MM_F_QSTRAND));
 }
 
 static const unsigned char comp_tab[128] = { // bseq.c:11-28 (ASCII range)

@@ -248,8 +248,14 @@ __global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
 			*(uint32_t*)(x2b[0] + i) = NQE24, *(uint32_t*)(x2b[1] + i) = NQE24;
 			if (!approx_max) { H[i] = H[i + 1] = H[i + 2] = H[i + 3] = KSW_NEG_INF; }
 		}
-		for (int i = g; i < tlen16; i += G)
-			sf[i] = i < tlen? fetch_target(A.target, A.t_packed, jb.t_start + (long long)i * jb.t_step) : 0;
+		{
+			const bool tc = (flag & MMB_JOB_T_COMP) != 0;
+			for (int i = g; i < tlen16; i += G) {
+				uint8_t c = i < tlen? fetch_target(A.target, A.t_packed, jb.t_start + (long long)i * jb.t_step) : 0;
+				if (tc && c < 4 && i < tlen) c = 3 - c;
+				sf[i] = c;
+			}
+		}
 		for (int i = g; i < LQ + 48; i += G) { // qr[-16 .. LQ+32)
 			int k = i - 16; // position in qr
 			uint8_t c = 0;
@@ -631,7 +637,8 @@ __global__ void __launch_bounds__(128) ksw_ll_kernel(LLArgs A)
 		__syncwarp(gmask);
 		int gmax = 0, qe = -1, te = -1;
 		for (int i = 0; i < tlen; ++i) {
-			const int t = fetch_target(A.target, A.t_packed, jb.t_start + (long long)i * jb.t_step);
+			int t = fetch_target(A.target, A.t_packed, jb.t_start + (long long)i * jb.t_step);
+			if ((jb.flag & MMB_JOB_T_COMP) && t < 4) t = 3 - t;
 			const int8_t *ma = A.mat + t * 5;
 			int16_t f = 0, mx = 0, h, e;
 			h = slen > 0? H0[(slen - 1) * 8 + k] : 0;

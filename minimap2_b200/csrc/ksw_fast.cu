@@ -586,7 +586,7 @@ void mmb_order_by_cells(std::vector<int> &v, const mmb_ksw_job_t *h_jobs)
 bool mmb_ksw_fast_eligible(const mmb_ksw_job_t &j)
 {
 	const int f = j.flag;
-	if (f & (MMB_JOB_LL | MMB_JOB_SPLICE | MMB_KSW_SCORE_ONLY | MMB_KSW_RIGHT | MMB_KSW_APPROX_DROP | MMB_KSW_EXTZ_ONLY)) return false;
+	if (f & (MMB_JOB_LL | MMB_JOB_SPLICE | MMB_JOB_T_COMP | MMB_KSW_SCORE_ONLY | MMB_KSW_RIGHT | MMB_KSW_APPROX_DROP | MMB_KSW_EXTZ_ONLY)) return false;
 	if (!(f & MMB_KSW_APPROX_MAX)) return false;
 	if (j.qlen <= 0 || j.tlen <= 0 || j.tlen > 512 || j.qlen > 2048) return false;
 	const int w = j.w < 0? std::max(j.qlen, j.tlen) : j.w;

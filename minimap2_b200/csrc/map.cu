@@ -230,7 +230,8 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 {
 	const char *what = nullptr;
 	if (opt->flag & (MM_F_SR | MM_F_SR_RNA)) what = "short-read mode (-x sr / splice:sr)";
-	else if (opt->flag & MM_F_QSTRAND) what = "--qstrand";
+	else if ((opt->flag & MM_F_QSTRAND) && (!(opt->flag & MM_F_NO_INV) || (opt->flag & (MM_F_SPLICE | MM_F_OUT_SAM)) || (mi->flag & MM_I_HPC)))
+		what = "query-strand mode without MM_F_NO_INV (main.c:252 sets both), or combined with splice / SAM / HPC (mm_check_opt rejects those)";
 	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
 	if (what) {
 		fprintf(stderr, "[ERROR] minimap2_b200: %s is not implemented in this build; refusing to run (no CPU fallback)\n", what);
@@ -450,7 +451,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		r.hash = wang_hash(hash);
 		r.a.assign(r.a_src, r.a_src + r.n_a);
 		int n_regs0 = r.n_u;
-		mm_reg1_t *regs0 = hl_gen_regs(r.hash, r.qlen, r.n_u, r.u, r.a.data(), 0);
+		mm_reg1_t *regs0 = hl_gen_regs(r.hash, r.qlen, r.n_u, r.u, r.a.data(), !!(opt->flag & MM_F_QSTRAND)); // map.c:320
 		if (mi->n_alt) { // map.c:321-324 (mm_mark_alt, hit.c:91-97)
 			for (int k = 0; k < n_regs0; ++k) if (mi->seq[regs0[k].rid].is_alt) regs0[k].is_alt = 1;
 			hl_hit_sort(&n_regs0, regs0, opt->alt_drop);
@@ -459,8 +460,10 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 			hl_set_parent(opt->mask_level, opt->mask_len, n_regs0, regs0, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
 			hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 1, (int)(opt->max_gap * 0.8), &n_regs0, regs0);
 		}
-		hl_est_err(mi, r.qlen, n_regs0, regs0, r.a.data(), r.n_mini_pos, r.mini_pos);
-		n_regs0 = hl_filter_strand_retained(n_regs0, regs0);
+		if (!(opt->flag & MM_F_QSTRAND)) { // map.c:333-336
+			hl_est_err(mi, r.qlen, n_regs0, regs0, r.a.data(), r.n_mini_pos, r.mini_pos);
+			n_regs0 = hl_filter_strand_retained(n_regs0, regs0);
+		}
 		r.n_regs0 = n_regs0, r.regs0 = regs0;
 		if (with_cigar && n_regs0 > 0) {
 			ReadAlign *ra = &bb.ra_pool[live[j]];

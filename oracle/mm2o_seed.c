@@ -14,7 +14,7 @@
 #define F_NO_DUAL   0x002LL
 #define F_FOR_ONLY  0x100000LL
 #define F_REV_ONLY  0x200000LL
-#define F_QSTRAND   0x10000000LL
+#define F_QSTRAND   0x100000000LL
 #define SEED_TANDEM (1ULL<<42)
 #define SEED_SELF   (1ULL<<43)
 #define SEED_SEG_SHIFT 48

@@ -36,7 +36,11 @@ static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t 
 		if ((j.flag & MMB_JOB_Q_COMP) && c < 4) c = 3 - c;
 		q[i] = c;
 	}
-	for (int i = 0; i < j.tlen; ++i) t[i] = (uint8_t)mmx_seq4_get(mi->S, (uint64_t)(j.t_start + (int64_t)i * j.t_step));
+	for (int i = 0; i < j.tlen; ++i) {
+		uint8_t c = (uint8_t)mmx_seq4_get(mi->S, (uint64_t)(j.t_start + (int64_t)i * j.t_step));
+		if ((j.flag & MMB_JOB_T_COMP) && c < 4) c = 3 - c;
+		t[i] = c;
+	}
 	KswDone d;
 	memset(&d, 0, sizeof(d));
 	d.r.zd_max = -1; // the scan of mm_test_zdrop is left to the driver (host path)

@@ -81,6 +81,8 @@ def compare_formats(H, R, api, mi, qname, qstr, n, pm, pr, rep_len, flag):
             R.refshim_free(C.c_void_p(ks.s))
             ln = H.hs_write_paf(buf, len(buf), mi, qname.encode(), qstr, len(qstr), C.c_void_p(pm + j * REG_SIZE), C.c_int64(fl), C.c_int(rep_len))
             assert ln >= 0 and buf.raw[:ln] == ref_line, (qname, j, hex(extra), ref_line[:300], buf.raw[:min(ln, 300)])
+    if flag & 0x100000000:  # SAM is not defined in query-strand mode (mm_check_opt, options.c)
+        return
     fl = flag | F_OUT_SAM | F_OUT_MD
     n_arr = (C.c_int * 1)(n); regs_arr = (C.c_void_p * 1)(pr)
     for j in range(n):
@@ -112,7 +114,8 @@ def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0
     n_checked = n_split = 0
     for qi, rd in enumerate(reads):
         qstr = bytes(rd); qlen = len(qstr)
-        a, rep, mini = oidx.anchors(qstr, mid_occ=mo.mid_occ, q_occ_frac=mo.q_occ_frac, max_max_occ=mo.max_max_occ, occ_dist=mo.occ_dist)
+        qst = 1 if mo.flag & 0x100000000 else 0  # MM_F_QSTRAND: reverse hits in the coordinates of the target's other strand (map.c:188-192)
+        a, rep, mini = oidx.anchors(qstr, flag=(0x100000000 if qst else 0), mid_occ=mo.mid_occ, q_occ_frac=mo.q_occ_frac, max_max_occ=mo.max_max_occ, occ_dist=mo.occ_dist)
         if len(a) == 0:
             continue
         gap_ref = mo.max_gap_ref if mo.max_gap_ref > 0 else mo.max_gap  # map.c:262-269
@@ -123,11 +126,11 @@ def run_case(H, R, api, contigs, names, reads, preset="map-ont", w=10, is_cdna=0
         n = len(u)
         uu = u.copy(); bb = np.ascontiguousarray(b.copy())
         hash_ = 12345 + qi
-        regs0 = R.mm_gen_regs(None, C.c_uint32(hash_), qlen, n, uu.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p), 0)
+        regs0 = R.mm_gen_regs(None, C.c_uint32(hash_), qlen, n, uu.ctypes.data_as(C.c_void_p), bb.ctypes.data_as(C.c_void_p), qst)
         R.mm_set_parent(None, C.c_float(mo.mask_level), mo.mask_len, n, C.c_void_p(regs0), mo.a * 2 + mo.b, 0, C.c_float(mo.alt_drop))
         nn = C.c_int(n)
         R.mm_select_sub(None, C.c_float(mo.pri_ratio), k * 2, mo.best_n, 1, int(mo.max_gap * 0.8), C.byref(nn), C.c_void_p(regs0))
-        n0 = R.mm_filter_strand_retained(nn.value, C.c_void_p(regs0))
+        n0 = nn.value if qst else R.mm_filter_strand_retained(nn.value, C.c_void_p(regs0))  # map.c:333-336
         snap = C.string_at(regs0, n0 * REG_SIZE)
         # mine first (inputs are const), then the reference (consumes regs0 and rewrites the anchors)
         nm = C.c_int(n0); waves = C.c_int(0)
@@ -354,6 +357,20 @@ def test_driver_with_splice_scores(libs, tmp_path):
     g, reads, introns = _spliced_set(61, 36)
     fn = str(tmp_path / "sc.txt"); _write_spsc(fn, g, introns, rng)
     n, _ = run_case(H, R, api, [g], ["chr0"], reads, preset="splice", w=5, is_cdna=1, spsc=fn)
+    assert n >= 30
+
+
+def test_driver_in_query_strand_mode(libs):
+    """--qstrand (MM_F_QSTRAND | MM_F_NO_INV, main.c:252): the query stays forward and a reverse hit is aligned against the other
+    strand of the target (mm_idx_getseq2, align.c:780-783,815-818,875-878,899-901), coordinates on that strand; PAF prints them
+    flipped (format.c:440-443) and cs/MD use the same view"""
+    H, R, api = libs
+    contigs = synth.random_genome(200_000, 27, n_contigs=2, repeat_frac=0.1)
+    reads = synth.make_reads(contigs, 40, 3000, 0.08, 127, chimeric_frac=0.1)
+
+    def qstrand(mo):
+        mo.flag |= 0x100000000 | 0x200000000  # MM_F_QSTRAND | MM_F_NO_INV
+    n, _ = run_case(H, R, api, contigs, ["chr0", "chr1"], reads, tweak=qstrand)
     assert n >= 30
 
 

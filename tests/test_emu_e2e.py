@@ -111,6 +111,20 @@ def _rechain_inputs(d):
     return ["-c", "-f", "3,50", "-e", "0", rf, qf]
 
 
+def _qstrand_inputs(d):
+    """--qstrand: reverse-strand hits are chained and aligned on the other strand of the target with the query kept forward"""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(51)
+    g = np.frombuffer(bytes(synth.random_genome(12_000, 23)[0]), dtype=np.uint8).copy()
+    comp = np.zeros(256, dtype=np.uint8); comp[list(b"ACGT")] = list(b"TGCA")
+    reads = [synth.mutate_ascii(g[800:2300], rng, 0.06), synth.mutate_ascii(comp[g[3000:4700][::-1]], rng, 0.06),
+             synth.mutate_ascii(np.concatenate([comp[g[7000:7900][::-1]], comp[g[6100:6800][::-1]]]), rng, 0.04)]
+    rf, qf = os.path.join(d, "qs_ref.fa"), os.path.join(d, "qs_reads.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["fwd", "rev", "rev_del"], reads)
+    return ["-c", "--cs", "--qstrand", rf, qf]
+
+
 def _asm_inputs(d, preset, div):
     import numpy as np
     import synth
@@ -208,6 +222,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["ava"] = (_ava_inputs(d), d, True)
         jobs["edge"] = (_edge_inputs(d), d, True)
         jobs["rechain"] = (_rechain_inputs(d), d, True)
+        jobs["qstrand"] = (_qstrand_inputs(d), d, True)
         jobs["multipart"] = (_multipart_inputs(d), d, True)
 
     def one(item):
@@ -288,6 +303,15 @@ def test_emulated_second_occurrence_cutoff_matches_reference(emu_runs):
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"]
     assert any(l.startswith("in0\t") for l in r["ref"]) and any(l.startswith("in1\t") for l in r["ref"])  # mapped thanks to the second pass
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_query_strand_mode_matches_reference(emu_runs):
+    """--qstrand end to end: anchors of reverse hits in other-strand coordinates (map.c:188-192), jobs that read the target
+    complemented (MMB_JOB_T_COMP, universal kernel), flipped PAF coordinates and cs on that view (format.c:343-346,440-443)"""
+    r = emu_runs["qstrand"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and sum(l.split("\t")[4] == "-" for l in r["ref"]) >= 2
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

@@ -129,3 +129,15 @@ def test_splice_kernel_with_score_tables_matches_oracle():
     ctx = mb.Context(0)
     E.check_splice_jobs((L, C.c_void_p(ctx.h), KswJob, KswRes, KswScore), np.random.default_rng(181), (0x400 | 0x800, 0x400, 0), 200, 5, with_score=True)
     ctx.close()
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_query_strand_mode(tmp_path):
+    """--qstrand (main.c:252; map.c:188-192; align.c:780-783,815-818,875-878,899-901; format.c:343-346,440-443)"""
+    contigs = synth.random_genome(500_000, 71, n_contigs=2, repeat_frac=0.1)
+    reads = synth.make_reads(contigs, 300, 4000, 0.08, 171, chimeric_frac=0.05)
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    assert compare(["-x", "map-ont", "-c", "--cs", "--qstrand", rf, qf]) >= 280
+    compare(["--qstrand", rf, qf])

@@ -465,3 +465,96 @@ void hl_update_dp_max(int qlen, int n_regs, mm_reg1_t *regs, float frac, int a, 
 		if (r->p->dp_max < 0) r->p->dp_max = 0;
 	}
 }
+
+
+// ---- symmetric DUST (sdust.c:66-186, W-window low-complexity masking): used by -T to drop query minimizers that lie mostly in
+// masked intervals (mm_dust_minier, map.c:33-57). Restated on std containers; the state handling is the reference's, including that
+// an ambiguous base ends the run (l, t) but leaves the word window and its counters as they are. ----
+#include <deque>
+namespace {
+struct DustState {
+	static constexpr int WLEN = 3, WTOT = 1 << (WLEN << 1);
+	struct Perf { int start, finish, r, l; };
+	std::deque<int> w;          // triplet words of the current window
+	std::vector<Perf> P;        // perfect intervals of the window, by descending start then ascending finish
+	std::vector<uint64_t> &res; // masked intervals start<<32 | finish
+	int cv[WTOT], cw[WTOT], rv = 0, rw = 0, L = 0;
+	const int T, W;
+	DustState(std::vector<uint64_t> &out, int T_, int W_) : res(out), T(T_), W(W_) { memset(cv, 0, sizeof(cv)); memset(cw, 0, sizeof(cw)); }
+
+	void shift_window(int t) { // sdust.c:66-88
+		int s;
+		if ((int)w.size() >= W - WLEN + 1) {
+			s = w.front(); w.pop_front();
+			rw -= --cw[s];
+			if (L > (int)w.size()) --L, rv -= --cv[s];
+		}
+		w.push_back(t);
+		++L;
+		rw += cw[t]++;
+		rv += cv[t]++;
+		if (cv[t] * 10 > T << 1) {
+			do {
+				s = w[w.size() - L];
+				rv -= --cv[s];
+				--L;
+			} while (s != t);
+		}
+	}
+	void save_masked(int start) { // sdust.c:90-104
+		if (P.empty() || P.back().start >= start) return;
+		const Perf &p = P.back();
+		bool saved = false;
+		if (!res.empty()) {
+			const int s = (int)(res.back() >> 32), f = (int)(uint32_t)res.back();
+			if (p.start <= f) saved = true, res.back() = (uint64_t)s << 32 | (uint32_t)(f > p.finish? f : p.finish);
+		}
+		if (!saved) res.push_back((uint64_t)p.start << 32 | (uint32_t)p.finish);
+		int i = (int)P.size() - 1;
+		while (i >= 0 && P[i].start < start) --i;
+		P.resize(i + 1);
+	}
+	void find_perfect(int start) { // sdust.c:106-133
+		int c[WTOT], r = rv, max_r = 0, max_l = 0;
+		memcpy(c, cv, sizeof(c));
+		for (int i = (int)w.size() - L - 1; i >= 0; --i) {
+			const int t = w[i];
+			r += c[t]++;
+			const int new_r = r, new_l = (int)w.size() - i - 1;
+			if (new_r * 10 > T * new_l) {
+				size_t j;
+				for (j = 0; j < P.size() && P[j].start >= i + start; ++j)
+					if (max_r == 0 || P[j].r * max_l > max_r * P[j].l) max_r = P[j].r, max_l = P[j].l;
+				if (max_r == 0 || new_r * max_l >= max_r * new_l) {
+					max_r = new_r, max_l = new_l;
+					P.insert(P.begin() + j, Perf{ i + start, (int)w.size() + (WLEN - 1) + start, new_r, new_l });
+				}
+			}
+		}
+	}
+};
+} // namespace
+
+void hl_sdust(const uint8_t *seq, int l_seq, int T, int W, std::vector<uint64_t> &res) // sdust_core (sdust.c:135-170); seq is ASCII
+{
+	res.clear();
+	DustState d(res, T, W);
+	int l = 0, start;
+	unsigned t = 0;
+	for (int i = 0; i <= l_seq; ++i) {
+		const int b = i < l_seq? mmx_nt4(seq[i]) : 4;
+		if (b < 4) {
+			++l, t = (t << 2 | (unsigned)b) & (DustState::WTOT - 1);
+			if (l >= DustState::WLEN) {
+				start = (l - W > 0? l - W : 0) + (i + 1 - l);
+				d.save_masked(start);
+				d.shift_window((int)t);
+				if (d.rw * 10 > d.L * T) d.find_perfect(start);
+			}
+		} else {
+			start = (l - W + 1 > 0? l - W + 1 : 0) + (i + 1 - l);
+			while (!d.P.empty()) d.save_masked(start++);
+			l = 0, t = 0;
+		}
+	}
+}

@@ -18,6 +18,7 @@ mm_reg1_t *hl_gen_regs(uint32_t hash, int qlen, int n_u, const uint64_t *u, cons
 void hl_split_reg(mm_reg1_t *r, mm_reg1_t *r2, int n, int qlen, m128 *a, int is_qstrand);
 void hl_set_parent(float mask_level, int mask_len, int n, mm_reg1_t *r, int sub_diff, int hard_mask_level, float alt_diff_frac);
 void hl_hit_sort(int *n_regs, mm_reg1_t *r, float alt_diff_frac);
+void hl_sdust(const uint8_t *seq, int l_seq, int T, int W, std::vector<uint64_t> &res); // sdust_core (sdust.c:135-170): masked intervals start<<32|finish of an ASCII sequence
 int hl_set_sam_pri(int n, mm_reg1_t *r);
 void hl_sync_regs(int n_regs, mm_reg1_t *regs);
 void hl_select_sub(float pri_ratio, int min_diff, int best_n, int check_strand, int min_strand_sc, int *n_, mm_reg1_t *r);

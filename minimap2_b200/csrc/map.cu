@@ -159,6 +159,35 @@ __global__ void init_nmz_kernel(const int64_t *mz_off, int n, int32_t *n_mz)
 	if (i < n) n_mz[i] = (int32_t)(mz_off[i + 1] - mz_off[i]);
 }
 
+// mm_dust_minier (map.c:33-57): minimizers of a read more than half covered by its masked (low-complexity) intervals are squeezed
+// out, order kept. dreg: the read's intervals start<<32|finish in query order (host: hl_sdust). One thread per read -- the -T option
+// is off by default and rarely used.
+__global__ void dust_filter_kernel(m128 *mz, const int64_t *mz_off, int32_t *n_mz, const uint64_t *dreg, const int64_t *dreg_off, int n_reads)
+{
+	const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+	if (rd >= n_reads) return;
+	const uint64_t *dr = dreg + dreg_off[rd];
+	const int n_dreg = (int)(dreg_off[rd + 1] - dreg_off[rd]), n = n_mz[rd];
+	if (n_dreg == 0) return;
+	m128 *a = mz + mz_off[rd];
+	int u = 0, k = 0;
+	for (int j = 0; j < n; ++j) {
+		const int32_t qpos = (int32_t)((uint32_t)a[j].y >> 1), span = (int32_t)(a[j].x & 0xff);
+		const int32_t s = qpos - (span - 1), e = s + span;
+		while (u < n_dreg && (int32_t)dr[u] <= s) ++u;
+		if (u < n_dreg && (int32_t)(dr[u] >> 32) < e) {
+			int l = 0;
+			for (int v = u; v < n_dreg && (int32_t)(dr[v] >> 32) < e; ++v) { // intervals overlapping this minimizer
+				const int ss = s > (int32_t)(dr[v] >> 32)? s : (int32_t)(dr[v] >> 32);
+				const int ee = e < (int32_t)dr[v]? e : (int32_t)(uint32_t)dr[v];
+				l += ee - ss;
+			}
+			if (l <= span >> 1) a[k++] = a[j];
+		} else a[k++] = a[j];
+	}
+	n_mz[rd] = k;
+}
+
 __global__ void to_i64_kernel(const int32_t *a, int n, int64_t *b)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -215,6 +244,7 @@ struct BatchBufs { // device arenas reused across batches (per context)
 	DevBuf n_u, n_v, u, a_out, ch1, ch2, t1, t2, doff, dense_u, dense_a, dense_mp;
 	DevBuf jobs, res, cig;
 	DevBuf qlo, qhi, k_cnt;                // skip_seed inputs (ava / strand-restricted modes only)
+	DevBuf dreg, dreg_off;                 // masked intervals of the reads (-T / SDUST only)
 	PinBuf h_seq, h_misc, h_jobs, h_res, h_cig[16];
 	std::vector<ReadState> rs_pool;        // persistent per-read objects: their vectors keep capacity => no allocation in steady state
 	std::vector<ReadAlign> ra_pool;
@@ -232,7 +262,6 @@ void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
 	if (opt->flag & (MM_F_SR | MM_F_SR_RNA)) what = "short-read mode (-x sr / splice:sr)";
 	else if ((opt->flag & MM_F_QSTRAND) && (!(opt->flag & MM_F_NO_INV) || (opt->flag & (MM_F_SPLICE | MM_F_OUT_SAM)) || (mi->flag & MM_I_HPC)))
 		what = "query-strand mode without MM_F_NO_INV (main.c:252 sets both), or combined with splice / SAM / HPC (mm_check_opt rejects those)";
-	else if (opt->sdust_thres > 0) what = "SDUST masking (-T)";
 	if (what) {
 		fprintf(stderr, "[ERROR] minimap2_b200: %s is not implemented in this build; refusing to run (no CPU fallback)\n", what);
 		abort();
@@ -322,6 +351,21 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	S.n_keep = bb.n_keep.as<int32_t>((size_t)n), S.rep_len = bb.rep_len.as<int32_t>((size_t)n), S.n_a = bb.n_a.as<int64_t>((size_t)n + 1);
 	init_nmz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_mz_off, n, S.n_mz);
 	++ctx->n_launch;
+	if (opt->sdust_thres > 0) { // map.c:68-69: low-complexity masking of the query minimizers; the intervals come from the host
+		std::vector<std::vector<uint64_t>> regs((size_t)n);
+		parallel_for(n, n_threads, [&](int64_t j, int) { hl_sdust((const uint8_t*)rs[live[j]].seq, rs[live[j]].qlen, opt->sdust_thres, 64, regs[j]); });
+		std::vector<int64_t> doff((size_t)n + 1, 0);
+		for (int j = 0; j < n; ++j) doff[j + 1] = doff[j] + (int64_t)regs[j].size();
+		std::vector<uint64_t> flat((size_t)doff[n] + 1);
+		for (int j = 0; j < n; ++j) std::copy(regs[j].begin(), regs[j].end(), flat.begin() + doff[j]);
+		uint64_t *d_dreg = bb.dreg.as<uint64_t>(flat.size());
+		int64_t *d_doff = bb.dreg_off.as<int64_t>((size_t)n + 1);
+		MMB_CUDA_CHECK(cudaMemcpyAsync(d_dreg, flat.data(), sizeof(uint64_t) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+		MMB_CUDA_CHECK(cudaMemcpyAsync(d_doff, doff.data(), sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->stream));
+		dust_filter_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(S.mz, d_mz_off, S.n_mz, d_dreg, d_doff, n);
+		MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); // the pageable staging vectors go out of scope here
+		++ctx->n_launch;
+	}
 	if (opt->flag & (MM_F_NO_DIAG | MM_F_NO_DUAL | MM_F_FOR_ONLY | MM_F_REV_ONLY)) { // skip_seed (map.c:78-100) runs on the device
 		S.k_cnt = bb.k_cnt.as<uint32_t>(nm);
 		if (names && (opt->flag & (MM_F_NO_DIAG | MM_F_NO_DUAL))) {

@@ -20,3 +20,12 @@ void hs_set_mapq(int n, mm_reg1_t *r, int min_chain_sc, int match_sc, int rep_le
 void hs_est_err(const mm_idx_t *mi, int qlen, int n_regs, mm_reg1_t *regs, const m128 *a, int32_t n, const uint64_t *mini_pos) { hl_est_err(mi, qlen, n_regs, regs, a, n, mini_pos); }
 void hs_free(void *p) { free(p); }
 }
+
+// symmetric DUST (csrc/hits.cc hl_sdust) next to the reference's sdust(): returns the number of intervals, copies up to cap of them
+extern "C" int hs_sdust(const uint8_t *seq, int l_seq, int T, int W, uint64_t *out, int cap)
+{
+	std::vector<uint64_t> res;
+	hl_sdust(seq, l_seq, T, W, res);
+	for (int i = 0; i < (int)res.size() && i < cap; ++i) out[i] = res[i];
+	return (int)res.size();
+}

@@ -125,6 +125,22 @@ def _qstrand_inputs(d):
     return ["-c", "--cs", "--qstrand", rf, qf]
 
 
+def _sdust_inputs(d):
+    """-T 20: query minimizers inside low-complexity stretches (microsatellites present many times in the genome) are masked
+    before seeding (mm_dust_minier, map.c:33-57,68-69)"""
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(61)
+    g = np.frombuffer(bytes(synth.random_genome(10_000, 29)[0]), dtype=np.uint8).copy()
+    for st in (1500, 4200, 7700):  # the same microsatellite at three places
+        g[st:st + 160] = np.frombuffer(b"ACACACACATACACACACGC" * 8, dtype=np.uint8)
+    g[5600:5680] = ord("A")
+    reads = [synth.mutate_ascii(g[900:2400], rng, 0.04), synth.mutate_ascii(g[3800:6000], rng, 0.05), synth.mutate_ascii(g[7650:7900], rng, 0.02)]
+    rf, qf = os.path.join(d, "sd_ref.fa"), os.path.join(d, "sd_reads.fa")
+    synth.write_fasta(rf, ["chr0"], [g.tobytes()]); synth.write_fasta(qf, ["r0", "r1", "r2"], reads)
+    return ["-c", "-T", "20", "-w", "5", rf, qf]
+
+
 def _asm_inputs(d, preset, div):
     import numpy as np
     import synth
@@ -223,6 +239,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["edge"] = (_edge_inputs(d), d, True)
         jobs["rechain"] = (_rechain_inputs(d), d, True)
         jobs["qstrand"] = (_qstrand_inputs(d), d, True)
+        jobs["sdust"] = (_sdust_inputs(d), d, True)
         jobs["multipart"] = (_multipart_inputs(d), d, True)
 
     def one(item):
@@ -312,6 +329,14 @@ def test_emulated_query_strand_mode_matches_reference(emu_runs):
     r = emu_runs["qstrand"]
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"] and sum(l.split("\t")[4] == "-" for l in r["ref"]) >= 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_sdust_masking_matches_reference(emu_runs):
+    """-T: symmetric DUST intervals from the host (hl_sdust), minimizers squeezed on the device before the occurrence filter"""
+    r = emu_runs["sdust"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) >= 2
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

@@ -141,3 +141,21 @@ def test_query_strand_mode(tmp_path):
     synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
     assert compare(["-x", "map-ont", "-c", "--cs", "--qstrand", rf, qf]) >= 280
     compare(["--qstrand", rf, qf])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_sdust_masking(tmp_path):
+    """-T 20 (mm_dust_minier, map.c:33-57): reads over a genome seeded with microsatellites and homopolymer runs"""
+    rng = np.random.default_rng(17)
+    contigs = synth.random_genome(400_000, 81, n_contigs=2, repeat_frac=0.05)
+    gs = [np.frombuffer(bytes(c), dtype=np.uint8).copy() for c in contigs]
+    for g in gs:
+        for _ in range(150):
+            st = int(rng.integers(0, len(g) - 400)); unit = synth.ALPHA[rng.integers(0, 4, int(rng.integers(1, 5)))]
+            L = int(rng.integers(40, 300)); g[st:st + L] = np.resize(unit, L)
+    reads = synth.make_reads(gs, 300, 3000, 0.06, 181, chimeric_frac=0.02)
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr0", "chr1"], [g.tobytes() for g in gs])
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    assert compare(["-c", "-T", "20", rf, qf]) >= 280
+    compare(["-x", "map-ont", "-T", "12", rf, qf])

@@ -116,3 +116,39 @@ def test_hit_logic_matches_reference(libs, seed):
         assert H.hs_set_sam_pri(nh.value, C.c_void_p(ph)) == R.mm_set_sam_pri(nr.value, C.c_void_p(pr))
         assert regs_bytes(ph, nh.value) == regs_bytes(pr, nr.value), ("set_sam_pri", it)
         H.hs_free(C.c_void_p(ph)); O.ref().refshim_free(C.c_void_p(pr))
+
+
+def test_sdust_matches_reference(libs):
+    """symmetric DUST (sdust.c) restated in csrc/hits.cc vs the reference's sdust(): random, low-complexity, tandem-repeat and
+    N-interrupted sequences, several thresholds and window sizes"""
+    H, R = libs[0], libs[1]
+    R.sdust.restype = C.POINTER(C.c_uint64)
+    R.sdust.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+    H.hs_sdust.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(9)
+    n_masked = 0
+    for it in range(120):
+        parts = []
+        for _ in range(int(rng.integers(1, 8))):
+            kind = int(rng.integers(0, 5))
+            if kind == 0:
+                parts.append(bytes(rng.choice(list(b"ACGT"), int(rng.integers(5, 400)))))
+            elif kind == 1:
+                parts.append(bytes([int(rng.choice(list(b"ACGT")))]) * int(rng.integers(3, 120)))
+            elif kind == 2:
+                unit = bytes(rng.choice(list(b"ACGT"), int(rng.integers(2, 7)))); parts.append(unit * int(rng.integers(2, 40)))
+            elif kind == 3:
+                parts.append(b"N" * int(rng.integers(1, 5)))
+            else:
+                parts.append(bytes(rng.choice(list(b"AAAT"), int(rng.integers(10, 200)))).lower())
+        seq = b"".join(parts)
+        T = int(rng.choice([10, 20, 20, 30, 50])); W = int(rng.choice([16, 32, 64, 64, 100]))
+        n = C.c_int(0)
+        p = R.sdust(None, seq, len(seq), T, W, C.byref(n))
+        ref = [int(p[i]) for i in range(n.value)]
+        R.refshim_free(p)
+        out = (C.c_uint64 * 4096)()
+        m = H.hs_sdust(seq, len(seq), T, W, out, 4096)
+        assert m == n.value and [int(out[i]) for i in range(m)] == ref, (it, T, W, seq[:80])
+        n_masked += m
+    assert n_masked > 300

@@ -919,7 +919,13 @@ extern "C" int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn
 		parsed.close();
 	});
 	std::thread writer([&]() { // step 2: format in parallel over blocks of reads, print in input order
-		const int n_fmt = n_threads < 1? 1 : n_threads > 16? 16 : n_threads;
+		// formatting runs next to the following batch's host phases: keep it to an eighth of the CPUs (at most 16 threads), the
+		// scheduler's own threads must not queue behind it (see the pool cap in HostPool)
+		const int hw = (int)std::thread::hardware_concurrency();
+		int n_fmt = hw >= 16? hw / 8 : 1;
+		if (n_fmt > n_threads) n_fmt = n_threads;
+		if (n_fmt > 16) n_fmt = 16;
+		if (n_fmt < 1) n_fmt = 1;
 		BatchPtr fb;
 		while (mapped.pop(fb)) {
 			const int n = (int)fb->recs.size(), blk = 128, n_blk = (n + blk - 1) / blk;

@@ -62,7 +62,7 @@ def transform(src):
             p += 1
         args = src[e + 4:p]
         smem = cfg[2] if len(cfg) > 2 else "0"
-        out += src[i:k] + "emu_launch(dim3(%s), dim3(%s), (size_t)(%s), [=]() { %s(%s); })" % (cfg[0], cfg[1], smem, name, args)
+        out += src[i:k] + "(emu_trace(\"%s\"), emu_launch(dim3(%s), dim3(%s), (size_t)(%s), [=]() { %s(%s); }))" % (name.replace('"', ''), cfg[0], cfg[1], smem, name, args)
         i = p + 1
     return out
 

@@ -20,6 +20,7 @@ extern thread_local uint3 threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 void *emu_dyn_smem();
 void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body);
+void emu_trace(const char *kernel_name); // EMU_TRACE=1: print every launch to stderr (debugging aid)
 
 // ---- warp / block collectives (emu_runtime.cc) ----
 void emu_warp_exchange(unsigned mask, uint64_t mine, uint64_t out[32], unsigned *present); // rendezvous of the live lanes in mask

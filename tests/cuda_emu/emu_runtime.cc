@@ -58,6 +58,12 @@ void __syncthreads()
 }
 
 // One set of OS threads per launch; the blocks of the grid run one after another on it (thread t plays CUDA thread t of every block).
+void emu_trace(const char *kernel_name)
+{
+	static const bool on = getenv("EMU_TRACE") != nullptr;
+	if (on) fprintf(stderr, "[emu] launch %s\n", kernel_name);
+}
+
 void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, const std::function<void()> &body)
 {
 	const int nt = (int)(block.x * block.y * block.z);

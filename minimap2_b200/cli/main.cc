@@ -32,6 +32,8 @@ static void yes_or_no(mm_mapopt_t *opt, int64_t flag, const char *name, const ch
 }
 
 static struct option long_options[] = {
+	{ "splice-flank", required_argument, 0, 319 }, { "end-seed-pen", required_argument, 0, 321 }, { "cost-non-gt-ag", required_argument, 0, 'C' },
+	{ "max-intron-len", required_argument, 0, 'G' }, { "lj-min-ratio", required_argument, 0, 330 }, { "cap-kalloc", required_argument, 0, 349 }, { "no-kalloc", no_argument, 0, 303 },
 	{ "bucket-bits", required_argument, 0, 300 }, { "mb-size", required_argument, 0, 'K' }, { "seed", required_argument, 0, 302 },
 	{ "no-self", no_argument, 0, 'D' }, { "max-chain-skip", required_argument, 0, 307 }, { "min-dp-len", required_argument, 0, 308 },
 	{ "splice", no_argument, 0, 310 }, { "no-long-join", no_argument, 0, 312 }, { "secondary", required_argument, 0, 315 },
@@ -122,6 +124,11 @@ int main(int argc, char *argv[])
 		else if (c == 310) opt.flag |= MM_F_SPLICE;
 		else if (c == 312) opt.flag |= MM_F_NO_LJOIN;
 		else if (c == 317) opt.end_bonus = atoi(optarg);
+		else if (c == 319) yes_or_no(&opt, MM_F_SPLICE_FLANK, "splice-flank", optarg, 1);
+		else if (c == 321) opt.anchor_ext_shift = atoi(optarg);
+		else if (c == 330) fprintf(stderr, "[WARNING] \033[1;31m --lj-min-ratio has been deprecated.\033[0m\n");
+		else if (c == 349) opt.cap_kalloc = (int64_t)parse_num(optarg); // no kalloc pool here: accepted, without effect
+		else if (c == 303) { /* --no-kalloc: nothing to switch off */ }
 		else if (c == 322) opt.flag |= MM_F_FOR_ONLY;
 		else if (c == 348) opt.flag |= MM_F_QSTRAND | MM_F_NO_INV; // main.c:252
 		else if (c == 323) opt.flag |= MM_F_REV_ONLY;

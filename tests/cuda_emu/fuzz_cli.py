@@ -2,7 +2,7 @@
 reference binary oracle/_ref/minimap2: random small genomes (repeats, tandem blocks), reads with deletions / inversions / chimeric
 joins on either strand, and random option sets (presets, output formats, -P -X --for-only --rev-only --qstrand -T -f a,b -e -k -w -A -B
 -O -E -z -r -N -p -s -m -n -K -g ...). Every run must reproduce the reference output line for line. Development tool, not part of
-the suite (a case takes seconds to minutes under emulation): python tests/cuda_emu/fuzz_cli.py FIRST_SEED LAST_SEED"""
+the suite (a case takes seconds to minutes under emulation): python tests/cuda_emu/fuzz_cli.py [--splice] FIRST_SEED LAST_SEED"""
 import sys, os, subprocess, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -78,7 +78,63 @@ def one_(seed):
             info = "rc %d/%d lines %d/%d %s ERR:%s" % (x.returncode, y.returncode, len(xs), len(ys), [(a[:250], b[:250]) for a, b in diff], y.stderr.decode()[-300:])
     return seed, ok, " ".join(args), len(xs), info
 
+def splice_case(seed):
+    """-x splice with random transcripts, canonical / non-canonical introns, optional --junc-bed / --spsc files and options"""
+    rng = np.random.default_rng(seed)
+    d = tempfile.mkdtemp(prefix="fzs%d_" % seed)
+    g = np.frombuffer(bytes(synth.random_genome(int(rng.integers(12000, 24000)), seed)[0]), dtype=np.uint8).copy()
+    reads, introns = [], []
+    for i in range(int(rng.integers(1, 4))):
+        pos = int(rng.integers(500, len(g) - 6000)); exons = []; rev = rng.random() < 0.5
+        for k in range(int(rng.integers(2, 5))):
+            el = int(rng.integers(60, 260)); exons.append((pos, pos + el)); il = int(rng.integers(80, 900))
+            if rng.random() < 0.6:
+                d_, a_ = (b"GT", b"AG") if not rev else (b"CT", b"AC")
+                g[pos + el:pos + el + 2] = list(d_); g[pos + el + il - 2:pos + el + il] = list(a_)
+            introns.append((pos + el, pos + el + il, "-" if rev else "+"))
+            pos += el + il
+        introns.pop()
+        tr = np.concatenate([g[s_:e_] for s_, e_ in exons])
+        reads.append(synth.mutate_ascii(comp[tr[::-1]] if rev else tr, rng, float(rng.choice([0.0, 0.02, 0.05]))))
+    rf, qf = d + "/ref.fa", d + "/q.fa"
+    synth.write_fasta(rf, ["c0"], [g.tobytes()]); synth.write_fasta(qf, ["t%d" % i for i in range(len(reads))], reads)
+    args = ["-x", str(rng.choice(["splice", "splice", "splice:hq"]))] + str(rng.choice(["-c", "-c --cs", "-a", "-c --MD"])).split()
+    if rng.random() < .4: args += ["-u" + str(rng.choice(["f", "r", "b", "n"]))]
+    if rng.random() < .3: args += ["-C", str(int(rng.choice([0, 5, 9])))]
+    if rng.random() < .2: args += ["--splice-flank=no"]
+    if rng.random() < .2: args += ["-G", str(int(rng.choice([500, 5000])))]
+    k = rng.random()
+    if k < .35:
+        bed = d + "/j.bed"
+        with open(bed, "w") as f:
+            for st, en, sd in introns:
+                if rng.random() < .8: f.write("c0\t%d\t%d\tj\t0\t%s\n" % (st + int(rng.choice([0, 0, 0, 2])), en + int(rng.choice([0, 0, 0, -1])), sd))
+        args += ["--junc-bed", bed] + (["--junc-bonus", str(int(rng.choice([5, 15])))] if rng.random() < .4 else [])
+    elif k < .65:
+        fn = d + "/s.txt"
+        with open(fn, "w") as f:
+            for st, en, sd in introns:
+                dp, ap = (st, en - 1) if sd == "+" else (en - 1, st)
+                f.write("c0\t%d\t%s\tD\t%d\nc0\t%d\t%s\tA\t%d\n" % (dp, sd, int(rng.integers(-3, 15)), ap, sd, int(rng.integers(-3, 15))))
+            for _ in range(int(rng.integers(0, 300))):
+                f.write("c0\t%d\t%s\t%s\t%d\n" % (int(rng.integers(1, len(g) - 1)), "+-"[int(rng.integers(0, 2))], "DA"[int(rng.integers(0, 2))], int(rng.integers(-12, 10))))
+        args += ["--spsc", fn] + (["--spsc-scale", str(rng.choice(["0.5", "1"]))] if rng.random() < .4 else []) + (["--spsc0", str(int(rng.choice([3, 8])))] if rng.random() < .3 else [])
+    full = args + [rf, qf]
+    try:
+        x = subprocess.run([O.REF_BIN, "-t", "2"] + full, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        y = subprocess.run([EMU, "-t", "3"] + full, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
+    except subprocess.TimeoutExpired:
+        return seed, True, "TIMEOUT(emulation too slow) " + " ".join(args), 0, ""
+    xs = [l for l in x.stdout.decode().splitlines() if not l.startswith("@PG")]; ys = [l for l in y.stdout.decode().splitlines() if not l.startswith("@PG")]
+    ok = xs == ys and x.returncode == y.returncode
+    info = "" if ok else "rc %d/%d lines %d/%d %s ERR:%s" % (x.returncode, y.returncode, len(xs), len(ys), [(a[:300], b[:300]) for a, b in zip(xs, ys) if a != b][:1], y.stderr.decode()[-300:])
+    return seed, ok, " ".join(a if not a.startswith(d) else os.path.basename(a) for a in args), len(xs), info
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "--splice":
+        one = splice_case
+        sys.argv.pop(1)
     lo, hi = int(sys.argv[1]), int(sys.argv[2])
     with ThreadPoolExecutor(4) as ex:
         for seed, ok, a, n, info in ex.map(one, range(lo, hi)):

@@ -218,7 +218,7 @@ def _multipart_inputs(d):
 
 @pytest.fixture(scope="module")
 def emu_runs(emu_cli, tmp_path_factory):
-    """Every emulated CLI run of this module, started together (4 at a time): the emulator spends most of its time in thread
+    """Every emulated CLI run of this module, started together (6 at a time): the emulator spends most of its time in thread
     rendezvous, so the runs overlap well and the module's wall time is that of the longest chain rather than the sum."""
     from concurrent.futures import ThreadPoolExecutor
     d = str(tmp_path_factory.mktemp("emu_e2e"))
@@ -251,7 +251,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         return name, dict(rc=p.returncode, err=p.stderr.decode()[-2000:], out=p.stdout.decode().splitlines(), ref=ref)
 
     order = sorted(jobs.items(), key=lambda kv: {"splice": 0, "splice_junc": 0, "splice_spsc": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
-    with ThreadPoolExecutor(4) as ex:
+    with ThreadPoolExecutor(6) as ex:
         return dict(ex.map(one, order))
 
 

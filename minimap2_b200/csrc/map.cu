@@ -245,7 +245,8 @@ struct BatchBufs { // device arenas reused across batches (per context)
 	DevBuf jobs, res, cig;
 	DevBuf qlo, qhi, k_cnt;                // skip_seed inputs (ava / strand-restricted modes only)
 	DevBuf dreg, dreg_off;                 // masked intervals of the reads (-T / SDUST only)
-	PinBuf h_seq, h_misc, h_jobs, h_res, h_cig[16];
+	PinBuf h_seq, h_misc, h_jobs, h_res;
+	std::vector<std::unique_ptr<PinBuf>> h_cig; // one CIGAR staging buffer per alignment wave (cached results point into them until the batch ends)
 	std::vector<ReadState> rs_pool;        // persistent per-read objects: their vectors keep capacity => no allocation in steady state
 	std::vector<ReadAlign> ra_pool;
 	std::vector<uint8_t> qseq_pool;        // nt4 forward + reverse-complement copies of the batch (2 x total bases)
@@ -592,7 +593,10 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 			}
 			const int64_t n_jobs = joff[active.size()];
 			if (n_jobs > 0) {
-				if (wave >= 16) { fprintf(stderr, "[ERROR] minimap2_b200: too many alignment waves\n"); abort(); }
+				// every wave executes all jobs the replays asked for, so each read advances by at least one ksw call per wave and the
+				// loop ends; reads that keep splitting under a very small z-drop (-z 30) legitimately need dozens of waves. The
+				// bound only guards against a logic error.
+				if (wave >= 100000) { fprintf(stderr, "[ERROR] minimap2_b200: too many alignment waves\n"); abort(); }
 				mmb_ksw_job_t *jobs = bb.h_jobs.as<mmb_ksw_job_t>((size_t)n_jobs);
 				parallel_for((int64_t)active.size(), n_threads, [&](int64_t t, int) {
 					ReadState &r = rs[active[t]];
@@ -604,7 +608,8 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				mmb_ksw_res_t *res = bb.h_res.as<mmb_ksw_res_t>((size_t)n_jobs);
 				int64_t cap_tot = 0;
 				for (int64_t i = 0; i < n_jobs; ++i) if (!(jobs[i].flag & MMB_JOB_LL)) cap_tot += (jobs[i].qlen + jobs[i].tlen) / 2 + 8;
-				uint32_t *h_cig = bb.h_cig[wave].as<uint32_t>((size_t)cap_tot + 64);
+				while (bb.h_cig.size() <= (size_t)wave) bb.h_cig.emplace_back(new PinBuf);
+				uint32_t *h_cig = bb.h_cig[wave]->as<uint32_t>((size_t)cap_tot + 64);
 				GateHold gatew(G.gated, 1);
 				lap("  gate wait w");
 				std::vector<int64_t> chunk_base; // offset of each chunk's CIGAR block inside h_cig

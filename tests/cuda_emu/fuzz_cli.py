@@ -60,6 +60,13 @@ def one_(seed):
     if rng.random() < .2: args += ["-s", str(int(rng.choice([20, 40]))), "-m", str(int(rng.choice([20, 30]))), "-n", str(int(rng.choice([2, 3])))]
     if rng.random() < .15: args += ["-K", "1k"]
     if rng.random() < .1: args += ["-g", str(int(rng.choice([200, 1000])))]
+    if nc == 2 and rng.random() < .3:  # the second contig as an ALT haplotype of part of the first
+        m_ = min(len(gs[1]), 3000, len(gs[0]) - 500)
+        gs[1][:m_] = gs[0][500:500 + m_]
+        gs[1][rng.integers(0, m_, max(1, m_ // 100))] = list(rng.choice(list(b"ACGT"), max(1, m_ // 100)))
+        synth.write_fasta(rf, ["c%d" % i for i in range(nc)], [g.tobytes() for g in gs])
+        open(d + "/alt.txt", "w").write("c1\n")
+        args += ["--alt", d + "/alt.txt"] + (["--alt-drop", "0.3"] if rng.random() < .5 else [])
     qarg = [rf, rf] if preset == "ava-ont" and rng.random() < .5 else [rf, qf]
     full = args + qarg
     if os.environ.get("DRY"):

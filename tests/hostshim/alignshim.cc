@@ -111,7 +111,7 @@ mm_reg1_t *hs_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, int qle
 	mm_reg1_t *out = nullptr;
 	int n_out = 0;
 	for (int wave = 0;; ++wave) {
-		if (wave > 16) abort();
+		if (wave > 100000) abort();
 		ra.want.clear(); ra.want_slot.clear();
 		ra.incomplete = false;
 		memcpy(a.data(), a0, sizeof(m128) * n_a);

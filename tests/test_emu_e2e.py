@@ -141,6 +141,23 @@ def _sdust_inputs(d):
     return ["-c", "-T", "20", "-w", "5", rf, qf]
 
 
+def _many_waves_inputs(d):
+    """a case the fuzzing tool found (seed 6017): with -z 30,20 a read keeps being split by z-drop and its alignment needs far more
+    than 16 GPU waves -- the former fixed bound of the scheduler"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_cli", os.path.join(O.ROOT, "tests", "cuda_emu", "fuzz_cli.py"))
+    fz = importlib.util.module_from_spec(spec); spec.loader.exec_module(fz)
+    old = os.environ.get("DRY"); os.environ["DRY"] = "1"
+    try:
+        args = fz.one_(6017)[2].split()
+    finally:
+        if old is None:
+            del os.environ["DRY"]
+        else:
+            os.environ["DRY"] = old
+    return [a for a in args if a != "--qstrand"]
+
+
 def _asm_inputs(d, preset, div):
     import numpy as np
     import synth
@@ -240,6 +257,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["rechain"] = (_rechain_inputs(d), d, True)
         jobs["qstrand"] = (_qstrand_inputs(d), d, True)
         jobs["sdust"] = (_sdust_inputs(d), d, True)
+        jobs["waves"] = (_many_waves_inputs(d), d, True)
         jobs["multipart"] = (_multipart_inputs(d), d, True)
 
     def one(item):
@@ -250,7 +268,7 @@ def emu_runs(emu_cli, tmp_path_factory):
         p = subprocess.run([emu_cli, "-t", "4"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=env)
         return name, dict(rc=p.returncode, err=p.stderr.decode()[-2000:], out=p.stdout.decode().splitlines(), ref=ref)
 
-    order = sorted(jobs.items(), key=lambda kv: {"splice": 0, "splice_junc": 0, "splice_spsc": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
+    order = sorted(jobs.items(), key=lambda kv: {"waves": 0, "splice": 0, "splice_junc": 0, "splice_spsc": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
     with ThreadPoolExecutor(6) as ex:
         return dict(ex.map(one, order))
 
@@ -337,6 +355,14 @@ def test_emulated_sdust_masking_matches_reference(emu_runs):
     r = emu_runs["sdust"]
     assert r["rc"] == 0, r["err"]
     assert r["out"] == r["ref"] and len(r["ref"]) >= 2
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_many_alignment_waves_match_reference(emu_runs):
+    """repeated z-drop splits: more replay / GPU waves than the scheduler used to allow (regression test for a fuzzing find)"""
+    r = emu_runs["waves"]
+    assert r["rc"] == 0, r["err"]
+    assert r["out"] == r["ref"] and len(r["ref"]) >= 1
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

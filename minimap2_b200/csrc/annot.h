@@ -10,11 +10,14 @@
 #include <vector>
 #include <algorithm>
 #include <zlib.h>
+#include "mm_algo.cuh"
 
 typedef struct { // index.c:35-38
 	int32_t st, en, cnt;
 	int32_t score:30, strand:2;
 } mm_idx_intv1_t;
+struct MmxKeyIntvSt { MM_HD uint64_t operator()(const mm_idx_intv1_t &v) const { return (uint64_t)(uint32_t)v.st; } }; // sort_key_bed, index.c:676
+struct MmxKeyIntvEn { MM_HD uint64_t operator()(const mm_idx_intv1_t &v) const { return (uint64_t)(uint32_t)v.en; } }; // sort_key_end, index.c:679
 
 struct mm_idx_intv_s { // index.c:40-43
 	int32_t n, m;
@@ -89,9 +92,18 @@ template<class Name2Id> static inline mm_idx_intv_s *mmx_bed_read(const char *fn
 	for (uint32_t i = 0; i < n_seq; ++i) {
 		mm_idx_intv_s *v = &I[i];
 		n0 += v->n;
-		// (st, en) order; the fields of merged duplicates come from the first of each group, which for a stable sort is the
-		// first in file order -- only score could differ and nothing on the mapping path reads it
-		std::stable_sort(v->a, v->a + v->n, [](const mm_idx_intv1_t &x, const mm_idx_intv1_t &y) { return x.st != y.st? x.st < y.st : x.en < y.en; });
+		// (st, en) order exactly as index.c:776-783 establishes it: radix_sort_bed by st, then radix_sort_end inside each group of
+		// equal st. Both are the unstable American-flag sort of ksort.h:101-151, so which of several identical (st, en) lines
+		// comes first -- and hence whose strand the merged interval keeps -- is defined by that sort's walk; mmx_rs_sort replays it.
+		if (v->n > 1) {
+			std::vector<int32_t> stk((size_t)mmx_rs_stack_len(v->n));
+			mmx_rs_sort(v->a, (int64_t)v->n, stk.data(), MmxKeyIntvSt());
+			for (int32_t j = 1, j0 = 0; j <= v->n; ++j)
+				if (j == v->n || v->a[j].st != v->a[j0].st) {
+					if (j - j0 > 1) mmx_rs_sort(v->a + j0, (int64_t)(j - j0), stk.data(), MmxKeyIntvEn());
+					j0 = j;
+				}
+		}
 		int32_t j, j0, k;
 		for (j = 1, j0 = 0, k = 0; j <= v->n; ++j)
 			if (j == v->n || v->a[j].st != v->a[j0].st || v->a[j].en != v->a[j0].en) {

@@ -8,3 +8,4 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "gpu_ext: GPU test of an option outside the hot-path scope table (run separately: -m gpu_ext)")

@@ -297,6 +297,39 @@ def test_bed_reader_and_junction_flags_match_reference(libs, tmp_path):
     H.hs_bed_free(C.c_void_p(I), 1)
 
 
+def test_bed_reader_unstable_merge_order_matches_reference(libs, tmp_path):
+    """more than 64 lines per contig take the reference's unstable radix sort (index.c:776-783, ksort.h:101-151): of several lines with the
+    same (st, en) but different strands, the one that sort happens to put first names the merged intron's strand. Round 1 used a
+    stable sort here and lost a junction bonus on the device suite (same CIGAR, AS off by 2*junc_bonus)."""
+    H, R, api = libs
+    rng = np.random.default_rng(15)
+    g, reads, introns = _spliced_set(70, 150, glen=800_000)
+    bed = str(tmp_path / "anno.bed")
+    lines = []
+    for st, en, sd in introns:
+        for _ in range(int(rng.integers(1, 4))):  # the same interval on both strands, several times
+            lines.append("chr0\t%d\t%d\tj\t%d\t%s" % (st, en, int(rng.integers(0, 100)), "+-"[int(rng.integers(0, 2))]))
+        if rng.random() < 0.5:  # same start, other ends
+            lines.append("chr0\t%d\t%d\tk\t0\t%s" % (st, en + int(rng.integers(1, 300)), "+-"[int(rng.integers(0, 2))]))
+    order = rng.permutation(len(lines))
+    open(bed, "w").write("".join(lines[i] + "\n" for i in order))
+    assert len(lines) > 300
+    mi, keep = build_ref_index(R, [g], ["chr0"], w=5)
+    R.mm_idx_bed_read(mi, bed.encode(), 1)
+    H.hs_bed_read.restype = C.c_void_p
+    I = H.hs_bed_read(mi, bed.encode(), 1)
+    for _ in range(300):
+        st = int(rng.integers(0, len(g) - 10)); en = min(len(g), st + int(rng.integers(1, 60000)))
+        a = np.zeros(en - st, dtype=np.uint8); b = np.full(en - st, 77, dtype=np.uint8)
+        ra = R.mm_idx_bed_junc(mi, 0, st, en, a.ctypes.data_as(C.c_void_p))
+        rb = H.hs_bed_junc(C.c_void_p(I), 1, 0, st, en, b.ctypes.data_as(C.c_void_p))
+        assert ra == rb and np.array_equal(a, b), (st, en)
+    a = np.zeros(len(g), dtype=np.uint8); b = np.zeros(len(g), dtype=np.uint8)
+    R.mm_idx_bed_junc(mi, 0, 0, len(g), a.ctypes.data_as(C.c_void_p)); H.hs_bed_junc(C.c_void_p(I), 1, 0, 0, len(g), b.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(a, b)
+    H.hs_bed_free(C.c_void_p(I), 1)
+
+
 def test_driver_with_junction_annotation(libs, tmp_path):
     """-x splice --junc-bed: the junction flags reach ksw_exts2 exactly as mm_get_junc / mm_idx_bed_junc pass them (per-call windows,
     reversed for the left extension), for annotated non-canonical introns, decoys next to the true sites and both strands"""

@@ -106,6 +106,15 @@ int main(int argc, char *argv[])
 			else if (*optarg == 'n') opt.flag &= ~(MM_F_SPLICE_FOR | MM_F_SPLICE_REV);
 			else { fprintf(stderr, "[ERROR] unrecognized cDNA direction\n"); return 1; }
 		}
+		else if (c == 'J') { // splice model (main.c:203-208)
+			const int t = atoi(optarg);
+			if (t == 0) opt.flag |= MM_F_SPLICE_OLD;
+			else if (t == 1) opt.flag &= ~MM_F_SPLICE_OLD;
+		}
+		else if (c == 'R' || c == 'j') { // accepted by the reference, not built here: refuse instead of silently ignoring (no read-group / jump-BED support)
+			fprintf(stderr, "[ERROR] option -%c (%s) is not supported by minimap2-b200\n", c, c == 'R'? "SAM read group" : "junction jump BED for short RNA-seq reads");
+			return 1;
+		}
 		else if (c == 'I') ipt.batch_size = parse_num(optarg);
 		else if (c == 'K') opt.mini_batch_size = parse_num(optarg);
 		else if (c == 'e') opt.occ_dist = (int)parse_num(optarg);
@@ -212,6 +221,12 @@ int main(int argc, char *argv[])
 	mm_idx_t *mi;
 	while ((mi = mm_idx_reader_read(idx_rdr, n_threads)) != 0) {
 		int ret = 0;
+		if ((opt.flag & MM_F_CIGAR) && (mi->flag & MM_I_NO_SEQ)) { // main.c:439-443
+			fprintf(stderr, "[ERROR] the prebuilt index doesn't contain sequences.\n");
+			mm_idx_destroy(mi);
+			mm_idx_reader_close(idx_rdr);
+			return 1;
+		}
 		if (fn_bed_junc) { // main.c:467-471
 			mm_idx_bed_read(mi, fn_bed_junc, 1);
 			if (mi->I == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] failed to load the junction BED file\n");

@@ -1,5 +1,6 @@
 // minimap2_b200/csrc/fastx.cc -- see fastx.h
 #include "fastx.h"
+#include <cctype>
 #include <cstring>
 #include <unistd.h>
 
@@ -64,13 +65,13 @@ int FastxReader::next(FastxRecord &r, bool with_qual, bool with_comment)
 	}
 	std::string hdr;
 	readline_(hdr, false);
-	size_t sp = hdr.find_first_of(" \t");
+	// kseq.h: the name ends at the first isspace() character; exactly that one delimiter is consumed and the rest of the line is the comment
+	size_t sp = 0;
+	while (sp < hdr.size() && !isspace((unsigned char)hdr[sp])) ++sp;
+	if (sp == hdr.size()) sp = std::string::npos;
 	r.name = sp == std::string::npos? hdr : hdr.substr(0, sp);
 	r.comment.clear();
-	if (with_comment && sp != std::string::npos) {
-		size_t cs = hdr.find_first_not_of(" \t", sp);
-		if (cs != std::string::npos) r.comment = hdr.substr(cs);
-	}
+	if (with_comment && sp != std::string::npos && sp + 1 < hdr.size()) r.comment = hdr.substr(sp + 1);
 	r.seq.clear(); r.qual.clear();
 	const bool is_fq = last_ == '@';
 	last_ = 0;

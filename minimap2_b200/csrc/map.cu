@@ -606,8 +606,13 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				// the end of the batch, so per-read caches just point into it
 				const int64_t CH = 1 << 20;
 				mmb_ksw_res_t *res = bb.h_res.as<mmb_ksw_res_t>((size_t)n_jobs);
+				// CIGAR arena estimate per job: (qlen+tlen)/2 + 8 operations covers every realistic alignment, the true bound is qlen+tlen
+				// (alternating 1I1D); an overflow is recovered below by rerunning the chunk with the exact size the kernels reported
+				// and growing the host staging buffer. MM_B200_CIG_SHIFT (test hook) shrinks the estimate to force that path.
+				static const int cig_shift = getenv("MM_B200_CIG_SHIFT")? atoi(getenv("MM_B200_CIG_SHIFT")) : 0;
+				auto cig_est = [&](const mmb_ksw_job_t &jb) -> int64_t { return (jb.flag & MMB_JOB_LL)? 0 : (((int64_t)(jb.qlen + jb.tlen) / 2 + 8) >> cig_shift) + 1; };
 				int64_t cap_tot = 0;
-				for (int64_t i = 0; i < n_jobs; ++i) if (!(jobs[i].flag & MMB_JOB_LL)) cap_tot += (jobs[i].qlen + jobs[i].tlen) / 2 + 8;
+				for (int64_t i = 0; i < n_jobs; ++i) cap_tot += cig_est(jobs[i]);
 				while (bb.h_cig.size() <= (size_t)wave) bb.h_cig.emplace_back(new PinBuf);
 				uint32_t *h_cig = bb.h_cig[wave]->as<uint32_t>((size_t)cap_tot + 64);
 				GateHold gatew(G.gated, 1);
@@ -617,7 +622,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				for (int64_t b = 0; b < n_jobs; b += CH) {
 					const int64_t m = std::min(CH, n_jobs - b);
 					int64_t cap = 0;
-					for (int64_t i = 0; i < m; ++i) if (!(jobs[b + i].flag & MMB_JOB_LL)) cap += (jobs[b + i].qlen + jobs[b + i].tlen) / 2 + 8;
+					for (int64_t i = 0; i < m; ++i) cap += cig_est(jobs[b + i]);
 					for (;;) {
 						mmb_ksw_job_t *d_jobs = bb.jobs.as<mmb_ksw_job_t>((size_t)m);
 						mmb_ksw_res_t *d_res = bb.res.as<mmb_ksw_res_t>((size_t)m);
@@ -631,7 +636,17 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 						MMB_CUDA_CHECK(cudaMemcpyAsync(&used, d_used, 8, cudaMemcpyDeviceToHost, ctx->stream));
 						MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 						if ((int64_t)used > cap) { cap = (int64_t)used + 16; continue; } // rare: rerun the chunk with a larger CIGAR arena
-						if (cig_fill + (int64_t)used > cap_tot) { fprintf(stderr, "[ERROR] minimap2_b200: CIGAR staging overflow\n"); abort(); }
+						if (cig_fill + (int64_t)used > cap_tot) { // grow the wave's host staging buffer, keeping the chunks already staged
+							int64_t rest = 0;
+							for (int64_t i = b + m; i < n_jobs; ++i) rest += cig_est(jobs[i]);
+							const int64_t new_tot = cig_fill + (int64_t)used + rest + 64;
+							std::unique_ptr<PinBuf> nb(new PinBuf);
+							uint32_t *np_ = nb->as<uint32_t>((size_t)new_tot + 64);
+							if (cig_fill) memcpy(np_, h_cig, (size_t)cig_fill * 4);
+							bb.h_cig[wave]->release();
+							bb.h_cig[wave] = std::move(nb);
+							h_cig = np_, cap_tot = new_tot;
+						}
 						ctx->last_d2h_bytes += sizeof(mmb_ksw_res_t) * (uint64_t)m + 4ull * used;
 						ctx->last_h2d_bytes += sizeof(mmb_ksw_job_t) * (uint64_t)m;
 						if (ctx->profiling) ctx->prof_bytes[MMB_PROF_KSW] += 4ull * used;

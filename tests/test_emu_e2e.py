@@ -244,6 +244,7 @@ def emu_runs(emu_cli, tmp_path_factory):
     jobs = {}
     for name in GOLDEN:
         jobs[name] = (cases()[name], data, None)
+    jobs["cig_overflow"] = (cases()["x3s_paf_cigar"], data, None, {"MM_B200_CIG_SHIFT": "6"})
     if HAVE_REF:
         jobs["splice"] = (_splice_inputs(d), d, True)
         jobs["splice_junc"] = (_splice_inputs(d, junc=True), d, True)
@@ -261,11 +262,11 @@ def emu_runs(emu_cli, tmp_path_factory):
         jobs["multipart"] = (_multipart_inputs(d), d, True)
 
     def one(item):
-        name, (args, cwd, with_ref) = item
+        name, (args, cwd, with_ref), more_env = item[0], item[1][:3], (item[1][3] if len(item[1]) > 3 else {})
         ref = None
         if with_ref:
             ref = subprocess.run([O.REF_BIN, "-t", "2"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, check=True).stdout.decode().splitlines()
-        p = subprocess.run([emu_cli, "-t", "4"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=env)
+        p = subprocess.run([emu_cli, "-t", "4"] + args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800, env=dict(env, **more_env))
         return name, dict(rc=p.returncode, err=p.stderr.decode()[-2000:], out=p.stdout.decode().splitlines(), ref=ref)
 
     order = sorted(jobs.items(), key=lambda kv: {"waves": 0, "splice": 0, "splice_junc": 0, "splice_spsc": 0, "inv_paf_cigar": 1, "asm20": 2}.get(kv[0], 9))  # longest first
@@ -280,6 +281,15 @@ def test_emulated_pipeline_matches_recorded_reference(emu_runs, name):
     got = [l for l in r["out"] if not l.startswith("@PG")]
     exp = open(os.path.join(GOLD, "expected", name + ".txt")).read().splitlines()
     assert got == exp, (len(got), len(exp), [(a[:200], b[:200]) for a, b in zip(got, exp) if a != b][:2])
+
+
+def test_emulated_cigar_arena_overflow_is_recovered(emu_runs):
+    """the CIGAR arena estimate (qlen+tlen)/2+8 per job is a heuristic; MM_B200_CIG_SHIFT shrinks it 64-fold so that every wave overflows:
+    the chunk is rerun with the size the kernels reported and the host staging buffer grows (it used to abort: ADVICE round 1)"""
+    r = emu_runs["cig_overflow"]
+    assert r["rc"] == 0, r["err"]
+    exp = open(os.path.join(GOLD, "expected", "x3s_paf_cigar.txt")).read().splitlines()
+    assert r["out"] == exp
 
 
 @pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")

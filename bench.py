@@ -1,27 +1,33 @@
 #!/usr/bin/env python
-"""bench.py -- aligned bases/sec of the seed-chain-extend hot path (map-ont, 10 kb reads vs a 3 Gbp reference) on B200.
+"""bench.py -- aligned bases/sec of the seed-chain-extend hot path on B200, next to the unmodified reference on the host CPUs.
 
-  python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA path (one process per GPU)
-  python bench.py --impl reference --gpus N --steps K --warmup W  # the UNMODIFIED reference (oracle/_ref) on the host CPUs
+  python bench.py --gpus N --steps K --warmup W [--workload map-ont|map-hifi|splice|ava-ont]   # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K --warmup W [--workload ...]                 # the UNMODIFIED reference (oracle/_ref)
 
-A "step" is one pass of the whole hot path (mm_sketch -> seeds -> chain -> ksw2 -> hits, i.e. mm_map semantics with -c)
-over one batch of synthetic reads. Workload = BASELINE.json configs[1]: 100k x 10 kb ONT-profile reads vs a 3 Gbp
-uniform-random reference in 24 contigs, `-x map-ont -c`. Data are synthetic (device-side counter-based generator,
-minimap2_b200/csrc/synth.cu); the reference arm maps the same genome (written to FASTA) and a bounded sample of the same reads.
+A "step" is one pass of the whole hot path (mm_sketch -> seeds -> chain -> ksw2 -> hits, i.e. mm_map semantics) over one batch of
+synthetic reads. The default workload is BASELINE.json configs[1]: 100k x 10 kb ONT-profile reads vs a 3 Gbp uniform-random
+reference in 24 contigs, `-x map-ont -c`; --workload selects configs[2..4] (map-hifi -a, splice -c, ava-ont). Data are synthetic
+(device-side counter-based generators, minimap2_b200/csrc/synth.cu); the reference arm maps the same genome (written to FASTA)
+and a bounded sample of the same reads.
 
-JSON line (rank 0): value = whole-job aligned bases/s with the read bases already resident in HBM when the timed region
-starts; e2e = the same metric through the minimap.h-level C-ABI call mm_map_batch() with HOST buffers (H2D of the reads
-and D2H of all results inside the timed region); roofline = the dominant kernel (K3 ksw2 extd2) from CUDA events on the
-launch stream; cpu_baseline = the reference's own CPU code (oracle/_ref/libminimap2_ref.so) on this box's host cores.
+JSON line (rank 0):
+  value        whole-job aligned bases/s with the read bases already resident in HBM when the timed region starts
+  e2e          the same metric through the C-ABI call mm_map_batch() with HOST buffers (H2D of the reads and D2H of all results
+               inside the timed region)
+  file_e2e     the same metric through mm_map_file() -- FASTA parsing, mapping, PAF/SAM formatting and writing, i.e. exactly what
+               the reference arm's number contains (like for like with `--impl reference`)
+  parity       the bounded sample mapped by BOTH arms through mm_map_file(): output lines compared one by one
+  roofline     the dominant kernel (K3 ksw2) from CUDA events on the launch stream + per-stage figures
+  cpu_baseline the reference's own CPU code (oracle/_ref/libminimap2_ref.so) on this box's host cores
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -30,6 +36,24 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+MM_F_CIGAR, MM_F_OUT_SAM, MM_F_OUT_CG = 0x004, 0x008, 0x020
+
+# BASELINE.json configs[1..4] (SURVEY 8d describes the synthetic inputs). err = (rate, substitution share, insertion share).
+WORKLOADS = {
+    "map-ont": dict(preset="map-ont", k=15, w=10, genome_mbp=3000.0, contigs=24, reads=100000, read_len=10000, err=(0.10, 0.40, 0.25),
+                    kind="genomic", out="-c", metric="aligned bases/sec (map-ont, 10 kb reads)",
+                    desc="%d synthetic %d bp ONT-profile reads (10%% err, sub/ins/del 40/25/35) vs synthetic %.0f Mbp reference (24 contigs), -x map-ont -c"),
+    "map-hifi": dict(preset="map-hifi", k=19, w=19, genome_mbp=3000.0, contigs=24, reads=200000, read_len=15000, err=(0.005, 1 / 3., 1 / 3.),
+                     kind="genomic", out="-a", metric="aligned bases/sec (map-hifi, 15 kb reads)",
+                     desc="%d synthetic %d bp HiFi-profile reads (0.5%% err, sub/ins/del 1/1/1) vs synthetic %.0f Mbp reference (24 contigs), -x map-hifi -a"),
+    "splice": dict(preset="splice", k=15, w=5, genome_mbp=3000.0, contigs=24, reads=500000, read_len=2000, err=(0.03, 1 / 3., 1 / 3.),
+                   kind="cdna", out="-c", metric="aligned bases/sec (splice, 2 kb cDNA reads)",
+                   desc="%d synthetic %d bp cDNA reads (exons 100-500 bp over GT..AG introns of 100 bp-50 kb, 3%% err) vs synthetic %.0f Mbp reference (24 contigs), -x splice -c"),
+    "ava-ont": dict(preset="ava-ont", k=15, w=5, genome_mbp=50.0, contigs=1, reads=50000, read_len=20000, err=(0.10, 0.40, 0.25),
+                    kind="ava", out="", metric="aligned bases/sec (ava-ont, 20 kb reads, all-vs-all)",
+                    desc="all-vs-all overlap of %d synthetic %d bp ONT-profile reads (10%% err) drawn from a %.0f Mbp genome, -x ava-ont"),
+}
+
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -37,13 +61,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    # workload knobs (defaults = BASELINE.json configs[1]); smaller values are for development only and are reported in config
-    ap.add_argument("--genome-mbp", type=float, default=3000.0)
-    ap.add_argument("--reads", type=int, default=100000)
-    ap.add_argument("--read-len", type=int, default=10000)
+    ap.add_argument("--workload", default="map-ont", choices=sorted(WORKLOADS))
+    # workload knobs (defaults = the BASELINE.json config); smaller values are for development only and are reported in config
+    ap.add_argument("--genome-mbp", type=float, default=None)
+    ap.add_argument("--reads", type=int, default=None)
+    ap.add_argument("--read-len", type=int, default=None)
     ap.add_argument("--threads", type=int, default=0, help="host threads for orchestration / the reference arm (0 = all cores)")
-    ap.add_argument("--cpu-sample", type=int, default=20000, help="reads in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the bounded CPU sample (0 = sized from a calibration run)")
+    ap.add_argument("--ref-budget-s", type=float, default=100.0, help="wall-clock target for all reference-arm steps together")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-file-e2e", action="store_true")
     return ap.parse_args()
 
 
@@ -102,94 +129,184 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def aligned_bases(n_regs, regs, api):
-    tot = 0
-    for i in np.nonzero(n_regs)[0]:
-        arr = C.cast(C.c_void_p(int(regs[i])), C.POINTER(api.Reg1))
-        for j in range(n_regs[i]):
-            if arr[j].id == arr[j].parent:
-                tot += arr[j].qe - arr[j].qs
-    return tot
+def physical_cores():
+    try:
+        seen = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    seen.add((phys, core))
+                phys = core = None
+        return len(seen) or None
+    except Exception:
+        return None
+
+
+class StdoutTo:
+    """redirects the C-level stdout (fd 1) of this process to a file while a library writes its PAF/SAM records"""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        sys.stdout.flush()
+        C.CDLL(None).fflush(None)
+        self.saved = os.dup(1)
+        fd = os.open(self.path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        os.dup2(fd, 1)
+        os.close(fd)
+        return self
+
+    def __exit__(self, *a):
+        C.CDLL(None).fflush(None)
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def paf_aligned_bases(path, sam=False, all_records=False):
+    """sum of query spans of the primary records (PAF: tp:A:P; SAM: neither secondary nor supplementary... the PAF rule is what the
+    metric defines, SAM output is converted with the CIGAR's query span)"""
+    bases = 0
+    with open(path) as f:
+        for line in f:
+            if sam:
+                if line.startswith("@"):
+                    continue
+                c = line.split("\t", 7)
+                flag = int(c[1])
+                if flag & 4 or flag & 0x100:
+                    continue
+                n, span = 0, 0
+                for ch in c[5]:
+                    if ch.isdigit():
+                        n = n * 10 + ord(ch) - 48
+                    else:
+                        if ch in "MI=X":
+                            span += n
+                        n = 0
+                bases += span
+            elif all_records or "tp:A:P" in line or "tp:A:I" in line:
+                c = line.split("\t", 5)
+                bases += int(c[3]) - int(c[2])
+    return bases
+
+
+def apply_output_flags(mo, wl):
+    if wl["out"] == "-c":
+        mo.flag |= MM_F_CIGAR | MM_F_OUT_CG
+    elif wl["out"] == "-a":
+        mo.flag |= MM_F_CIGAR | MM_F_OUT_SAM
+    else:
+        mo.flag &= ~MM_F_CIGAR
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def reference_lib():
-    from oracle_lib import REF_SO
-    if not os.path.exists(REF_SO):
-        return None
-    L = C.CDLL(REF_SO)
-    return L
+class Reference:
+    """The UNMODIFIED reference (libminimap2_ref.so built from /root/reference by oracle/Makefile; loaded RTLD_LOCAL) through its own
+    public API: mm_idx_reader_read (index build, untimed) and mm_map_file per step."""
+
+    def __init__(self, wl, ref_fa, n_threads, log):
+        from minimap2_b200 import api  # only the ctypes struct mirrors (IdxOpt/MapOpt share the reference's layout)
+        from oracle_lib import REF_SO
+        self.ok = os.path.exists(REF_SO)
+        if not self.ok:
+            return
+        self.api, self.nthr = api, n_threads
+        L = self.L = C.CDLL(REF_SO)
+        L.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
+        L.mm_idx_reader_open.restype = C.c_void_p
+        L.mm_idx_reader_open.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.c_char_p]
+        L.mm_idx_reader_read.restype = C.c_void_p
+        L.mm_idx_reader_read.argtypes = [C.c_void_p, C.c_int]
+        L.mm_idx_reader_close.argtypes = [C.c_void_p]
+        L.mm_mapopt_update.argtypes = [C.POINTER(api.MapOpt), C.c_void_p]
+        L.mm_map_file.restype = C.c_int
+        L.mm_map_file.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(api.MapOpt), C.c_int]
+        L.mm_idx_destroy.argtypes = [C.c_void_p]
+        C.c_int.in_dll(L, "mm_verbose").value = 1
+        self.io, self.mo = api.IdxOpt(), api.MapOpt()
+        L.mm_set_opt(None, C.byref(self.io), C.byref(self.mo))
+        L.mm_set_opt(wl["preset"].encode(), C.byref(self.io), C.byref(self.mo))
+        apply_output_flags(self.mo, wl)
+        t0 = time.time()
+        rdr = L.mm_idx_reader_open(ref_fa.encode(), C.byref(self.io), None)
+        self.mi = L.mm_idx_reader_read(rdr, n_threads)
+        L.mm_idx_reader_close(rdr)
+        L.mm_mapopt_update(C.byref(self.mo), self.mi)
+        self.t_idx = time.time() - t0
+        log("reference index built in %.1fs on %d threads (mid_occ=%d)" % (self.t_idx, n_threads, self.mo.mid_occ))
+
+    def map_file(self, reads_fa, out_path, mini_batch=None, n_threads=None):
+        mo = self.api.MapOpt.from_buffer_copy(self.mo)
+        if mini_batch:
+            mo.mini_batch_size = int(mini_batch)
+        with StdoutTo(out_path):
+            t = time.time()
+            self.L.mm_map_file(self.mi, reads_fa.encode(), C.byref(mo), n_threads or self.nthr)
+            C.CDLL(None).fflush(None)
+            dt = time.time() - t
+        return dt
+
+    def close(self):
+        if self.ok and self.mi:
+            self.L.mm_idx_destroy(self.mi)
+            self.mi = None
 
 
-def run_reference_sample(ref_fa, reads_fa, n_threads, steps=1, warmup=0, log=None):
-    """Times the UNMODIFIED reference (libminimap2_ref.so built from /root/reference by oracle/Makefile) through its own
-    public API: mm_idx_reader_read (index build, untimed) then mm_map_file per step on the sample file. Returns
-    (aligned bases per step, [seconds per timed step], index seconds)."""
-    from minimap2_b200 import api  # only the ctypes struct mirrors (IdxOpt/MapOpt share the reference's layout)
-    L = reference_lib()
-    if L is None:
-        return None
-    L.mm_set_opt.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.POINTER(api.MapOpt)]
-    L.mm_idx_reader_open.restype = C.c_void_p
-    L.mm_idx_reader_open.argtypes = [C.c_char_p, C.POINTER(api.IdxOpt), C.c_char_p]
-    L.mm_idx_reader_read.restype = C.c_void_p
-    L.mm_idx_reader_read.argtypes = [C.c_void_p, C.c_int]
-    L.mm_idx_reader_close.argtypes = [C.c_void_p]
-    L.mm_mapopt_update.argtypes = [C.POINTER(api.MapOpt), C.c_void_p]
-    L.mm_map_file.restype = C.c_int
-    L.mm_map_file.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(api.MapOpt), C.c_int]
-    L.mm_idx_destroy.argtypes = [C.c_void_p]
-    C.c_int.in_dll(L, "mm_verbose").value = 1
-    io, mo = api.IdxOpt(), api.MapOpt()
-    L.mm_set_opt(None, C.byref(io), C.byref(mo))
-    L.mm_set_opt(b"map-ont", C.byref(io), C.byref(mo))
-    mo.flag |= 0x004 | 0x020  # -c
-    t0 = time.time()
-    rdr = L.mm_idx_reader_open(ref_fa.encode(), C.byref(io), None)
-    mi = L.mm_idx_reader_read(rdr, n_threads)
-    L.mm_idx_reader_close(rdr)
-    L.mm_mapopt_update(C.byref(mo), mi)
-    t_idx = time.time() - t0
-    if log:
-        log("reference index built in %.1fs (mid_occ=%d)" % (t_idx, mo.mid_occ))
-    times, bases = [], 0
-    out_path = reads_fa + ".ref.paf"
-    for it in range(warmup + steps):
-        sys.stdout.flush()
-        saved = os.dup(1)
-        fd = os.open(out_path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
-        os.dup2(fd, 1)
-        t = time.time()
-        L.mm_map_file(mi, reads_fa.encode(), C.byref(mo), n_threads)
-        libc = C.CDLL(None)
-        libc.fflush(None)
-        dt = time.time() - t
-        os.dup2(saved, 1)
-        os.close(fd); os.close(saved)
-        if it >= warmup:
-            times.append(dt)
-    bases = 0
-    with open(out_path) as f:
-        for line in f:
-            c = line.split("\t", 13)
-            if "tp:A:P" in line:
-                bases += int(c[3]) - int(c[2])
-    L.mm_idx_destroy(mi)
-    return bases, times, t_idx
+def write_reads_fasta(path, buf, read_len, lo, hi):
+    with open(path, "wb") as f:
+        for i in range(lo, hi):
+            f.write(b">r%d\n" % i)
+            f.write(buf[i * read_len:(i + 1) * read_len].tobytes())
+            f.write(b"\n")
+
+
+def gen_reads(L, idx, wl, n, read_len, seed, buf):
+    if wl["kind"] == "cdna":
+        L.mmb_synth_cdna_reads(idx, n, read_len, seed, wl["err"][0], buf.ctypes.data)
+    else:
+        L.mmb_synth_reads(idx, n, read_len, seed, wl["err"][0], wl["err"][1], wl["err"][2], buf.ctypes.data)
+
+
+def compare_outputs(a_path, b_path, log, sam=False):
+    def lines(p):
+        with open(p) as f:
+            return [l.rstrip("\n") for l in f if not (sam and l.startswith("@"))]
+    a, b = lines(a_path), lines(b_path)
+    mism = abs(len(a) - len(b))
+    shown = 0
+    for x, y in zip(a, b):
+        if x != y:
+            mism += 1
+            if shown < 3:
+                log("parity mismatch:\n  ref: %s\n  got: %s" % (x[:300], y[:300]))
+                shown += 1
+    return len(a), len(b), mism
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 def main():
     a = parse_args()
+    wl = dict(WORKLOADS[a.workload])
+    for key, val in (("genome_mbp", a.genome_mbp), ("reads", a.reads), ("read_len", a.read_len)):
+        if val is not None:
+            wl[key] = val
+    n_reads, read_len, genome_mbp = int(wl["reads"]), int(wl["read_len"]), float(wl["genome_mbp"])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_threads_all = os.cpu_count() or 1
     nthr = a.threads or max(1, n_threads_all // max(1, world))
-    cfg = {"workload": "map-ont: %d synthetic %d bp ONT-profile reads (10%% err, sub/ins/del 40/25/35) vs synthetic %.0f Mbp reference "
-                       "(24 contigs), -x map-ont -c" % (a.reads, a.read_len, a.genome_mbp),
-           "preset": "map-ont", "k": 15, "w": 10, "reads_per_step_per_gpu": a.reads, "read_len": a.read_len,
-           "genome_mbp": a.genome_mbp, "host_threads": nthr,
+    sam = wl["out"] == "-a"
+    ava = wl["kind"] == "ava"  # all-vs-all overlap: no hit is marked primary (tp:A:S everywhere), every record counts
+    # identical in both arms (the driver compares it); everything arm-specific lives in cpu_baseline / e2e / host
+    cfg = {"workload": a.workload + ": " + wl["desc"] % (n_reads, read_len, genome_mbp), "preset": wl["preset"], "k": wl["k"], "w": wl["w"],
+           "reads_per_step_per_gpu": n_reads, "read_len": read_len, "genome_mbp": genome_mbp,
            "l2_policy": "inputs larger than L2 (>=1 GB of read bases + multi-GB index touched every step)"}
 
     def log(msg):
@@ -199,62 +316,101 @@ def main():
     os.environ["MM_B200_DEVICE"] = str(local_rank)
     import torch
     dist_on = world > 1
-    if a.impl == "reference":
-        if rank != 0:
-            return 0
-        import minimap2_b200 as mb
-        from minimap2_b200 import api
-        L = api._setup()
-        tmp = tempfile.mkdtemp(prefix="mm2bench_")
-        log("generating the synthetic genome/reads for the reference arm")
-        idx = L.mmb_synth_index(int(a.genome_mbp * 1e6), 24, 11, 10, 15, 14)
-        ref_fa, reads_fa = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "sample.fa")
-        L.mmb_idx_write_fasta(idx, ref_fa.encode())
-        ns = min(a.cpu_sample, a.reads)
-        buf = np.zeros(ns * a.read_len, dtype=np.uint8)
-        L.mmb_synth_reads(idx, ns, a.read_len, 12, 0.10, 0.40, 0.25, buf.ctypes.data)
-        with open(reads_fa, "wb") as f:
-            for i in range(ns):
-                f.write(b">r%d\n" % i); f.write(buf[i * a.read_len:(i + 1) * a.read_len].tobytes()); f.write(b"\n")
-        L.mm_idx_destroy(idx)
-        res = run_reference_sample(ref_fa, reads_fa, n_threads_all, steps=a.steps, warmup=a.warmup, log=log)
-        if res is None:
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libminimap2_ref.so missing"}))
-            return 0
-        bases, times, t_idx = res
-        tot_t = sum(times)
-        val = bases * len(times) / tot_t
-        line = {"metric": "aligned bases/sec (map-ont, 10 kb reads)", "value": val, "unit": "bases/s", "n_gpus": a.gpus, "steps": a.steps,
-                "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8/int32", "data": "synthetic", "impl": "reference", "config": dict(cfg, sample_reads=ns, cpu_threads=n_threads_all),
-                "cpu_baseline": {"value": val, "unit": "bases/s", "cores": n_threads_all, "kind": "reference",
-                                 "sample": "%d of the %d reads per step, same 3 Gbp reference; mm_map_file() wall time, index build (%.0fs) excluded" % (ns, a.reads, t_idx)},
-                "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+    if a.impl == "reference" and rank != 0:
         return 0
-
-    # ---------------- this repo's arm ----------------
-    if dist_on:
+    if dist_on and a.impl != "reference":
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     # host worker pool per rank: half of this rank's share of the logical CPUs (the group threads that feed the GPU need idle cores)
     os.environ.setdefault("MM_B200_HOST_THREADS", str(max(8, n_threads_all // (2 * max(1, world)))))
-    import minimap2_b200 as mb
+    import minimap2_b200 as mb  # noqa: F401
     from minimap2_b200 import api
     L = api._setup()
+    L.mmb_synth_cdna_reads.restype = C.c_int
+    L.mmb_synth_cdna_reads.argtypes = [C.POINTER(api.Idx), C.c_int, C.c_int, C.c_uint64, C.c_float, C.c_void_p]
+    L.mmb_aligned_bases.restype = C.c_int64
+    L.mmb_aligned_bases.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    L.mm_map_file.restype = C.c_int
+    L.mm_map_file.argtypes = [C.POINTER(api.Idx), C.c_char_p, C.POINTER(api.MapOpt), C.c_int]
+    tmp = tempfile.mkdtemp(prefix="mm2bench_")
+    ref_fa, sample_fa, full_fa = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "sample.fa"), os.path.join(tmp, "reads.fa")
+
+    # ---------------- data + index (untimed) ----------------
     t0 = time.time()
     # Every rank builds the same index deterministically on its own GPU from the seed (the device build takes seconds).
     # A loaded (non-synthetic) index is broadcast instead: see minimap2_b200/dist.py (NCCL broadcast of the device arrays).
-    idx = L.mmb_synth_index(int(a.genome_mbp * 1e6), 24, 11, 10, 15, 14)
-    log("index built on device in %.1fs" % (time.time() - t0))
-    al = api.Aligner(preset="map-ont", _idx=idx, n_threads=nthr)
-    al.map_opt.flag |= api.MM_F_CIGAR | api.MM_F_OUT_CG
-    buf = np.zeros(a.reads * a.read_len, dtype=np.uint8)
-    L.mmb_synth_reads(idx, a.reads, a.read_len, 12 + 1000 * rank, 0.10, 0.40, 0.25, buf.ctypes.data)
-    qlens = np.full(a.reads, a.read_len, dtype=np.int32)
-    names = ["r%d" % i for i in range(a.reads)]
-    ctx = L.mmb_default_ctx_c()
+    gidx = L.mmb_synth_index(int(genome_mbp * 1e6), int(wl["contigs"]), 11, wl["w"], wl["k"], 14)
+    buf = np.zeros(n_reads * read_len, dtype=np.uint8)
+    gen_reads(L, gidx, wl, n_reads, read_len, 12 + 1000 * (rank if a.impl != "reference" else 0), buf)
+    names = ["r%d" % i for i in range(n_reads)]
+    if wl["kind"] == "ava":  # the index IS the read set
+        write_reads_fasta(full_fa, buf, read_len, 0, n_reads)
+        L.mm_idx_destroy(gidx)
+        gidx = None
+        ref_fa = full_fa
+    log("synthetic genome + reads ready in %.1fs" % (time.time() - t0))
+
+    def make_aligner():
+        if wl["kind"] == "ava":
+            al_ = api.Aligner(fn_idx_in=full_fa, preset=wl["preset"], n_threads=nthr)
+        else:
+            al_ = api.Aligner(preset=wl["preset"], _idx=gidx, n_threads=nthr)
+        al_.map_opt.flag &= ~MM_F_CIGAR  # the Aligner class follows mappy (CIGAR on); the bench follows the CLI flags of the config
+        apply_output_flags(al_.map_opt, wl)
+        return al_
+
+    # =====================================================================================================================
+    if a.impl == "reference":
+        if gidx is not None:
+            L.mmb_idx_write_fasta(gidx, ref_fa.encode())
+            L.mm_idx_destroy(gidx)
+        R = Reference(wl, ref_fa, n_threads_all, log)
+        if not R.ok:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libminimap2_ref.so missing"}))
+            return 0
+        # size the per-step sample from a calibration run so that all steps together take about --ref-budget-s
+        ns = a.cpu_sample
+        if ns <= 0:
+            nc = min(n_reads, max(256, int(3e7 // read_len)))
+            write_reads_fasta(sample_fa, buf, read_len, 0, nc)
+            dt = R.map_file(sample_fa, sample_fa + ".paf")
+            rate = nc / max(dt, 1e-3)
+            ns = int(min(n_reads, max(nc, rate * a.ref_budget_s / max(1, a.steps + a.warmup))))
+            log("calibration: %d reads in %.2fs -> %d reads per step" % (nc, dt, ns))
+        write_reads_fasta(sample_fa, buf, read_len, 0, ns)
+        mini = max(1, int(math.ceil(ns * read_len / 3.0))) if ns * read_len < 3 * R.mo.mini_batch_size else None  # >= 3 mini-batches => the reference's read/map/write steps overlap
+        times = []
+        for it in range(a.warmup + a.steps):
+            dt = R.map_file(sample_fa, sample_fa + ".ref.out", mini_batch=mini)
+            if it >= a.warmup:
+                times.append(dt)
+        bases = paf_aligned_bases(sample_fa + ".ref.out", sam, ava)
+        # single-thread figure on a small sample (per-core rate)
+        n1 = min(ns, max(64, int(3e6 // read_len)))
+        write_reads_fasta(sample_fa + ".t1", buf, read_len, 0, n1)
+        dt1 = R.map_file(sample_fa + ".t1", sample_fa + ".t1.out", n_threads=1)
+        b1 = paf_aligned_bases(sample_fa + ".t1.out", sam, ava)
+        R.close()
+        tot_t = sum(times)
+        val = bases * len(times) / tot_t
+        sample = ("%d of the %d reads per step (%d mini-batches of -K %s), same reference; mm_map_file() wall time incl. FASTA parsing and %s writing, "
+                  "index build (%.0fs) excluded" % (ns, n_reads, 3 if mini else int(math.ceil(ns * read_len / R.mo.mini_batch_size)), mini or R.mo.mini_batch_size,
+                                                   "SAM" if sam else "PAF", R.t_idx))
+        line = {"metric": wl["metric"], "value": val, "unit": "bases/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int8 DP cells (int32 scores), u64 hashes, f32 chain penalties", "data": "synthetic", "impl": "reference", "config": cfg,
+                "cpu_baseline": {"value": val, "unit": "bases/s", "cores": n_threads_all, "logical_cpus": n_threads_all, "physical_cores": physical_cores(),
+                                 "kind": "reference", "sample": sample, "sample_reads": ns,
+                                 "t1": {"value": b1 / dt1, "unit": "bases/s", "cores": 1, "sample": "%d reads, -t 1" % n1}},
+                "e2e": {"value": val, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # =====================================================================================================================
+    # ---------------- this repo's arm ----------------
+    al = make_aligner()
+    qlens = np.full(n_reads, read_len, dtype=np.int32)
     prepared = al.prepare_batch(buf, qlens, names)
 
     def barrier():
@@ -271,7 +427,7 @@ def main():
             n_regs, regs, rep = al.map_prepared(prepared)
             torch.cuda.synchronize()
             times.append(time.perf_counter() - t)
-            bases = aligned_bases(n_regs, regs, api)
+            bases = int(L.mmb_aligned_bases(n_reads, n_regs.ctypes.data, regs.ctypes.data, 1 if wl["kind"] == "ava" else 0))
             al.free_batch(n_regs, regs)
         return bases, times
 
@@ -291,8 +447,30 @@ def main():
     bases_b, times_b = run_steps(a.steps, False)
     barrier()
     t_b = sum(times_b)
+    d2h_bytes = int(L.mmb_last_d2h_bytes())
     clocks = sampler.stop()
-    # --- per-kernel device time for the roofline: one extra step with the read groups serialised (one stream), so that
+    # --- timed region C (rank 0's own figure is reported; every rank runs it so that the host is loaded as in production):
+    #     `file_e2e` = mm_map_file(): FASTA in (page cache), PAF/SAM out (tmpfs) -- what the reference arm's number contains ---
+    file_e2e = None
+    if not a.no_file_e2e:
+        if wl["kind"] != "ava":
+            write_reads_fasta(full_fa, buf, read_len, 0, n_reads)
+        out_full = full_fa + ".out"
+        tf = []
+        barrier()
+        for it in range(2):
+            with StdoutTo(out_full):
+                t = time.perf_counter()
+                L.mm_map_file(al._idx, full_fa.encode(), C.byref(al.map_opt), nthr)
+                C.CDLL(None).fflush(None)
+                tf.append(time.perf_counter() - t)
+        barrier()
+        fb = paf_aligned_bases(out_full, sam, ava)
+        file_e2e = {"value": fb / tf[-1], "unit": "bases/s", "ms_per_step": 1e3 * tf[-1], "per_gpu": True,
+                    "what": "mm_map_file(): %d reads from FASTA (page cache) -> %s on tmpfs, second of two runs; reader / GPU scheduler / writer overlapped (map.cu)" % (n_reads, "SAM" if sam else "PAF"),
+                    "in_bytes": os.path.getsize(full_fa), "out_bytes": os.path.getsize(out_full)}
+        os.unlink(out_full)
+    # --- per-kernel device time for the roofline: extra steps with the read groups serialised (one stream), so that
     #     CUDA-event durations are not inflated by kernels of other groups sharing the SMs ---
     L.mmb_set_groups(-int(os.environ.get("MM_B200_GROUPS", "12")))  # the default group count, run one after another
     L.mmb_profile_enable_all(1)
@@ -320,18 +498,22 @@ def main():
         if dist_on:
             dist.destroy_process_group()
         return 0
-    # --- roofline of the dominant kernel (K3) ---
+    # --- roofline of the dominant kernel (K3; for ava-ont, which runs no ksw2, the chaining stage) ---
     peak, peak_src = measured_peaks()
-    k = prof["ksw"]
-    n_launch_ksw = max(1, k["scopes"])
-    ksw_gbs = (k["bytes"] / 1e9) / (k["ms"] / 1e3) if k["ms"] > 0 else 0.0
-    roofline = {"kernel": "K3 ksw2 kernels (ksw_pk_kernel + ksw_extd2_kernel)", "bound": "hbm", "achieved": ksw_gbs, "peak": peak, "unit": "GB/s", "frac": ksw_gbs / peak,
+    dom = "ksw" if prof["ksw"]["ms"] > 0 else "chain"
+    k = prof[dom]
+    n_launch_k = max(1, k["scopes"])
+    k_gbs = (k["bytes"] / 1e9) / (k["ms"] / 1e3) if k["ms"] > 0 else 0.0
+    roofline = {"kernel": "K3 ksw2 kernels (ksw_pk_kernel + ksw_extd2_kernel)" if dom == "ksw" else "K2c chaining kernels (chain_fill + backtrack)",
+                "bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak,
                 "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": k["bytes"] / n_launch_ksw, "avg_launch_ms": k["ms"] / n_launch_ksw,
-                "gcups": (k["units"] / 1e9) / (k["ms"] / 1e3) if k["ms"] > 0 else 0.0,
-                "note": "ALU-bound by construction: ~%.0f DP cells per read base at 1 B/cell traceback; HBM fraction is expected to be small (SURVEY 8d)" % (k["units"] / max(1.0, tot_bases_a / max(1, world) * n_prof)),
+                "algorithmic_bytes_per_launch": k["bytes"] / n_launch_k, "avg_launch_ms": k["ms"] / n_launch_k,
                 "stage_ms_per_step": {nm: prof[nm]["ms"] / n_prof for nm in prof},
                 "timing": "CUDA events on the launch stream, %d profiled steps with the scheduler's read groups serialised" % n_prof}
+    if dom == "ksw":
+        roofline["gcups"] = (k["units"] / 1e9) / (k["ms"] / 1e3) if k["ms"] > 0 else 0.0
+        roofline["note"] = ("integer-pipe bound by construction: ~%.0f DP cells per read base at 1 B/cell (traceback) algorithmic bytes; the HBM fraction is expected "
+                            "to be small (SURVEY 8d)" % (k["units"] / max(1.0, tot_bases_a / max(1, world) * n_prof)))
     try:  # per-stage algorithmic bandwidth (DESIGN.md section 3 definitions); informational, never allowed to break the line
         roofline["stages"] = {nm: {"ms_per_step": prof[nm]["ms"] / n_prof, "algorithmic_gb_per_step": prof[nm]["bytes"] / n_prof / 1e9,
                                    "gb_per_s": (prof[nm]["bytes"] / 1e9) / (prof[nm]["ms"] / 1e3) if prof[nm]["ms"] > 0 else 0.0,
@@ -340,42 +522,64 @@ def main():
     except Exception:
         pass
     tp = os.path.join(ROOT, "profiles", "ksw_traffic.json")
-    if os.path.exists(tp):
-        try:
-            roofline["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+    if dom == "ksw" and a.workload == "map-ont" and os.path.exists(tp):
+        try:  # dram__bytes of the K3 launches from the committed `ncu --set full` capture of this command (profiles/README.md says which run)
+            tj = json.load(open(tp))
+            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = tj.get("source", "profiles/ksw_traffic.json")
         except Exception:
             pass
-    line = {"metric": "aligned bases/sec (map-ont, 10 kb reads)", "value": value, "unit": "bases/s", "n_gpus": world, "steps": a.steps,
+    line = {"metric": wl["metric"], "value": value, "unit": "bases/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_a / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 DP cells (int32 scores), u64 hashes, f32 chain penalties", "data": "synthetic", "config": cfg,
+            "host": {"threads_per_rank": nthr, "logical_cpus": n_threads_all, "physical_cores": physical_cores(), "pool_threads": int(os.environ["MM_B200_HOST_THREADS"])},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e, "unit": "bases/s", "ms_per_step": 1e3 * t_b / a.steps,
-                    "h2d_bytes_per_step": int(a.reads * a.read_len + 12 * a.reads), "d2h_bytes_per_step": int(L.mmb_last_d2h_bytes())},
+                    "h2d_bytes_per_step": int(n_reads * read_len + 12 * n_reads), "d2h_bytes_per_step": d2h_bytes},
             "roofline": roofline}
-    # --- CPU baseline: the reference's own code on this box's cores, bounded sample ---
+    if file_e2e:
+        line["file_e2e"] = file_e2e
+    # --- CPU baseline + parity: the reference's own code on this box's cores, bounded sample, both arms through mm_map_file ---
     if not a.no_cpu_baseline:
         try:
-            tmp = tempfile.mkdtemp(prefix="mm2bench_")
-            ref_fa, reads_fa = os.path.join(tmp, "ref.fa"), os.path.join(tmp, "sample.fa")
-            log("writing the reference FASTA for the CPU baseline")
-            L.mmb_idx_write_fasta(idx, ref_fa.encode())
-            ns = min(a.cpu_sample, a.reads)
-            with open(reads_fa, "wb") as f:
-                for i in range(ns):
-                    f.write(b">r%d\n" % i); f.write(buf[i * a.read_len:(i + 1) * a.read_len].tobytes()); f.write(b"\n")
+            ns = min(a.cpu_sample or max(2000, int(2e8 // read_len)), n_reads)
+            write_reads_fasta(sample_fa, buf, read_len, 0, ns)
+            mini = max(1, int(math.ceil(ns * read_len / 3.0)))
+            mo = api.MapOpt.from_buffer_copy(al.map_opt)
+            mo.mini_batch_size = mini
+            with StdoutTo(sample_fa + ".b200.out"):
+                L.mm_map_file(al._idx, sample_fa.encode(), C.byref(mo), nthr)
+                C.CDLL(None).fflush(None)
+            if gidx is not None:
+                log("writing the reference FASTA for the CPU baseline")
+                L.mmb_idx_write_fasta(gidx, ref_fa.encode())
+            mid_occ_mine = int(al.map_opt.mid_occ)
             al.close()
-            idx = None
-            res = run_reference_sample(ref_fa, reads_fa, n_threads_all, steps=1, warmup=0, log=log)
-            if res is not None:
-                cb, ct, t_idx = res
-                line["cpu_baseline"] = {"value": cb / ct[0], "unit": "bases/s", "cores": n_threads_all, "kind": "reference",
-                                        "sample": "%d of the %d reads of one step vs the same reference; mm_map_file() wall %.2fs (index build %.0fs excluded)" % (ns, a.reads, ct[0], t_idx)}
-            for fn in (ref_fa, reads_fa, reads_fa + ".ref.paf"):
-                if os.path.exists(fn):
-                    os.unlink(fn)
+            gidx = None
+            R = Reference(wl, ref_fa, n_threads_all, log)
+            if R.ok:
+                ct = R.map_file(sample_fa, sample_fa + ".ref.out", mini_batch=mini)
+                cb = paf_aligned_bases(sample_fa + ".ref.out", sam, ava)
+                n_ref, n_got, mism = compare_outputs(sample_fa + ".ref.out", sample_fa + ".b200.out", log, sam)
+                line["parity"] = {"reads": ns, "ref_lines": n_ref, "b200_lines": n_got, "mismatches": mism, "mid_occ": [int(R.mo.mid_occ), mid_occ_mine],
+                                  "what": "the same %d-read sample through mm_map_file() of both libraries, every %s record compared as text" % (ns, "SAM" if sam else "PAF")}
+                n1 = min(ns, max(64, int(3e6 // read_len)))
+                write_reads_fasta(sample_fa + ".t1", buf, read_len, 0, n1)
+                dt1 = R.map_file(sample_fa + ".t1", sample_fa + ".t1.out", n_threads=1)
+                b1 = paf_aligned_bases(sample_fa + ".t1.out", sam, ava)
+                line["cpu_baseline"] = {"value": cb / ct, "unit": "bases/s", "cores": n_threads_all, "logical_cpus": n_threads_all, "physical_cores": physical_cores(),
+                                        "kind": "reference",
+                                        "sample": "%d of the %d reads of one step (3 mini-batches) vs the same reference; mm_map_file() wall %.2fs incl. parsing and output (index build %.0fs excluded)" % (ns, n_reads, ct, R.t_idx),
+                                        "t1": {"value": b1 / dt1, "unit": "bases/s", "cores": 1, "sample": "%d reads, -t 1" % n1}}
+                R.close()
         except Exception as e:  # the baseline is reported, never required for the GPU number
             line["cpu_baseline"] = {"value": None, "unit": "bases/s", "cores": n_threads_all, "kind": "reference", "sample": "failed: %r" % (e,)}
     print(json.dumps(line))
+    try:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    except Exception:
+        pass
     if dist_on:
         dist.destroy_process_group()
     return 0

@@ -189,6 +189,8 @@ const void *mmb_idx_cnt_sorted(const mm_idx_t *mi, uint64_t *bytes); /* sorted o
 mm_idx_t *mmb_synth_index(uint64_t total_len, int n_contigs, uint64_t seed, int w, int k, int bucket_bits);
 int mmb_synth_reads(const mm_idx_t *mi, int n_reads, int read_len, uint64_t seed, float err, float sub, float ins, char *out);
 int mmb_idx_write_fasta(const mm_idx_t *mi, const char *fn); /* dump the indexed sequences (to feed the reference arm) */
+int mmb_synth_cdna_reads(const mm_idx_t *mi, int n_reads, int read_len, uint64_t seed, float err, char *out); /* spliced transcripts: exons joined over GT..AG introns */
+int64_t mmb_aligned_bases(int n, const int32_t *n_regs, mm_reg1_t *const *regs, int all_records); /* sum of qe-qs over primary (or all) hits: bench metric */
 
 #ifdef __cplusplus
 }

@@ -78,9 +78,17 @@ int FastxReader::next(FastxRecord &r, bool with_qual, bool with_comment)
 	std::string line;
 	while ((c = peek_()) >= 0 && c != '>' && c != '+' && c != '@') {
 		readline_(line, false);
-		for (char ch : line) if (ch > ' ') r.seq.push_back(ch); // kseq keeps graph characters only
+		// kseq keeps graph characters only; lines are almost always clean, so test first (vectorisable) and append in one go
+		bool clean = true;
+		for (char ch : line) clean &= ch > ' ';
+		if (clean) r.seq.append(line);
+		else for (char ch : line) if (ch > ' ') r.seq.push_back(ch);
 	}
-	for (char &ch : r.seq) if (ch == 'u' || ch == 'U') --ch;
+	{
+		bool has_u = false;
+		for (char ch : r.seq) has_u |= (ch == 'u') | (ch == 'U');
+		if (has_u) for (char &ch : r.seq) if (ch == 'u' || ch == 'U') --ch;
+	}
 	if (c == '>' || c == '@') { getc_(); last_ = c; }
 	if (c != '+') return 1;
 	// quality block

@@ -46,7 +46,7 @@ extern "C" void mmb_ctx_destroy(mmb_ctx_t *c)
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->d_a.release(); c->d_b.release(); c->d_c.release(); c->d_d.release();
-	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release(); c->d_junc.release(); c->d_spsc[0].release(); c->d_spsc[1].release();
+	c->d_e.release(); c->d_f.release(); c->d_g.release(); c->d_h.release(); c->sk_pk.release(); c->sk_nm.release(); c->sk_misc.release(); c->scan_sums.release(); c->d_junc.release(); c->d_spsc[0].release(); c->d_spsc[1].release();
 	cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
 	cudaStreamDestroy(c->stream);
 	delete c;

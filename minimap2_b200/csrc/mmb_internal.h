@@ -70,6 +70,7 @@ struct mmb_ctx_s {
 	uint64_t last_d2h_bytes = 0, last_h2d_bytes = 0;
 	// scratch used by the kernel-level host entry points
 	DevBuf d_a, d_b, d_c, d_d, d_e, d_f, d_g, d_h;
+	DevBuf sk_pk, sk_nm, sk_misc, scan_sums;   // stage scratch that lives with the context (2-bit bases / ambiguity bits / tile chaining of K1; tile sums of the scans)
 	// annotated introns for the spliced kernel (mm_idx_bed_junc semantics, index.c:802-826), sorted by start, in the coordinates
 	// of the target array the jobs address: first base, one past the last base, strand (+1/-1). Null: no annotation.
 	const int64_t *junc_st = nullptr, *junc_en = nullptr; const int8_t *junc_strand = nullptr; int64_t n_junc = 0;

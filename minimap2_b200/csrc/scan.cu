@@ -61,7 +61,7 @@ void mmb_exclusive_scan_i64_async(mmb_ctx_t *ctx, int64_t *d, int64_t n)
 {
 	if (n <= 0) { MMB_CUDA_CHECK(cudaMemsetAsync(d, 0, sizeof(int64_t), ctx->stream)); return; }
 	const int64_t n_tiles = (n + TILE - 1) / TILE;
-	static thread_local DevBuf sums; // small; one per host thread
+	DevBuf &sums = ctx->scan_sums;
 	int64_t *ts = sums.as<int64_t>((size_t)n_tiles + 1);
 	scan_tile_kernel<<<(unsigned)n_tiles, 256, 0, ctx->stream>>>(d, n, ts, 0);
 	scan_sums_kernel<<<1, 256, 0, ctx->stream>>>(ts, n_tiles, d, n);

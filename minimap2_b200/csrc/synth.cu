@@ -5,6 +5,7 @@
 #include "index.h"
 #include "mm_algo.cuh"
 #include <cstring>
+#include <cmath>
 #include <string>
 
 namespace {
@@ -73,6 +74,68 @@ __global__ void reads_kernel(ReadGenArgs A)
 			o[idx] = "ACGT"[b];
 			++n;
 		}
+	}
+}
+
+// cDNA reads (SURVEY 8d "splice"): a transcript is a run of exons (100-500 bp) separated by introns (log-uniform 100 bp - 50 kb) whose
+// first two / last two bases are GT / AG on the genome's forward strand (the exon is extended base by base until the genome offers the
+// signal, so the genome itself is not edited); the read is the first read_len transcript bases with 3% errors (sub/ins/del 1:1:1),
+// reverse-complemented for every other read (those introns then read CT..AC, the other transcript strand).
+__global__ void cdna_reads_kernel(ReadGenArgs A)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= A.n_reads) return;
+	uint64_t h = mix64(A.seed ^ (0x5151F00DULL * (uint64_t)(r + 1)));
+	const uint64_t span = 600000; // room for the read plus its introns inside one contig
+	uint64_t start = 0, end = 0;
+	for (int tries = 0; tries < 64; ++tries) {
+		h = mix64(h);
+		uint64_t g = h % A.total;
+		uint32_t lo = 0, hi = A.n_seq;
+		while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (A.seq_off[mid] <= g) lo = mid; else hi = mid; }
+		end = A.seq_off[lo] + A.seq_len[lo];
+		if (g + span <= end) { start = g; break; }
+		start = A.seq_off[lo];
+	}
+	h = mix64(h);
+	const bool rev = h & 1;
+	char *o = A.out + (size_t)r * A.read_len;
+	uint64_t p = start;
+	int n = 0;
+	const uint32_t te = (uint32_t)(A.err * 16777216.0f), ts = te / 3, ti = 2 * (te / 3);
+	while (n < A.read_len) {
+		h = mix64(h + p);
+		int exon_left = 100 + (int)(h % 401);
+		// exon bases, extended until the genome shows GT right after the exon
+		while (n < A.read_len && p + 4 < end) {
+			if (exon_left <= 0 && (mmx_seq4_get(A.S, p) & 3) == 2 && (mmx_seq4_get(A.S, p + 1) & 3) == 3) break;
+			--exon_left;
+			h = mix64(h + p);
+			const uint32_t u = (uint32_t)(h & 0xffffff);
+			const uint32_t c = mmx_seq4_get(A.S, p) & 3;
+			int emit = -1;
+			if (u >= te) emit = c, ++p;
+			else if (u < ts) emit = (c + 1 + ((h >> 24) % 3)) & 3, ++p;
+			else if (u < ti) emit = (h >> 24) & 3;
+			else ++p;
+			if (emit >= 0) {
+				const int idx = rev? A.read_len - 1 - n : n;
+				o[idx] = "ACGT"[rev? 3 - emit : emit];
+				++n;
+			}
+		}
+		if (n >= A.read_len) break;
+		if (p + 4 >= end) { // ran out of contig (practically unreachable with span): pad with A
+			while (n < A.read_len) { o[rev? A.read_len - 1 - n : n] = 'A'; ++n; }
+			break;
+		}
+		// intron: log-uniform length, its end moved right until the genome shows AG
+		h = mix64(h + p);
+		const float uu = (float)(h & 0xffffff) / 16777216.0f;
+		uint64_t q = p + (uint64_t)(100.0f * expf(uu * 6.2146f)); // 100 .. 50 000
+		while (q + 4 < end && !((mmx_seq4_get(A.S, q - 2) & 3) == 0 && (mmx_seq4_get(A.S, q - 1) & 3) == 2)) ++q;
+		if (q + 4 >= end) q = p; // no room: no intron
+		p = q;
 	}
 }
 
@@ -153,4 +216,37 @@ extern "C" int mmb_idx_write_fasta(const mm_idx_t *mi, const char *fn)
 	}
 	fclose(fp);
 	return 0;
+}
+
+// cDNA reads for the spliced workload (see cdna_reads_kernel); same output layout as mmb_synth_reads.
+extern "C" int mmb_synth_cdna_reads(const mm_idx_t *mi, int n_reads, int read_len, uint64_t seed, float err, char *out)
+{
+	mm_idx_bucket_s *B = mi->B;
+	mmb_ctx_t *ctx = B->ctx;
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	ReadGenArgs A;
+	uint64_t total = 0;
+	for (uint32_t i = 0; i < mi->n_seq; ++i) total += mi->seq[i].len;
+	A.S = B->d_S, A.seq_off = B->d_seq_off, A.seq_len = B->d_seq_len, A.n_seq = mi->n_seq, A.total = total;
+	A.n_reads = n_reads, A.read_len = read_len, A.seed = seed, A.err = err, A.sub = 0, A.ins = 0;
+	char *d_out;
+	MMB_CUDA_CHECK(cudaMalloc(&d_out, (size_t)n_reads * read_len + 16));
+	A.out = d_out;
+	cdna_reads_kernel<<<(n_reads + 127) / 128, 128, 0, ctx->stream>>>(A);
+	MMB_CUDA_CHECK(cudaGetLastError());
+	MMB_CUDA_CHECK(cudaMemcpyAsync(out, d_out, (size_t)n_reads * read_len, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	MMB_CUDA_CHECK(cudaFree(d_out));
+	return 0;
+}
+
+// sum of qe-qs over primary hits of a batch result (the bench's "aligned bases"; all_records: every hit, for all-vs-all overlap where no
+// hit is marked primary); n_regs / regs as mm_map_batch returns them
+extern "C" int64_t mmb_aligned_bases(int n, const int32_t *n_regs, mm_reg1_t *const *regs, int all_records)
+{
+	int64_t tot = 0;
+	for (int i = 0; i < n; ++i)
+		for (int j = 0; j < n_regs[i]; ++j)
+			if (all_records || regs[i][j].id == regs[i][j].parent) tot += regs[i][j].qe - regs[i][j].qs;
+	return tot;
 }

@@ -104,6 +104,9 @@ static inline float max(float a, float b) { return a > b? a : b; }
 // ---- integer intrinsics ----
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= (x >> i & 1u) << (31 - i); return r; }
+static inline unsigned long long __brevll(unsigned long long x) { unsigned long long r = 0; for (int i = 0; i < 64; ++i) r |= (x >> i & 1ull) << (63 - i); return r; }
 static inline int __clz(int x) { return x == 0? 32 : __builtin_clz((unsigned)x); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) { const uint64_t v = (uint64_t)hi << 32 | lo; return (unsigned)(v >> (sh & 31)); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s)

@@ -698,6 +698,71 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	return 0;
 }
 
+// Kernel-level entry for tests: the seeding stage alone (K1 sketch -> query-side filter -> index lookup -> streak selection ->
+// anchor expansion -> anchor sort, i.e. collect_minimizers + mm_collect_matches + collect_seed_hits of map.c:59-72,168-204) on the
+// context's stream. seqs: the reads back to back (ASCII), off: n_reads+1 offsets. Outputs (host): a_off_out[n_reads+1], rep_len_out,
+// n_mini_out; anchors_xy / mini_pos (if non-null) receive the sorted anchors (16 B each, a_cap entries) and the kept seeds'
+// span<<32|qpos words (mp_cap entries) read after read. Returns the total number of anchors (or -1 if a buffer is too small).
+extern "C" int64_t mmb_seed_batch_host(mmb_ctx_t *ctx, const mm_idx_t *mi, int n_reads, const char *seqs, const int64_t *off, int64_t flag, int mid_occ,
+										float q_occ_frac, int max_max_occ, int occ_dist, int64_t *a_off_out, int32_t *rep_len_out, int32_t *n_mini_out,
+										uint64_t *anchors_xy, int64_t a_cap, uint64_t *mini_pos, int64_t mp_cap)
+{
+	if (n_reads <= 0) return 0;
+	MMB_CUDA_CHECK(cudaSetDevice(ctx->device));
+	mm_idx_bucket_s *B = mi->B;
+	static BatchBufs bb; // test entry: one caller at a time
+	const int n = n_reads;
+	const int64_t total_bases = off[n];
+	uint8_t *d_seq = bb.seq.as<uint8_t>((size_t)total_bases + 16);
+	int64_t *d_off = bb.off.as<int64_t>((size_t)n + 1);
+	int32_t *d_qlen = bb.qlen.as<int32_t>((size_t)n);
+	std::vector<int32_t> h_qlen(n);
+	for (int j = 0; j < n; ++j) h_qlen[j] = (int32_t)(off[j + 1] - off[j]);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_seq, seqs, total_bases, cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_off, off, sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(d_qlen, h_qlen.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+	if (total_bases > 0) encode_kernel<<<(unsigned)((total_bases / 4 + 256) / 256), 256, 0, ctx->stream>>>(d_seq, total_bases);
+	int64_t *d_mz_off = bb.mz_off.as<int64_t>((size_t)n + 1);
+	const int64_t total_mz = mmb_sketch_device(ctx, d_seq, nullptr, d_off, n, nullptr, 0, mi->w, mi->k, mi->flag & MM_I_HPC, total_bases, bb.mz, d_mz_off, bb.t1, bb.t2, 1);
+	SeedArgs S;
+	S.ix = B->view(mi), S.n_reads = n, S.mz = (m128*)bb.mz.p, S.mz_off = d_mz_off, S.qlen = d_qlen;
+	S.n_mz = bb.n_mz.as<int32_t>((size_t)n);
+	S.q_occ_max = mid_occ, S.q_occ_frac = q_occ_frac, S.max_occ = mid_occ, S.max_max_occ = max_max_occ, S.occ_dist = occ_dist, S.flag = flag;
+	const size_t nm = (size_t)total_mz + 4;
+	S.s_n = bb.s_n.as<uint32_t>(nm), S.s_off = bb.s_off.as<uint64_t>(nm), S.k_idx = bb.k_idx.as<uint32_t>(nm), S.k_aoff = bb.k_aoff.as<uint32_t>(nm);
+	S.flt = bb.flt.as<uint8_t>(nm), S.mini_pos = bb.mini_pos.as<uint64_t>(nm);
+	S.n_keep = bb.n_keep.as<int32_t>((size_t)n), S.rep_len = bb.rep_len.as<int32_t>((size_t)n), S.n_a = bb.n_a.as<int64_t>((size_t)n + 1);
+	init_nmz_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_mz_off, n, S.n_mz);
+	if (flag & (MM_F_FOR_ONLY | MM_F_REV_ONLY)) S.k_cnt = bb.k_cnt.as<uint32_t>(nm); // skip_seed's strand rule (no query names here: no name tests)
+	mmb_seed_select_device(ctx, S, total_mz);
+	int64_t *d_a_off = bb.a_off.as<int64_t>((size_t)n + 1);
+	copy_i64_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(S.n_a, n, d_a_off);
+	const int64_t total_a = mmb_exclusive_scan_i64(ctx, d_a_off, n, true);
+	S.a = bb.a.as<m128>((size_t)total_a + 4), S.a_off = d_a_off;
+	S.a_sorted = bb.a2.as<m128>((size_t)total_a + 4);
+	mmb_seed_expand_sort_device(ctx, S, total_mz, total_a, bb.stk);
+	std::vector<int64_t> h_mz_off((size_t)n + 1);
+	MMB_CUDA_CHECK(cudaMemcpyAsync(a_off_out, d_a_off, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(rep_len_out, S.rep_len, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(n_mini_out, S.n_keep, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaMemcpyAsync(h_mz_off.data(), d_mz_off, sizeof(int64_t) * (n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	if (anchors_xy) {
+		if (total_a > a_cap) return -1;
+		if (total_a) MMB_CUDA_CHECK(cudaMemcpyAsync(anchors_xy, S.a_sorted, sizeof(m128) * (size_t)total_a, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	if (mini_pos) {
+		int64_t o = 0;
+		for (int j = 0; j < n; ++j) {
+			if (o + n_mini_out[j] > mp_cap) return -1;
+			if (n_mini_out[j]) MMB_CUDA_CHECK(cudaMemcpyAsync(mini_pos + o, S.mini_pos + h_mz_off[j], sizeof(uint64_t) * (size_t)n_mini_out[j], cudaMemcpyDeviceToHost, ctx->stream));
+			o += n_mini_out[j];
+		}
+	}
+	MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+	return total_a;
+}
+
 mmb_ctx_t *mmb_default_ctx(void);
 void mmb_register_ctx(mmb_ctx_t *c);
 

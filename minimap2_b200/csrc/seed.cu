@@ -514,6 +514,145 @@ __global__ void sort_block_kernel(const m128 *a_in, m128 *a_out, const int64_t *
 	}
 }
 
+// Stable LSD radix sort of one read's anchors by x in shared memory (replaces the O(n log^2 n) bitonic network above for every read
+// whose keys differ in at most 33 bit positions -- all of them in practice: strand bit + contig bits + position bits).
+//   * the bits in which the read's keys differ are found with one OR-reduction; the keys are squeezed to those bits (order-preserving:
+//     all other bits agree), 32 of them in a 32-bit word plus, if there is a 33rd (the strand bit), one flag bit next to the index;
+//   * 8-bit digits, least significant first: every warp owns a contiguous segment; __match_any_sync groups equal digits of 32
+//     consecutive elements, the group's first lane bumps the warp's counter, so an element's rank inside its segment is known without
+//     atomics and in input order (stability); one CTA-wide scan of the (digit, warp) counters turns them into scatter offsets;
+//   * the flag bit is a last 1-bit pass.
+// Equal keys end up adjacent in input order; reads that have any (and more than 64 anchors) are re-sorted by the exact emulation of the
+// reference's unstable radix sort, as before.
+template<int CAP, int NT>
+__global__ void __launch_bounds__(NT) sort_radix_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
+														int *exact_cnt, int *exact_list, int *fallback_cnt, int *fallback_list)
+{
+	constexpr int NW = NT / 32, ITER = CAP / NT, SEG = ITER * 32, RS = NW + 1, NH = 256 * RS, EPT = (NH + NT - 1) / NT;
+	extern __shared__ __align__(16) uint8_t sm_raw[];
+	uint32_t *kb0 = (uint32_t*)sm_raw, *kb1 = kb0 + CAP;
+	uint16_t *ib0 = (uint16_t*)(kb1 + CAP), *ib1 = ib0 + CAP;
+	uint16_t *hist = ib1 + CAP;
+	__shared__ unsigned long long s_or;
+	__shared__ int s_wsum[32];
+	__shared__ int s_tie;
+	const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+	const unsigned full = 0xffffffffu;
+	const int n_list = *cnt_ptr;
+	for (int li = blockIdx.x; li < n_list; li += gridDim.x) {
+		const int rd = list[li];
+		const int64_t off = a_off[rd];
+		const int n = (int)(a_off[rd + 1] - off);
+		// ---- stage the 64-bit keys (over both key buffers), find the varying bits ----
+		uint64_t *X64 = (uint64_t*)kb0;
+		if (tid == 0) s_or = 0, s_tie = 0;
+		__syncthreads();
+		const uint64_t x0 = a_in[off].x;
+		uint64_t m = 0;
+		for (int i = tid; i < n; i += NT) { const uint64_t x = a_in[off + i].x; X64[i] = x; m |= x ^ x0; }
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) m |= __shfl_xor_sync(full, m, o);
+		if (lane == 0 && m) atomicOr(&s_or, (unsigned long long)m);
+		__syncthreads();
+		const uint64_t M = s_or;
+		const int nb = __popcll(M);
+		if (nb > 33) { // cannot happen with < 2^32 distinct (contig, position) pairs per strand; kept exact by the network sort
+			if (tid == 0) fallback_list[atomicAdd(fallback_cnt, 1)] = rd;
+			__syncthreads();
+			continue;
+		}
+		uint64_t xr[ITER];
+		#pragma unroll
+		for (int it = 0; it < ITER; ++it) { const int e = w * SEG + it * 32 + lane; xr[it] = e < n? X64[e] : 0; }
+		__syncthreads();
+		#pragma unroll
+		for (int it = 0; it < ITER; ++it) {
+			const int e = w * SEG + it * 32 + lane;
+			if (e < n) { // squeeze the varying bits together, run by run (typically three runs: position, contig, strand)
+				uint64_t mm = M, ck = 0; int sh = 0;
+				while (mm) {
+					const int st = __ffsll((long long)mm) - 1;
+					const uint64_t r = mm >> st;
+					const int len = r == ~0ULL? 64 : __ffsll((long long)~r) - 1;
+					const uint64_t fm = len >= 64? ~0ULL : (1ULL << len) - 1;
+					ck |= ((xr[it] >> st) & fm) << sh;
+					sh += len;
+					mm = len + st >= 64? 0 : mm & ~(fm << st);
+				}
+				kb0[e] = (uint32_t)ck;
+				ib0[e] = (uint16_t)(e | (int)(ck >> 32 & 1) << 15);
+			}
+		}
+		__syncthreads();
+		uint32_t *kin = kb0, *kout = kb1;
+		uint16_t *iin = ib0, *iout = ib1;
+		const int n_pass = (min(nb, 32) + 7) / 8 + (nb > 32? 1 : 0);
+		for (int pass = 0; pass < n_pass; ++pass) {
+			const bool top = nb > 32 && pass == n_pass - 1;
+			const int shift = pass * 8;
+			for (int i = tid; i < NH; i += NT) hist[i] = 0;
+			__syncthreads();
+			int rank[ITER];
+			#pragma unroll
+			for (int it = 0; it < ITER; ++it) {
+				const int e = w * SEG + it * 32 + lane;
+				const bool valid = e < n;
+				const unsigned d = !valid? (0x100u | (unsigned)lane) : top? (unsigned)(iin[e] >> 15) : (kin[e] >> shift & 0xffu);
+				const unsigned peers = __match_any_sync(full, d);
+				const unsigned lt = peers & ((1u << lane) - 1u);
+				const int base = valid? hist[d * RS + w] : 0;
+				rank[it] = base + __popc(lt);
+				__syncwarp();
+				if (valid && lt == 0) hist[d * RS + w] = (uint16_t)(base + __popc(peers));
+				__syncwarp();
+			}
+			__syncthreads();
+			{ // exclusive scan of the counters in (digit, warp) order
+				int loc[EPT], sum = 0;
+				#pragma unroll
+				for (int k = 0; k < EPT; ++k) { const int i = tid * EPT + k; loc[k] = i < NH? hist[i] : 0; sum += loc[k]; }
+				int x = sum;
+				#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, x, o); if (lane >= o) x += y; }
+				if (lane == 31) s_wsum[w] = x;
+				__syncthreads();
+				if (w == 0) {
+					int v = lane < NW? s_wsum[lane] : 0, z = v;
+					#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(full, z, o); if (lane >= o) z += y; }
+					s_wsum[lane] = z - v;
+				}
+				__syncthreads();
+				int run = s_wsum[w] + x - sum;
+				#pragma unroll
+				for (int k = 0; k < EPT; ++k) { const int i = tid * EPT + k; if (i < NH) hist[i] = (uint16_t)run; run += loc[k]; }
+			}
+			__syncthreads();
+			#pragma unroll
+			for (int it = 0; it < ITER; ++it) {
+				const int e = w * SEG + it * 32 + lane;
+				if (e < n) {
+					const uint32_t k = kin[e]; const uint16_t ix = iin[e];
+					const unsigned d = top? (unsigned)(ix >> 15) : (k >> shift & 0xffu);
+					const int pos = hist[d * RS + w] + rank[it];
+					kout[pos] = k, iout[pos] = ix;
+				}
+			}
+			__syncthreads();
+			{ uint32_t *t = kin; kin = kout; kout = t; uint16_t *u = iin; iin = iout; iout = u; }
+		}
+		int tie = 0;
+		for (int i = tid; i < n; i += NT) {
+			a_out[off + i] = a_in[off + (iin[i] & 0x3fff)];
+			if (i + 1 < n && kin[i] == kin[i + 1] && (iin[i] >> 15) == (iin[i + 1] >> 15)) tie = 1;
+		}
+		if (tie) s_tie = 1;
+		__syncthreads();
+		if (tid == 0 && s_tie && n > 64) exact_list[atomicAdd(exact_cnt, 1)] = rd;
+		__syncthreads();
+	}
+}
+
 __global__ void __launch_bounds__(64) sort_exact_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
 														int32_t *stk, const int64_t *stk_off)
 {
@@ -695,17 +834,39 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_cls_cnt, 0, 16 * sizeof(int), ctx->stream));
 		sort_classify_kernel<<<(A.n_reads + 255) / 256, 256, 0, ctx->stream>>>(A.a_off, A.n_reads, d_cls_cnt, d_cls_list, N_CLS, CAP0);
 		++ctx->n_launch;
-		int cap = CAP0;
-		for (int c = 0; c < N_CLS; ++c, cap <<= 1) {
-			const size_t smem = (size_t)cap * 10;
-			const int threads = cap >= 8192? 1024 : cap >= 2048? 512 : 256;
-			{ static std::once_flag once; std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024)); }); }
-			int per_sm = 1;
-			MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_block_kernel, threads, smem));
-			const int grid = ctx->n_sm * (per_sm > 0? per_sm : 1);
-			sort_block_kernel<<<grid, threads, smem, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)c * A.n_reads, d_cls_cnt + c, cap,
-																	 d_cls_cnt + N_CLS + 1, d_cls_list + (size_t)(N_CLS + 1) * A.n_reads);
-			++ctx->n_launch;
+		int *d_tie_cnt = d_cls_cnt + N_CLS + 1, *d_tie_list = d_cls_list + (size_t)(N_CLS + 1) * A.n_reads;
+		int *d_fb_cnt = d_cls_cnt + N_CLS + 2, *d_fb_list = d_cls_list + (size_t)(N_CLS + 2) * A.n_reads;
+		static const bool use_bitonic = getenv("MM_B200_SORT_BITONIC") != nullptr; // development switch: the network sort for every read
+		if (!use_bitonic) {
+			#define MMB_RADIX_LAUNCH(CAP_, NT_, c_) do { \
+				const size_t smem_ = (size_t)(CAP_) * 12 + (size_t)256 * ((NT_) / 32 + 1) * 2; \
+				{ static std::once_flag once_; std::call_once(once_, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(sort_radix_kernel<CAP_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); }); } \
+				int per_sm_ = 1; \
+				MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_, sort_radix_kernel<CAP_, NT_>, NT_, smem_)); \
+				sort_radix_kernel<CAP_, NT_><<<ctx->n_sm * (per_sm_ > 0? per_sm_ : 1), NT_, smem_, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)(c_) * A.n_reads, \
+					d_cls_cnt + (c_), d_tie_cnt, d_tie_list, d_fb_cnt, d_fb_list); \
+				++ctx->n_launch; } while (0)
+			MMB_RADIX_LAUNCH(1024, 128, 0);
+			MMB_RADIX_LAUNCH(2048, 256, 1);
+			MMB_RADIX_LAUNCH(4096, 512, 2);
+			MMB_RADIX_LAUNCH(8192, 1024, 3);
+			MMB_RADIX_LAUNCH(16384, 1024, 4);
+			#undef MMB_RADIX_LAUNCH
+		}
+		{ // network sort: the fallback of the radix kernels (keys differing in more than 33 bit positions), or everything under the switch
+			int cap = CAP0;
+			for (int c = 0; c < N_CLS; ++c, cap <<= 1) {
+				if (!use_bitonic && c < N_CLS - 1) continue; // fallback list: one launch with the largest class
+				const size_t smem = (size_t)cap * 10;
+				const int threads = cap >= 8192? 1024 : cap >= 2048? 512 : 256;
+				{ static std::once_flag once; std::call_once(once, [&]() { MMB_CUDA_CHECK(cudaFuncSetAttribute(sort_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 1024)); }); }
+				int per_sm = 1;
+				MMB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sort_block_kernel, threads, smem));
+				const int grid = ctx->n_sm * (per_sm > 0? per_sm : 1);
+				sort_block_kernel<<<grid, threads, smem, ctx->stream>>>(A.a, A.a_sorted, A.a_off, use_bitonic? d_cls_list + (size_t)c * A.n_reads : d_fb_list,
+																		 use_bitonic? d_cls_cnt + c : d_fb_cnt, cap, d_tie_cnt, d_tie_list);
+				++ctx->n_launch;
+			}
 		}
 		// exact emulation: reads with equal keys go through the shared-memory walker (cap 15360 anchors: 12 B/entry + per-lane bucket tables);
 		// whatever does not fit, and the oversize class, falls back to the global-memory walker (one thread per read)
@@ -719,6 +880,13 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 		}
 		sort_exact_kernel<<<(A.n_reads + 63) / 64, 64, 0, ctx->stream>>>(A.a, A.a_sorted, A.a_off, d_cls_list + (size_t)N_CLS * A.n_reads, d_cls_cnt + N_CLS, d_stk, d_stk_off);
 		++ctx->n_launch;
+		static const bool dbg = getenv("MM_B200_SORT_STATS") != nullptr;
+		if (dbg) { // development aid: reads per class / oversize / with equal keys / fallback
+			int h[16];
+			MMB_CUDA_CHECK(cudaMemcpyAsync(h, d_cls_cnt, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+			MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+			fprintf(stderr, "[sort] reads=%d anchors=%lld classes=%d/%d/%d/%d/%d oversize=%d ties=%d fallback=%d\n", A.n_reads, (long long)total_a, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+		}
 	}
 	MMB_CUDA_CHECK(cudaGetLastError());
 }

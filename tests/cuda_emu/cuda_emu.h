@@ -104,6 +104,16 @@ static inline float max(float a, float b) { return a > b? a : b; }
 // ---- integer intrinsics ----
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline unsigned long long atomicOr(unsigned long long *p, unsigned long long v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline unsigned __match_any_sync(unsigned mask, unsigned v)
+{
+	uint64_t o[32]; unsigned p;
+	emu_warp_exchange(mask, v, o, &p);
+	unsigned r = 0;
+	for (int l = 0; l < 32; ++l) if ((p >> l & 1) && (unsigned)o[l] == v) r |= 1u << l;
+	return r;
+}
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; ++i) r |= (x >> i & 1u) << (31 - i); return r; }
 static inline unsigned long long __brevll(unsigned long long x) { unsigned long long r = 0; for (int i = 0; i < 64; ++i) r |= (x >> i & 1ull) << (63 - i); return r; }

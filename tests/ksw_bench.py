@@ -4,6 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import ctypes as C
 import numpy as np
+import minimap2_b200._lib as _L
+if os.environ.get('AB_LIB'):
+    _L.LIB_PATH = os.environ['AB_LIB']  # A/B of two builds on the same box (development only)
 import minimap2_b200 as mb
 from minimap2_b200 import kernels as K
 from minimap2_b200._lib import lib, KswJob, KswRes

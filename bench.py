@@ -340,7 +340,24 @@ def main():
     t0 = time.time()
     # Every rank builds the same index deterministically on its own GPU from the seed (the device build takes seconds).
     # A loaded (non-synthetic) index is broadcast instead: see minimap2_b200/dist.py (NCCL broadcast of the device arrays).
-    gidx = L.mmb_synth_index(int(genome_mbp * 1e6), int(wl["contigs"]), 11, wl["w"], wl["k"], 14)
+    # One rank builds (or, for a real genome, loads) the index; the others receive its device arrays by ONE NCCL broadcast over
+    # NVLink/NVSwitch (minimap2_b200/dist.py) and are independent from then on: no collective on the per-read path.
+    bcast = None
+    keep_idx_bufs = None
+    if dist_on and a.impl != "reference" and wl["kind"] != "ava":
+        from minimap2_b200 import dist as mdist
+        gidx = L.mmb_synth_index(int(genome_mbp * 1e6), int(wl["contigs"]), 11, wl["w"], wl["k"], 14) if rank == 0 else None
+        torch.cuda.synchronize(); dist.barrier()
+        tb = time.perf_counter()
+        gidx, keep_idx_bufs = mdist.broadcast_index(gidx, rank, src=0)
+        torch.cuda.synchronize(); dist.barrier()
+        tb = time.perf_counter() - tb
+        nbytes = int(sum(int(t.numel()) for t in keep_idx_bufs))
+        bcast = {"bytes": nbytes, "ms": 1e3 * tb, "gb_per_s": nbytes / 1e9 / tb, "ranks": world,
+                 "what": "device index arrays (hash table, positions, 4-bit sequence, offsets, occurrence counts) from rank 0 to all ranks, one NCCL broadcast per array; wall time between barriers"}
+        log("index broadcast: %.2f GB in %.0f ms (%.0f GB/s)" % (nbytes / 1e9, 1e3 * tb, nbytes / 1e9 / tb))
+    else:
+        gidx = L.mmb_synth_index(int(genome_mbp * 1e6), int(wl["contigs"]), 11, wl["w"], wl["k"], 14)
     buf = np.zeros(n_reads * read_len, dtype=np.uint8)
     gen_reads(L, gidx, wl, n_reads, read_len, 12 + 1000 * (rank if a.impl != "reference" else 0), buf)
     names = ["r%d" % i for i in range(n_reads)]
@@ -539,6 +556,8 @@ def main():
             "roofline": roofline}
     if file_e2e:
         line["file_e2e"] = file_e2e
+    if bcast:
+        line["index_broadcast"] = bcast
     # --- CPU baseline + parity: the reference's own code on this box's cores, bounded sample, both arms through mm_map_file ---
     if not a.no_cpu_baseline:
         try:

@@ -51,13 +51,15 @@ static struct option long_options[] = {
 	{ "min-dp-score", required_argument, 0, 's' }, { "sam", no_argument, 0, 'a' }, { 0, 0, 0, 0 }
 };
 
+extern "C" int mm_write_sam_hdr(const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[]); // mmpriv.h:104
+
 int main(int argc, char *argv[])
 {
 	const char *opt_str = "2aSDw:k:K:t:r:f:Vv:g:G:I:d:XT:s:x:Hcp:M:n:z:A:B:b:O:E:m:N:Qu:R:hF:LC:yYPo:e:U:J:j:";
 	mm_mapopt_t opt;
 	mm_idxopt_t ipt;
 	int c, n_threads = 3, old_best_n = -1, li = 0;
-	char *fnw = 0, *s, *alt_list = 0, *fn_bed_junc = 0, *fn_spsc = 0;
+	char *fnw = 0, *s, *alt_list = 0, *fn_bed_junc = 0, *fn_spsc = 0, *rg = 0;
 	float spsc_scale = 0.7f;
 	mm_verbose = 3;
 	mm_realtime0 = realtime();
@@ -111,8 +113,9 @@ int main(int argc, char *argv[])
 			if (t == 0) opt.flag |= MM_F_SPLICE_OLD;
 			else if (t == 1) opt.flag &= ~MM_F_SPLICE_OLD;
 		}
-		else if (c == 'R' || c == 'j') { // accepted by the reference, not built here: refuse instead of silently ignoring (no read-group / jump-BED support)
-			fprintf(stderr, "[ERROR] option -%c (%s) is not supported by minimap2-b200\n", c, c == 'R'? "SAM read group" : "junction jump BED for short RNA-seq reads");
+		else if (c == 'R') rg = optarg; // SAM read group line (main.c:199; written by mm_write_sam_hdr, repeated as RG:Z: on every record)
+		else if (c == 'j') { // accepted by the reference, not built here: refuse instead of silently ignoring
+			fprintf(stderr, "[ERROR] option -j (junction jump BED for short RNA-seq reads) is not supported by minimap2-b200\n");
 			return 1;
 		}
 		else if (c == 'I') ipt.batch_size = parse_num(optarg);
@@ -236,13 +239,11 @@ int main(int argc, char *argv[])
 			if (mi->spsc == 0 && mm_verbose >= 2) fprintf(stderr, "[WARNING] failed to load the splice score file\n");
 		}
 		if (alt_list) mm_idx_alt_read(mi, alt_list); // main.c:487
-		if ((opt.flag & MM_F_OUT_SAM) && idx_rdr->n_parts == 1) { // SAM header (format.c:128-148)
-			std::string hdr = "@HD\tVN:1.6\tSO:unsorted\tGO:query\n";
-			if (mm_idx_reader_eof(idx_rdr))
-				for (uint32_t i = 0; i < mi->n_seq; ++i) hdr += std::string("@SQ\tSN:") + mi->seq[i].name + "\tLN:" + std::to_string(mi->seq[i].len) + "\n";
-			hdr += std::string("@PG\tID:minimap2\tPN:minimap2\tVN:") + MM_VERSION;
-			if (argc > 1) { hdr += "\tCL:minimap2"; for (int i = 1; i < argc; ++i) hdr += std::string(" ") + argv[i]; }
-			puts(hdr.c_str());
+		if ((opt.flag & MM_F_OUT_SAM) && idx_rdr->n_parts == 1) { // SAM header (main.c:445-460, format.c:119-148)
+			int hret;
+			if (mm_idx_reader_eof(idx_rdr)) hret = mm_write_sam_hdr(mi, rg, MM_VERSION, argc, argv);
+			else hret = mm_write_sam_hdr(0, rg, MM_VERSION, argc, argv);
+			if (hret != 0) { mm_idx_destroy(mi); mm_idx_reader_close(idx_rdr); return 1; }
 		}
 		if (mm_verbose >= 3)
 			fprintf(stderr, "[M::%s::%.3f*%.2f] loaded/built the index for %d target sequence(s)\n", __func__, realtime() - mm_realtime0, cputime() / (realtime() - mm_realtime0), mi->n_seq);

@@ -8,6 +8,8 @@
 
 static inline void put_int(std::string &s, int64_t v) { s += std::to_string(v); }
 
+static char g_rg_id[256]; // ID of the -R read group (format.c:9), set by the header writer, printed as RG:Z: on every SAM record
+
 static void write_tags(std::string &s, const mm_reg1_t *r) // format.c:397-423
 {
 	int type;
@@ -207,6 +209,10 @@ static const unsigned char comp_tab[128] = { // bseq.c:11-28 (ASCII range)
 	'p', 'q', 'y', 's', 'a', 'a', 'b', 'w', 'x', 'r', 'z', 123, 124, 125, 126, 127
 };
 
+// the exported form (bseq.h:29; mappy's cmappy.h reverse-complements the mate with it): identity outside the ASCII letters
+extern "C" { unsigned char seq_comp_table[256]; }
+namespace { struct CompTabInit { CompTabInit() { for (int i = 0; i < 256; ++i) seq_comp_table[i] = i < 128? comp_tab[i] : (unsigned char)i; } } g_comp_tab_init; }
+
 static void sam_write_sq(std::string &s, const char *seq, int l, int rev, int comp) // format.c:463-476
 {
 	if (rev) {
@@ -287,6 +293,7 @@ void hl_write_sam(std::string &s, const mm_idx_t *mi, const char *qname, const c
 			if (qual) sam_write_sq(s, qual + r->qs, r->qe - r->qs, r->rev, 0); else s += '*';
 		}
 	}
+	if (g_rg_id[0]) { s += "\tRG:Z:"; s += g_rg_id; } // format.c:639
 	if (r) {
 		write_tags(s, r);
 		if (r->parent == r->id && r->p && n_regs > 1 && regs && r >= regs && r - regs < n_regs) { // SA tag
@@ -319,15 +326,48 @@ void hl_write_sam(std::string &s, const mm_idx_t *mi, const char *qname, const c
 	if (rep_len >= 0) { s += "\trl:i:"; put_int(s, rep_len); }
 }
 
-void hl_write_sam_hdr(std::string &s, const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[]) // format.c:128-148
+// read group (format.c:9,82-117): the @RG line goes into the header with its escapes resolved and its ID is repeated as RG:Z: on every record
+static int sam_rg_line(std::string &s, const char *rg)
 {
+	memset(g_rg_id, 0, 256);
+	if (rg == 0) return 0;
+	if (strstr(rg, "@RG") != rg) { if (mm_verbose >= 1) fprintf(stderr, "[ERROR] the read group line is not started with @RG\n"); return -1; }
+	if (strstr(rg, "\t") != NULL) { if (mm_verbose >= 1) fprintf(stderr, "[ERROR] the read group line contained literal <tab> characters -- replace with escaped tabs: \\t\n"); return -1; }
+	std::string line;
+	for (const char *p = rg; *p; ++p) { // mm_escape: \t -> tab, \\ -> backslash, any other escape is dropped
+		if (*p == '\\') { ++p; if (*p == 't') line += '\t'; else if (*p == '\\') line += '\\'; if (*p == 0) break; }
+		else line += *p;
+	}
+	const size_t id = line.find("\tID:");
+	if (id == std::string::npos) { if (mm_verbose >= 1) fprintf(stderr, "[ERROR] no ID within the read group line\n"); return -1; }
+	size_t e = id + 4;
+	while (e < line.size() && line[e] != '\t' && line[e] != '\n') ++e;
+	if (e - (id + 4) + 1 > 256) { if (mm_verbose >= 1) fprintf(stderr, "[ERROR] @RG:ID is longer than 255 characters\n"); return -1; }
+	memcpy(g_rg_id, line.data() + id + 4, e - (id + 4));
+	s += line; s += '\n';
+	return 0;
+}
+
+int hl_write_sam_hdr(std::string &s, const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[]) // format.c:119-148
+{
+	int ret = 0;
 	s += "@HD\tVN:1.6\tSO:unsorted\tGO:query\n";
 	if (mi) for (uint32_t i = 0; i < mi->n_seq; ++i) { s += "@SQ\tSN:"; s += mi->seq[i].name; s += "\tLN:"; put_int(s, mi->seq[i].len); s += '\n'; }
-	(void)rg;
+	if (rg) ret = sam_rg_line(s, rg);
 	s += "@PG\tID:minimap2\tPN:minimap2";
 	if (ver) { s += "\tVN:"; s += ver; }
 	if (argc > 1) {
 		s += "\tCL:minimap2";
 		for (int i = 1; i < argc; ++i) { s += ' '; s += argv[i]; }
 	}
+	return ret;
+}
+
+// mmpriv.h:104: what main.c:446-452 calls (the header goes to stdout through mm_err_puts, one line feed appended)
+extern "C" int mm_write_sam_hdr(const mm_idx_t *mi, const char *rg, const char *ver, int argc, char *argv[])
+{
+	std::string s;
+	const int ret = hl_write_sam_hdr(s, mi, rg, ver, argc, argv);
+	puts(s.c_str());
+	return ret;
 }

@@ -880,7 +880,22 @@ extern "C" mm_tbuf_t *mm_tbuf_init(void) { return (mm_tbuf_t*)calloc(1, sizeof(m
 extern "C" void mm_tbuf_destroy(mm_tbuf_t *b) { free(b); }
 extern "C" void *mm_tbuf_get_km(mm_tbuf_t *b) { return b? b->km : 0; }
 
-static std::mutex g_map_mu; // the batch arenas are shared: serialise concurrent single-read callers
+// mm_map is re-entrant in the reference (one mm_tbuf_t per thread, the index shared read-only: minimap.h:341-348, map.c:380-397; mappy drops
+// the GIL around it). Here every call is work for the one GPU scheduler, so concurrent callers are COALESCED instead of taking turns: a
+// caller queues its read; whoever finds no batch in flight becomes the leader, takes every queued request that uses the same index and
+// the same options, runs them as ONE mm_map_batch() and hands the results back. Requests that arrive meanwhile form the next batch.
+namespace {
+struct MapReq {
+	const mm_idx_t *mi; const mm_mapopt_t *opt;
+	int qlen; const char *seq, *name;
+	int n_regs = 0, rep_len = 0; mm_reg1_t *regs = nullptr;
+	bool done = false;
+};
+std::mutex g_req_mu;
+std::condition_variable g_req_cv;
+std::deque<MapReq*> g_req_q;
+bool g_req_leader = false;
+}
 
 extern "C" void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, const char **seqs, int *n_regs, mm_reg1_t **regs, mm_tbuf_t *b, const mm_mapopt_t *opt, const char *qname)
 {
@@ -888,12 +903,39 @@ extern "C" void mm_map_frag(const mm_idx_t *mi, int n_segs, const int *qlens, co
 		fprintf(stderr, "[ERROR] minimap2_b200: multi-segment (paired-end) mapping is not implemented\n");
 		abort();
 	}
-	std::lock_guard<std::mutex> lk(g_map_mu);
-	int rep_len = 0;
-	const char *names[1] = { qname };
-	mm_map_batch(mi, 1, qlens, seqs, qname? names : nullptr, n_regs, regs, &rep_len, opt, 1);
+	MapReq me;
+	me.mi = mi, me.opt = opt, me.qlen = qlens[0], me.seq = seqs[0], me.name = qname;
+	std::unique_lock<std::mutex> lk(g_req_mu);
+	g_req_q.push_back(&me);
+	while (!me.done) {
+		if (g_req_leader) { g_req_cv.wait(lk); continue; }
+		g_req_leader = true;
+		// my request is still queued (only a leader removes requests, and it marks them done before it steps down)
+		std::vector<MapReq*> batch;
+		for (auto it = g_req_q.begin(); it != g_req_q.end();) {
+			MapReq *r = *it;
+			if (r->mi == mi && (r->opt == opt || memcmp(r->opt, opt, sizeof(mm_mapopt_t)) == 0)) { batch.push_back(r); it = g_req_q.erase(it); }
+			else ++it;
+		}
+		lk.unlock();
+		const int n = (int)batch.size();
+		std::vector<int> ql(n), nr(n, 0), rl(n, 0);
+		std::vector<const char*> sq(n), nm(n);
+		std::vector<mm_reg1_t*> rg(n, nullptr);
+		bool any_name = false;
+		for (int i = 0; i < n; ++i) { ql[i] = batch[i]->qlen, sq[i] = batch[i]->seq, nm[i] = batch[i]->name; any_name |= batch[i]->name != nullptr; }
+		// query names enter the result only through the hash that breaks ties (map.c:246-248) and skip_seed's name tests; a missing name is
+		// passed as such (NULL entry), exactly like a lone call without a name
+		mm_map_batch(mi, n, ql.data(), sq.data(), any_name? nm.data() : nullptr, nr.data(), rg.data(), rl.data(), opt, n > 1? 8 : 1);
+		lk.lock();
+		for (int i = 0; i < n; ++i) batch[i]->n_regs = nr[i], batch[i]->regs = rg[i], batch[i]->rep_len = rl[i], batch[i]->done = true;
+		g_req_leader = false;
+		g_req_cv.notify_all();
+	}
+	lk.unlock();
+	*n_regs = me.n_regs, regs[0] = me.regs;
 	if (b) {
-		b->rep_len = rep_len;
+		b->rep_len = me.rep_len;
 		b->frag_gap = opt->max_gap_ref > 0? opt->max_gap_ref : opt->max_gap; // map.c:263-271,317
 	}
 }

@@ -525,7 +525,7 @@ __global__ void sort_block_kernel(const m128 *a_in, m128 *a_out, const int64_t *
 // Equal keys end up adjacent in input order; reads that have any (and more than 64 anchors) are re-sorted by the exact emulation of the
 // reference's unstable radix sort, as before.
 template<int CAP, int NT>
-__global__ void __launch_bounds__(NT) sort_radix_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
+__global__ void __launch_bounds__(NT, NT >= 1024? 1 : 1024 / NT) sort_radix_kernel(const m128 *a_in, m128 *a_out, const int64_t *a_off, const int *list, const int *cnt_ptr,
 														int *exact_cnt, int *exact_list, int *fallback_cnt, int *fallback_list)
 {
 	constexpr int NW = NT / 32, ITER = CAP / NT, SEG = ITER * 32, RS = NW + 1, NH = 256 * RS, EPT = (NH + NT - 1) / NT;
@@ -687,7 +687,13 @@ __global__ void __launch_bounds__(32) sort_exact_smem_kernel(const m128 *a_in, m
 		const int64_t off = a_off[rd];
 		const int n = (int)(a_off[rd + 1] - off);
 		if (n > cap) { if (lane == 0) over_list[atomicAdd(over_cnt, 1)] = rd; continue; }
-		for (int i = lane; i < n; i += 32) X[i] = a_in[off + i].x, pd[i] = (uint32_t)i;
+		uint64_t vary = 0; // bits in which the read's keys differ: a level whose byte of `vary` is zero leaves every range untouched
+		{
+			const uint64_t x0 = a_in[off].x;
+			for (int i = lane; i < n; i += 32) { const uint64_t x = a_in[off + i].x; X[i] = x, pd[i] = (uint32_t)i; vary |= x ^ x0; }
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) vary |= __shfl_xor_sync(0xffffffffu, vary, o);
+		}
 		if (lane == 0) tasks0[0] = 0u | (uint32_t)n << 16, s_next = 0;
 		__syncwarp();
 		uint32_t *cur = tasks0, *nxt = tasks1;
@@ -703,8 +709,82 @@ __global__ void __launch_bounds__(32) sort_exact_smem_kernel(const m128 *a_in, m
 			n_task = 0;
 		}
 		for (int shift = 56; n_task > 0; shift = shift > 8? shift - 8 : 0) {
+			if ((vary >> shift & 0xff) == 0) { // every key has the same digit here: the reference's pass counts, moves nothing and recurses on the same ranges
+				if (shift == 0) break;
+				continue;
+			}
+			// large ranges (the first levels: one or two ranges holding the whole read) are handled by the whole warp: digit stamping, counting
+			// and the bucket post-processing run on all lanes, only the cycle-leader walk itself -- sequential by nature -- stays on lane 0
+			for (int t = 0; t < n_task; ++t) {
+				const int beg = cur[t] & 0xffff, end = cur[t] >> 16;
+				if (end - beg < 1024) continue;
+				uint16_t *h0 = head - (size_t)lane * 512, *t0 = h0 + 256; // lane 0's tables
+				uint32_t *cnt = (uint32_t*)(h0 + 512 * 4); // lane 4's tables double as 256 32-bit counters (every lane rebuilds its tables before use)
+				for (int b = lane; b < 256; b += 32) cnt[b] = 0;
+				__syncwarp();
+				for (int i = beg + lane; i < end; i += 32) {
+					const uint32_t idx = pd[i] & 0xffffu, d = (uint32_t)(X[idx] >> shift) & 0xffu;
+					pd[i] = idx | d << 16;
+					atomicAdd(&cnt[d], 1u);
+				}
+				__syncwarp();
+				uint32_t c8[8], sum = 0, mx = 0;
+				#pragma unroll
+				for (int k = 0; k < 8; ++k) { c8[k] = cnt[lane * 8 + k]; sum += c8[k]; mx = max(mx, c8[k]); }
+				uint32_t inc = sum;
+				#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+				#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+				__syncwarp();
+				uint32_t run = (uint32_t)beg + inc - sum;
+				#pragma unroll
+				for (int k = 0; k < 8; ++k) { h0[lane * 8 + k] = (uint16_t)run; run += c8[k]; t0[lane * 8 + k] = (uint16_t)run; }
+				__syncwarp();
+				if (lane == 0 && mx != (uint32_t)(end - beg)) { // permute (ksort.h:126-138)
+					for (int b = 0; b < 256;) {
+						const uint32_t hb = h0[b];
+						if (hb != t0[b]) {
+							const uint32_t w = pd[hb];
+							uint32_t l = w >> 16;
+							if (l != (uint32_t)b) {
+								uint32_t tmp = w;
+								do {
+									const uint32_t sw = tmp, hl = h0[l];
+									tmp = pd[hl]; pd[hl] = sw; h0[l] = (uint16_t)(hl + 1);
+									l = tmp >> 16;
+								} while (l != (uint32_t)b);
+								pd[hb] = tmp;
+							}
+							h0[b] = (uint16_t)(hb + 1);
+						} else ++b;
+					}
+				}
+				__syncwarp();
+				if (shift) {
+					for (int b = lane; b < 256; b += 32) {
+						const uint32_t bb = b? t0[b - 1] : (uint32_t)beg, be = t0[b];
+						if (be - bb > 64) nxt[atomicAdd(&s_next, 1)] = bb | be << 16;
+						else if (be - bb > 1) { // insertion sort on the full key (ksort.h:100-110)
+							for (uint32_t i = bb + 1; i < be; ++i) {
+								const uint32_t wi = pd[i];
+								const uint64_t ki = X[wi & 0xffffu];
+								if (ki < X[pd[i - 1] & 0xffffu]) {
+									uint32_t j;
+									for (j = i; j > bb && ki < X[pd[j - 1] & 0xffffu]; --j) pd[j] = pd[j - 1];
+									pd[j] = wi;
+								}
+							}
+						}
+					}
+				}
+				__syncwarp();
+				if (lane == 0) cur[t] = 0; // done
+				__syncwarp();
+			}
 			for (int t = lane; t < n_task; t += 32) {
 				const int beg = cur[t] & 0xffff, end = cur[t] >> 16;
+				if (end <= beg) continue;
 				for (int b = 0; b < 256; b += 2) *(uint32_t*)(head + b) = 0;
 				for (int i = beg; i < end; ++i) { // count, and stamp each word with its digit at this level
 					const uint32_t idx = pd[i] & 0xffffu, d = (uint32_t)(X[idx] >> shift) & 0xffu;
@@ -849,7 +929,7 @@ void mmb_seed_expand_sort_device(mmb_ctx_t *ctx, SeedArgs &A, int64_t total_mz, 
 			MMB_RADIX_LAUNCH(1024, 128, 0);
 			MMB_RADIX_LAUNCH(2048, 256, 1);
 			MMB_RADIX_LAUNCH(4096, 512, 2);
-			MMB_RADIX_LAUNCH(8192, 1024, 3);
+			MMB_RADIX_LAUNCH(8192, 512, 3); // 16 elements per thread, 64 registers: two CTAs per SM instead of one 1024-thread CTA that owns the whole register file
 			MMB_RADIX_LAUNCH(16384, 1024, 4);
 			#undef MMB_RADIX_LAUNCH
 		}

@@ -45,6 +45,7 @@ struct FastArgs {
 	int8_t zd_q, zd_e;                    // gap open/extension as mm_test_zdrop uses them (opt->q, opt->e: not reordered)
 	int long_thres, long_diff;
 	int8_t mat[25];
+	uint32_t one, neg1;                   // 1 and 0xffffffff, passed at run time so that ptxas keeps the IMAD form of PK_FADD/PK_FSUB
 };
 
 __device__ __forceinline__ uint8_t fetch_t(const void *target, int packed, long long idx)
@@ -65,7 +66,7 @@ __device__ __forceinline__ void push_cig(uint32_t *cig, int &n, uint32_t op, int
 template<int C>
 __global__ void __launch_bounds__(128) ksw_fast_kernel(FastArgs A)
 {
-	extern __shared__ uint8_t smem[];
+	extern __shared__ __align__(16) uint8_t smem[];
 	const int lane = threadIdx.x & 31, wk = threadIdx.x >> 5, nwk = blockDim.x >> 5;
 	const int worker = blockIdx.x * nwk + wk;
 	uint8_t *qs = smem + (size_t)wk * (A.qmax + 1024);   // staged query bytes
@@ -270,12 +271,31 @@ __global__ void __launch_bounds__(128) ksw_fast_kernel(FastArgs A)
 // lane l+1 runs two rows behind lane l. Traceback bytes are stored as (tag | flags), i.e. the reference byte XOR 0x7f.
 // Jobs with tlen <= 256 use LN = 16 lanes (two jobs per warp, up to 16 columns per lane): more columns per lane amortise
 // the per-step overhead (shuffles, stores, row bookkeeping) and halve the pipeline fill/drain of the lane skew.
+// Pipe balancing. On sm_100 IADD3/LOP3/VIMNMX/PRMT all issue on the ALU pipe and IMAD on the FMA pipe, each at one warp
+// instruction per two cycles per scheduler: the recurrence written with plain adds keeps the ALU pipe at 80 % while the FMA pipe
+// idles (ncu, round 1), i.e. half of the issue slots are unusable. The linear steps are therefore written as two-input multiply-adds
+// x * 1 + y / y * (-1) + x whose multiplier is a kernel argument: ptxas cannot fold it back into an IADD3, and packed words add
+// exactly like before (the halves never carry into each other in the final values; intermediate borrows cancel modulo 2^32).
+#if defined(MMB_EMU) || defined(MMB_PK_NO_FMA)
+#define PK_FADD(x, y) ((x) + (y))
+#define PK_FSUB(x, y) ((x) - (y))
+#else
+#define PK_FADD(x, y) pk_mad((x), ONE, (y))
+#define PK_FSUB(x, y) pk_mad((y), NEG1, (x))
+__device__ __forceinline__ uint32_t pk_mad(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
+}
+#endif
+
 template<int H, int LN>
 __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 {
-	extern __shared__ uint8_t smem[];
+	extern __shared__ __align__(16) uint8_t smem[];
 	constexpr int C = 2 * H;
-	constexpr int CPH = H <= 1? 1 : H <= 2? 2 : H <= 4? 4 : 8; // traceback bytes per block per row (one aligned store)
+	constexpr int CPH = H <= 1? 1 : H <= 2? 2 : H <= 4? 4 : H <= 8? 8 : 16; // traceback bytes per block per row (one aligned store)
 	constexpr int CP = 2 * CPH;
 	constexpr int NW = (H + 3) / 4;
 	constexpr int NJ = 32 / LN;                                // jobs per warp
@@ -284,19 +304,27 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 	const int sub = lane & (LN - 1), grp = lane / LN, lead = lane & ~(LN - 1);
 	const int worker0 = (blockIdx.x * nwk + wk) * NJ;
 	uint8_t *qs = smem + (size_t)(wk * NJ + grp) * A.qmax;   // staged query, one-hot (0x80 = ambiguous), one sentinel past the end
+	constexpr int TSM = LN * C;                              // staged target (nt4 codes) per job, for the z-drop scan
+	constexpr int TW = 80, TILE = 32 * TW;                   // traceback tile: 32 rows x 80 physical bytes per warp
+	uint8_t *ts = smem + (size_t)nwk * NJ * A.qmax + (size_t)(wk * NJ + grp) * TSM;
+	uint8_t *tile = smem + (size_t)nwk * NJ * (A.qmax + TSM) + (size_t)wk * TILE;
 	uint8_t *p = A.pws + A.pws_stride * (size_t)(worker0 + grp);
 	const int q = A.q, e = A.e, q2 = A.q2, e2 = A.e2, qe = q + e, qe2 = q2 + e2;
 	const unsigned full = 0xffffffffu;
 	#define PK_ENC(v) ((uint32_t)((v) + 128) << 8)
 	#define PK2(v) (PK_ENC(v) * 0x10001u)
 	const uint32_t BB2 = 0x80008000u, CLEAN = 0xff00ff00u;
-	const uint32_t K_A = 0x00060006u - BB2, K_B = 0x00050005u - BB2, K_A2 = 0x00040004u - BB2, K_B2 = 0x00030003u - BB2;
+	// state words carry the tag of the candidate they feed (x: 6, y: 5, x2: 4, y2: 3; sc: 7) in the low byte of each half
+	const uint32_t TAGS = 0x03040506u, NBB2 = 0u - BB2;
+	const uint32_t ONE = A.one, NEG1 = A.neg1;
+	(void)ONE; (void)NEG1;
 	const uint32_t KX = BB2 - ((uint32_t)e << 8) * 0x10001u - 0x00060006u, KY = BB2 - ((uint32_t)e << 8) * 0x10001u - 0x00050005u;
 	const uint32_t KX2 = BB2 - ((uint32_t)e2 << 8) * 0x10001u - 0x00040004u, KY2 = BB2 - ((uint32_t)e2 << 8) * 0x10001u - 0x00030003u;
 	const uint32_t NQX = PK2(-qe) | 0x00080008u, NQY = PK2(-qe) | 0x00100010u, NQX2 = PK2(-qe2) | 0x00200020u, NQY2 = PK2(-qe2) | 0x00400040u;
 	const uint32_t SCN_T = PK2((int)A.scn) + 0x00070007u;
 	const uint32_t KMM = (uint32_t)((int)A.mch - (int)A.mis) << 8;
 	const uint32_t E_QE = PK_ENC(-q - e), E_E = PK_ENC(-e), E_E2 = PK_ENC(-e2), E_LD = PK_ENC(A.long_diff), E_QE2 = PK_ENC(-q2 - e2);
+	const uint32_t XT0 = E_QE | 6u, YT0 = E_QE | 5u, X2T0 = E_QE2 | 4u, Y2T0 = E_QE2 | 3u; // gap states at a boundary, tagged
 	const int lt = A.long_thres;
 
 	#pragma unroll 1
@@ -326,18 +354,19 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			for (int h = 0; h < 2; ++h) {
 				const int t = t0 + h * H + c;
 				const int b = t < tlen? fetch_t(A.target, A.t_packed, jb.t_start + (long long)t * jb.t_step) : 4;
+				ts[t] = (uint8_t)b;
 				// top boundary (ksw2_extd2_sse.c:159-162)
 				const uint32_t u0 = t == 0? E_QE : t < lt? E_E : t == lt? E_LD : E_E2;
 				tbm |= (b < 4? 1u << b : 0u) << (16 * h);
 				msc |= (PK_ENC(b == 4? (int)A.scn : (int)A.mis) + 7u) << (16 * h);
 				u |= u0 << (16 * h);
 			}
-			TBM[c] = tbm, MSC[c] = msc, U[c] = u, Y[c] = E_QE * 0x10001u, Y2[c] = E_QE2 * 0x10001u;
+			TBM[c] = tbm, MSC[c] = msc, U[c] = u, Y[c] = YT0 * 0x10001u, Y2[c] = Y2T0 * 0x10001u;
 		}
 		__syncwarp();
 		int hrow = 0;
 		uint32_t hcol_acc = 0;             // sum over rows of enc(v) in column 0 (only meaningful in the group's first lane)
-		uint32_t vl_end = PK2(0), xl_end = E_QE * 0x10001u, x2l_end = E_QE2 * 0x10001u; // right edges of the previous step (lo: block A, hi: block B)
+		uint32_t vl_end = PK2(0), xl_end = XT0 * 0x10001u, x2l_end = X2T0 * 0x10001u; // right edges of the previous step (lo: block A, hi: block B); x words tagged
 		uint32_t oh_prev = 0x80;           // one-hot query base of row jA-1
 		const int n_lanes = (tlen + C - 1) / C;
 		int n_steps = act? qlen + 2 * (n_lanes - 1) + 1 : 0;
@@ -355,9 +384,12 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 				bv = jA == lt? E_LD : bv;
 				bv = jA == 0? E_QE : bv;
 				const bool first = sub == 0;
-				uint32_t vl = __byte_perm(first? bv : sv >> 16, vl_end, 0x5410);
-				uint32_t xl = __byte_perm(first? E_QE : sx >> 16, xl_end, 0x5410);
-				uint32_t x2l = __byte_perm(first? E_QE2 : sx2 >> 16, x2l_end, 0x5410);
+				const uint32_t vlE = __byte_perm(first? bv : sv >> 16, vl_end, 0x5410);
+				uint32_t xl = __byte_perm(first? XT0 : sx >> 16, xl_end, 0x5410);
+				uint32_t x2l = __byte_perm(first? X2T0 : sx2 >> 16, x2l_end, 0x5410);
+				// v travels through the column loop without its bias (vl = enc(v) - BB2, a 32-bit difference whose half-borrows cancel in
+				// every sum it enters): x + v and z - v are then two-input operations
+				uint32_t vl = PK_FADD(vlE, NBB2);
 				const uint32_t oh = qs[jA];
 				const uint32_t ohx = oh | oh_prev << 16;
 				const uint32_t qbm = ohx & 0x000f000fu;
@@ -371,27 +403,28 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 					const uint32_t f = __vminu2(TBM[c] & qbm, 0x00010001u);
 					uint32_t sc = f * KMM + MSC[c];
 					sc = (sc & ~mN) | (SCN_T & mN);
-					const uint32_t uc = U[c];
-					const uint32_t a = xl + vl + K_A, a2 = x2l + vl + K_A2, b = Y[c] + uc + K_B, b2 = Y2[c] + uc + K_B2;
+					const uint32_t uc = U[c], ucr = PK_FADD(uc, NBB2);
+					const uint32_t a = PK_FADD(xl, vl), a2 = PK_FADD(x2l, vl), b = PK_FADD(Y[c], ucr), b2 = PK_FADD(Y2[c], ucr);
 					uint32_t zt = __vimax3_u16x2(sc, a, b);
 					zt = __vimax3_u16x2(zt, a2, b2);
 					const uint32_t z8 = zt & CLEAN; // no clip to the match score (:243) needed: H(i,j) - H(i-1,j-1) <= match holds in every cell when the band does not clip
-					const uint32_t un = z8 - vl + BB2, vn = z8 - uc + BB2;
-					const uint32_t xt = __vmaxu2(a - z8 + KX, NQX), yt = __vmaxu2(b - z8 + KY, NQY);
-					const uint32_t x2t = __vmaxu2(a2 - z8 + KX2, NQX2), y2t = __vmaxu2(b2 - z8 + KY2, NQY2);
+					const uint32_t un = PK_FSUB(z8, vl), vn = PK_FSUB(z8, uc); // un = enc(u'), vn = enc(v') - BB2
+					const uint32_t xt = __vmaxu2(PK_FADD(a, PK_FSUB(KX, z8)), NQX), yt = __vmaxu2(PK_FADD(b, PK_FSUB(KY, z8)), NQY);
+					const uint32_t x2t = __vmaxu2(PK_FADD(a2, PK_FSUB(KX2, z8)), NQX2), y2t = __vmaxu2(PK_FADD(b2, PK_FSUB(KY2, z8)), NQY2);
 					wd[c] = (xt | yt | x2t) | y2t | zt; // low byte of each half = tag | flags (the value sits in the high byte)
-					xl = xt & CLEAN, Y[c] = yt & CLEAN, x2l = x2t & CLEAN, Y2[c] = y2t & CLEAN;
+					// next cell's gap states: value bytes kept, low bytes replaced by the candidate tags (one PRMT each)
+					xl = __byte_perm(xt, TAGS, 0x3414), Y[c] = __byte_perm(yt, TAGS, 0x3515), x2l = __byte_perm(x2t, TAGS, 0x3616), Y2[c] = __byte_perm(y2t, TAGS, 0x3717);
 					U[c] = un, vl = vn;
-					if (c == 0) v_first = vn;
+					if (c == 0) v_first = vn ^ 0x8000u; // low half back to enc(v)
 				}
-				vl_end = vl, xl_end = xl, x2l_end = x2l;
+				vl_end = PK_FADD(vl, BB2), xl_end = xl, x2l_end = x2l;
 				if (jA < qlen) hcol_acc += v_first & 0xffffu;
 				if (jA == 0) { // block B has not started: put its column state (hi halves) back to the top boundary
 					#pragma unroll
 					for (int c = 0; c < H; ++c) {
 						const int t = t0 + H + c;
 						const uint32_t u0 = t < lt? E_E : t == lt? E_LD : E_E2; // t >= 1 here
-						U[c] = (U[c] & 0xffffu) | u0 << 16, Y[c] = (Y[c] & 0xffffu) | E_QE << 16, Y2[c] = (Y2[c] & 0xffffu) | E_QE2 << 16;
+						U[c] = (U[c] & 0xffffu) | u0 << 16, Y[c] = (Y[c] & 0xffffu) | YT0 << 16, Y2[c] = (Y2[c] & 0xffffu) | Y2T0 << 16;
 					}
 				}
 				// score pieces: H(t, qlen-1) = H(t-1, qlen-1) + u(t, qlen-1) along the last row
@@ -411,17 +444,19 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 					lo[k] = __byte_perm(r01, r23, 0x5410), hi[k] = __byte_perm(r01, r23, 0x7632);
 				}
 				if (jA < qlen) {
-					if (CPH == 1) *pa = (uint8_t)lo[0];
-					else if (CPH == 2) *(uint16_t*)pa = (uint16_t)lo[0];
-					else if (CPH == 4) *(uint32_t*)pa = lo[0];
-					else *(uint2*)pa = make_uint2(lo[0], lo[NW - 1]);
+					if constexpr (CPH == 1) *pa = (uint8_t)lo[0];
+					else if constexpr (CPH == 2) *(uint16_t*)pa = (uint16_t)lo[0];
+					else if constexpr (CPH == 4) *(uint32_t*)pa = lo[0];
+					else if constexpr (CPH == 8) *(uint2*)pa = make_uint2(lo[0], lo[NW - 1]);
+					else *(uint4*)pa = make_uint4(lo[0], lo[1], lo[2], lo[NW - 1]);
 				}
 				if (jA >= 1) {
 					uint8_t *pb = pa - W + CPH;
-					if (CPH == 1) *pb = (uint8_t)hi[0];
-					else if (CPH == 2) *(uint16_t*)pb = (uint16_t)hi[0];
-					else if (CPH == 4) *(uint32_t*)pb = hi[0];
-					else *(uint2*)pb = make_uint2(hi[0], hi[NW - 1]);
+					if constexpr (CPH == 1) *pb = (uint8_t)hi[0];
+					else if constexpr (CPH == 2) *(uint16_t*)pb = (uint16_t)hi[0];
+					else if constexpr (CPH == 4) *(uint32_t*)pb = hi[0];
+					else if constexpr (CPH == 8) *(uint2*)pb = make_uint2(hi[0], hi[NW - 1]);
+					else *(uint4*)pb = make_uint4(hi[0], hi[1], hi[2], hi[NW - 1]);
 				}
 			}
 		}
@@ -447,24 +482,46 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			uint32_t run_op = 0, run_len = 0; // pending CIGAR run (lane 0 writes it when the operator changes)
 			#define PK_EMIT(op_, len_) do { const uint32_t o__ = (op_), l__ = (len_); if (l__) { if (run_len && o__ == run_op) run_len += l__; \
 				else { if (run_len && lane == 0) cig[n] = run_len << 4 | run_op; n += run_len? 1 : 0; run_op = o__, run_len = l__; } } } while (0)
+			// The traceback bytes live in HBM/L2; reading them cell by cell along the path is a chain of dependent global loads (the
+			// long-scoreboard stall that kept half of the warps waiting in round 1). The warp stages a tile instead -- the 32 rows up from
+			// the current cell x the 80 physical bytes that cover the 32 columns left of it, five independent 16-byte loads per lane --
+			// and walks inside it at shared-memory latency; a new tile is staged when the path leaves the current one (~every 32 steps).
+			bool have = false;
+			int tj = 0, tpb = 0;
 			while (i >= 0 && jj >= 0) {
 				const int di = (state == 0 || state == 1 || state == 3)? 1 : 0, dj = (state == 0 || state == 2 || state == 4)? 1 : 0;
 				const int ci = i - lane * di, cj = jj - lane * dj;
 				const bool inr = ci >= 0 && cj >= 0;
-				uint32_t tmp = 0;
-				if (inr) {
-					const int wi = ci % C;
-					tmp = gp[(size_t)cj * W + (ci / C) * CP + (wi < H? wi : CPH + wi - H)] ^ 0x7fu;
+				int ph = 0;
+				if (inr) { const int wi = ci % C; ph = (ci / C) * CP + (wi < H? wi : CPH + wi - H); }
+				const bool intile = have && inr && cj <= tj && cj > tj - 32 && ph >= tpb && ph < tpb + TW;
+				if (!__shfl_sync(full, (int)intile, 0)) { // the current cell is not staged: stage the tile that has it in its bottom right corner
+					const int c0 = i > 31? i - 31 : 0, w0 = c0 % C;
+					tj = jj, tpb = ((c0 / C) * CP + (w0 < H? w0 : CPH + w0 - H)) & ~15;
+					__syncwarp();
+					const int rr = tj - lane;
+					if (rr >= 0) {
+						const uint4 *src = (const uint4*)(gp + (size_t)rr * W + tpb);
+						uint4 *dst = (uint4*)(tile + lane * TW);
+						#pragma unroll
+						for (int k = 0; k < TW / 16; ++k) dst[k] = src[k];
+					}
+					__syncwarp();
+					have = true;
+					continue;
 				}
-				const bool cont = inr && (state == 0? (tmp & 7) == 0 : (tmp >> (state + 2) & 1) != 0);
+				uint32_t tmp = 0;
+				if (intile) tmp = tile[(tj - cj) * TW + (ph - tpb)] ^ 0x7fu;
+				const bool cont = intile && (state == 0? (tmp & 7) == 0 : (tmp >> (state + 2) & 1) != 0);
 				const unsigned stop = __ballot_sync(full, !cont);
 				const int r = stop? __ffs(stop) - 1 : 32;
 				PK_EMIT(state == 0? 0u : di? 2u : 1u, (uint32_t)r);
 				i -= r * di, jj -= r * dj;
 				if (r < 32) {
 					const uint32_t tr = __shfl_sync(full, tmp, r);
-					const bool in_r = __shfl_sync(full, (int)inr, r) != 0;
+					const bool in_r = __shfl_sync(full, (int)inr, r) != 0, in_t = __shfl_sync(full, (int)intile, r) != 0;
 					if (!in_r) break;              // ran off the matrix: the leftover is a leading gap (below)
+					if (!in_t) continue;           // ran off the tile: the next round stages the tile around the cell the run stopped at
 					if (state == 0) {              // first cell that leaves the diagonal: its own step, in its new state
 						state = tr & 7;
 						if (state == 1 || state == 3) { PK_EMIT(2u, 1u); --i; } else { PK_EMIT(1u, 1u); --jj; }
@@ -482,8 +539,7 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			int zd_max = -1, zd_t0 = -1, zd_t1 = -1, zd_q0 = -1, zd_q1 = -1;
 			if (g_flag & MMB_JOB_ZDROP) {
 				const uint8_t *gq = smem + (size_t)(wk * NJ + g) * A.qmax;
-				const long long g_ts = (long long)__shfl_sync(full, (int)(jb.t_start >> 32), src) << 32 | (unsigned)__shfl_sync(full, (int)jb.t_start, src);
-				const int g_tstep = __shfl_sync(full, jb.t_step, src);
+				const uint8_t *gt = smem + (size_t)nwk * NJ * A.qmax + (size_t)(wk * NJ + g) * TSM;
 				const int zq = A.zd_q, ze = A.zd_e, mch = A.mch, mis = A.mis, scn = A.scn;
 				int sco = 0, mx = INT32_MIN, mi = -1, mj = -1, ti0 = 0, qj0 = 0;
 				zd_max = 0;
@@ -496,7 +552,7 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 							int sc = 0;
 							if (valid) {
 								const uint32_t oh = gq[qj];
-								const int tb = fetch_t(A.target, A.t_packed, g_ts + (long long)ti * g_tstep);
+								const int tb = gt[ti];
 								sc = (oh == 0x80 || tb == 4)? scn : (oh >> tb & 1)? mch : mis;
 							}
 							int S = sc;
@@ -607,6 +663,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 	if (q2 + e2 < q + e) std::swap(q, q2), std::swap(e, e2);
 	A.q = q, A.e = e, A.q2 = q2, A.e2 = e2;
 	A.zd_q = sc->q, A.zd_e = sc->e;
+	A.one = 1u, A.neg1 = 0xffffffffu;
 	A.mch = sc->mat[0], A.mis = sc->mat[1], A.scn = sc->mat[24] == 0? (int8_t)(-e2) : sc->mat[24];
 	for (int i = 0; i < 25; ++i) A.mat[i] = sc->mat[i];
 	int lt = e != e2? (q2 - q) / (e - e2) - 1 : 0;
@@ -618,10 +675,10 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 	const int amax = std::max(std::abs((int)A.mch), std::max(std::abs((int)A.mis), std::abs((int)A.scn)));
 	const bool pk_ok = !no_pk && 2 * std::max(q + e, q2 + e2) + amax + 8 <= 127 && A.mch > 0 && A.mis <= 0 && A.scn <= 0;
 	// column strips: the smallest C with 32*C >= tlen keeps the idle-lane fraction low (C is a template parameter)
-	static const int CW[] = { 2, 4, 6, 7, 8, 9, 10, 12, 14, 16,   4, 8, 12, 16,   10, 12, 14, 16 };
-	static const int CPW[] = { 4, 4, 8, 8, 8, 16, 16, 16, 16, 16,   4, 8, 16, 16,   16, 16, 16, 16 };
-	static const int LNW[] = { 32, 32, 32, 32, 32, 32, 32, 32, 32, 32,   16, 16, 16, 16,   32, 32, 32, 32 };
-	const int NS = 10, NC = 18; // [0,NS): scalar kernel widths, [NS,NC): packed kernel widths (16-lane classes, then 32-lane)
+	static const int CW[] = { 2, 4, 6, 7, 8, 9, 10, 12, 14, 16,   4, 8, 12, 16, 20, 24,   14, 16 };
+	static const int CPW[] = { 4, 4, 8, 8, 8, 16, 16, 16, 16, 16,   4, 8, 16, 16, 32, 32,   16, 16 };
+	static const int LNW[] = { 32, 32, 32, 32, 32, 32, 32, 32, 32, 32,   16, 16, 16, 16, 16, 16,   32, 32 };
+	const int NS = 10, NC = 18; // [0,NS): scalar kernel widths, [NS,NC): packed kernel widths (16-lane classes up to tlen 384, then 32-lane)
 	std::vector<int> v[NC];
 	for (int i : idx) {
 		const bool pk = pk_ok && !(h_jobs[i].flag & MMB_KSW_GENERIC_SC);
@@ -639,14 +696,14 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 		const int C = CW[k], W = LNW[k] * CPW[k], NJ = 32 / LNW[k];
 		A.qmax = (maxq + 1 + 15) / 16 * 16;
 		const int threads = 128, nwk = threads / 32;
-		const size_t smem = k >= NS? (size_t)A.qmax * nwk * NJ : (size_t)(A.qmax + 1024) * nwk;
+		const size_t smem = k >= NS? ((size_t)A.qmax + (size_t)LNW[k] * C) * nwk * NJ + (size_t)32 * 80 * nwk : (size_t)(A.qmax + 1024) * nwk;
 		void (*kern)(FastArgs) = nullptr;
 		if (k >= NS && NJ == 2) switch (C) {
 		case 4: kern = ksw_pk_kernel<2, 16>; break;   case 8: kern = ksw_pk_kernel<4, 16>; break;
-		case 12: kern = ksw_pk_kernel<6, 16>; break;  default: kern = ksw_pk_kernel<8, 16>; break;
+		case 12: kern = ksw_pk_kernel<6, 16>; break;  case 16: kern = ksw_pk_kernel<8, 16>; break;
+		case 20: kern = ksw_pk_kernel<10, 16>; break; default: kern = ksw_pk_kernel<12, 16>; break;
 		}
 		else if (k >= NS) switch (C) {
-		case 10: kern = ksw_pk_kernel<5, 32>; break;  case 12: kern = ksw_pk_kernel<6, 32>; break;
 		case 14: kern = ksw_pk_kernel<7, 32>; break;  default: kern = ksw_pk_kernel<8, 32>; break;
 		}
 		else switch (C) {
@@ -668,7 +725,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 		MMB_CUDA_CHECK(cudaMemsetAsync(d_order, 0, sizeof(int), ctx->stream));
 		A.counter = d_order, A.order = d_order + 1, A.n = (int)v[k].size();
 		KswPlan pl;
-		pl.pws_bytes = A.pws_stride * (size_t)grid * nwk * NJ, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nwk * NJ;
+		pl.pws_bytes = A.pws_stride * (size_t)grid * nwk * NJ + 256 /* the tile loads may read past the last row */, pl.cigws_bytes = A.cigws_stride * 4 * (size_t)grid * nwk * NJ;
 		const FastArgs A0 = A;
 		pl.go = [=](uint8_t *pws, uint32_t *cigws) {
 			FastArgs B = A0;

@@ -139,6 +139,29 @@ int mmb_chain_rmq_batch_host(mmb_ctx_t *ctx, const mmb_chain_par_t *par, int n_r
 							 int32_t *n_u, int32_t *n_v, uint64_t *u_out, uint64_t *a_out_xy);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * K4: per-hit tail of the alignment driver on the device   (replaces mm_append_cigar align.c:317-334, mm_fix_cigar
+ * align.c:105-181 and mm_update_extra align.c:254-303 for finished hits)
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+	int64_t q0;            /* offset of the read's first base in `query` */
+	int64_t t0;            /* offset of the hit's first target base in `target` */
+	int32_t qlen;          /* read length */
+	int32_t qs;            /* start of the aligned query piece on the strand it is read on */
+	int32_t rev;           /* 1: the query piece is read on the reverse-complement strand */
+	int32_t qspan, tspan;  /* query / target bases the hit's CIGAR consumes */
+	int32_t piece_first, n_pieces; /* the hit's ksw2 pieces, in driver order */
+	int32_t pad;
+} mmb_tail_hit_t;
+typedef struct { int32_t n_cigar, blen, mlen, n_ambi, dp_max, qshift, tshift, status, is_spliced, pad[3]; } mmb_tail_out_t;
+/* Kernel-level entry with HOST buffers. query / target: nt4 codes (0..4), one byte per base (the target is packed to the index's
+ * 4-bit layout on the way in). piece_len[n_pieces_total] operations per piece, stored back to back in ops[]. mat: the 5x5 scoring
+ * matrix; q, e: opt->q / opt->e. out[n_hits]; hit i's final CIGAR goes to cigar_out + cig_off[i] (cig_off[n_hits+1]: prefix sums of the
+ * hits' piece totals, computed by the caller). Returns 0. */
+int mmb_tail_batch_host(mmb_ctx_t *ctx, int n_hits, const mmb_tail_hit_t *hits, int64_t n_pieces_total, const uint32_t *piece_len, const uint32_t *ops,
+						const uint8_t *query, int64_t query_len, const uint8_t *target, int64_t target_len, const int8_t *mat, int q, int e,
+						const int64_t *cig_off, mmb_tail_out_t *out, uint32_t *cigar_out);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Index on device + whole-path batch mapping are driven through the minimap.h API (include/minimap.h):
  * mm_idx_* builds/loads the index on the GPU (side table keyed by mm_idx_t*), mm_map_file / mm_map_batch run the GPU
  * batch scheduler that replaces worker_pipeline/kt_for (map.c:403-691). The entries below are the knobs and hand-off

@@ -20,6 +20,7 @@ namespace {
 struct Ez {
 	int max, zdropped, max_q, max_t, mqe, mqe_t, mte, mte_q, score, n_cigar, reach_end;
 	const uint32_t *cigar;
+	const uint32_t *dcigar;   // device copy of the CIGAR (K4 input)
 	int zd_max, zd_pos[2][2]; // mm_test_zdrop's scan evaluated by the kernel (MMB_JOB_ZDROP); zd_max < 0: not available
 };
 
@@ -27,7 +28,7 @@ inline void ez_reset(Ez *ez) // ksw2.h:164-169
 {
 	ez->max_q = ez->max_t = ez->mqe_t = ez->mte_q = -1;
 	ez->max = 0, ez->score = ez->mqe = ez->mte = KSW_NEG_INF_H;
-	ez->n_cigar = 0, ez->zdropped = 0, ez->reach_end = 0, ez->cigar = 0;
+	ez->n_cigar = 0, ez->zdropped = 0, ez->reach_end = 0, ez->cigar = 0, ez->dcigar = 0;
 	ez->zd_max = -1;
 }
 
@@ -98,7 +99,7 @@ struct Driver {
 			ez->max = d.r.max, ez->zdropped = d.r.zdropped, ez->max_q = d.r.max_q, ez->max_t = d.r.max_t;
 			ez->mqe = d.r.mqe, ez->mqe_t = d.r.mqe_t, ez->mte = d.r.mte, ez->mte_q = d.r.mte_q;
 			ez->score = d.r.score, ez->n_cigar = d.r.n_cigar, ez->reach_end = d.r.reach_end;
-			ez->cigar = d.cig;
+			ez->cigar = d.cig, ez->dcigar = d.dcig;
 			ez->zd_max = d.r.zd_max, ez->zd_pos[0][0] = d.r.zd_t0, ez->zd_pos[0][1] = d.r.zd_t1, ez->zd_pos[1][0] = d.r.zd_q0, ez->zd_pos[1][1] = d.r.zd_q1;
 			return true;
 		}
@@ -229,6 +230,20 @@ struct Driver {
 			memcpy(p->cigar + p->n_cigar, cigar, n_cigar * 4);
 			p->n_cigar += n_cigar;
 		}
+	}
+
+	// one piece of a hit's CIGAR: appended here, or (device tail) only recorded -- the hit keeps a header-only mm_extra_t for dp_score
+	int fin_first = 0; // first piece of the hit being walked
+	void add_cigar(mm_reg1_t *r, const Ez &ez) {
+		if (!ra.defer) { append_cigar(r, ez.n_cigar, ez.cigar); return; }
+		if (ez.n_cigar == 0) return;
+		if (r->p == 0) {
+			uint32_t capacity = roundup32(sizeof(mm_extra_t) / 4);
+			r->p = (mm_extra_t*)calloc(capacity, 4);
+			r->p->capacity = capacity;
+		}
+		HlFinJob j; j.dcig = ez.dcigar, j.n = (uint32_t)ez.n_cigar;
+		ra.fin_jobs.push_back(j);
 	}
 
 	static void fix_cigar(mm_reg1_t *r, const uint8_t *qseq, const uint8_t *tseq, int *qshift, int *tshift) { // align.c:105-181
@@ -613,6 +628,7 @@ struct Driver {
 		pending = false;
 		r2->cnt = 0;
 		if (r->cnt == 0) return true;
+		fin_first = (int)ra.fin_jobs.size();
 		bw = (int)(opt->bw * 1.5 + 1.);
 		bw_long = (int)(opt->bw_long * 1.5 + 1.);
 		if (bw_long < bw) bw_long = bw;
@@ -701,7 +717,7 @@ struct Driver {
 			Seg s; s.rev = qrev, s.qs = qs0, s.qlen = qs - qs0, s.q_reversed = 1, s.rid = rid, s.rs = rs0, s.tlen = rs - rs0, s.t_reversed = 1, s.t_rc = trc;
 			bool ok = align_pair(s, bw, opt->end_bonus, r->split_inv? opt->zdrop_inv : opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY | MMB_KSW_RIGHT | MMB_KSW_REV_CIGAR, &ez);
 			if (ok) {
-				if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
+				if (ez.n_cigar > 0) { add_cigar(r, ez); r->p->dp_score += ez.max; }
 				rs1 = rs - (ez.reach_end? ez.mqe_t + 1 : ez.max_t + 1);
 				qs1 = qs - (ez.reach_end? qs - qs0 : ez.max_q + 1);
 			} else rs1 = rs, qs1 = qs; // placeholder while the result is pending; the region is replayed later
@@ -727,7 +743,7 @@ struct Driver {
 					if (zdrop_code > 0) ok = align_pair(s, bw1, -1, zdrop_code == 2? opt->zdrop_inv : opt->zdrop, sflag, &ez); // second pass
 					else if (zdrop_code < 0) ok = false;
 					if (ok) {
-						if (ez.n_cigar > 0) append_cigar(r, ez.n_cigar, ez.cigar);
+						if (ez.n_cigar > 0) add_cigar(r, ez);
 						if (ez.zdropped) { // truncated by Z-drop
 							if (!r->p) {
 								uint32_t capacity = roundup32(sizeof(mm_extra_t) / 4);
@@ -757,18 +773,24 @@ struct Driver {
 			Seg s; s.rev = qrev, s.qs = qe, s.qlen = qe0 - qe, s.q_reversed = 0, s.rid = rid, s.rs = re, s.tlen = re0 - re, s.t_reversed = 0, s.t_rc = trc;
 			bool ok = align_pair(s, bw, opt->end_bonus, opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY, &ez);
 			if (ok) {
-				if (ez.n_cigar > 0) { append_cigar(r, ez.n_cigar, ez.cigar); r->p->dp_score += ez.max; }
+				if (ez.n_cigar > 0) { add_cigar(r, ez); r->p->dp_score += ez.max; }
 				re1 = re + (ez.reach_end? ez.mqe_t + 1 : ez.max_t + 1);
 				qe1 = qe + (ez.reach_end? qe0 - qe : ez.max_q + 1);
 			}
 		}
-		if (pending) return false;
+		if (pending) { ra.fin_jobs.resize(fin_first); return false; }
 		assert(qe1 <= qlen);
 		r->rs = rs1, r->re = re1;
 		if (!rev || (opt->flag & MM_F_QSTRAND)) r->qs = qs1, r->qe = qe1;
 		else r->qs = qlen - qe1, r->qe = qlen - qs1;
 		assert(re1 - rs1 <= re0 - rs0);
-		if (r->p) {
+		if (r->p && ra.defer) { // the device tail assembles, fixes and rescans this hit (K4)
+			HlFinHit h;
+			h.p = r->p, h.rev = r->rev, h.qs = qs1, h.rid = rid, h.rs = rs1, h.qspan = qe1 - qs1, h.tspan = re1 - rs1;
+			h.job_first = fin_first, h.n_jobs = (int)ra.fin_jobs.size() - fin_first, h.n_cig_max = 0;
+			for (int k = fin_first; k < (int)ra.fin_jobs.size(); ++k) h.n_cig_max += ra.fin_jobs[k].n;
+			ra.fin_hits.push_back(h);
+		} else if (r->p) {
 			get_tseq(rid, rs1, re1, tseq, trc);
 			update_extra(r, qptr(qst? 0 : r->rev, qs1), tseq.data(), opt->q, opt->e, opt->flag & MM_F_EQX, 1);
 			if (rev && r->p->trans_strand) r->p->trans_strand ^= 3;
@@ -856,7 +878,9 @@ mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAli
 	HpScope hp_(HP_SKEL);
 	int32_t n_regs = *n_regs_, n_a;
 	Driver D(opt, mi, ra);
-	ra.incomplete = false;
+	ra.incomplete = false, ra.defer_abort = false;
+	ra.fin_hits.clear(), ra.fin_jobs.clear();
+	if (ra.defer && !hl_defer_supported(opt)) ra.defer = false;
 	(void)n_a_in;
 	n_a = hl_squeeze_a(n_regs, regs, a); // idempotent across replays: after the first call regions are already packed in order
 	for (int i = 0; i < n_regs; ++i) {
@@ -885,6 +909,7 @@ mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAli
 		}
 		if (r2.cnt > 0) regs = insert_reg(&r2, i, &n_regs, regs);
 		if (i > 0 && regs[i].split_inv && !(opt->flag & MM_F_NO_INV)) {
+			if (ra.defer) { ra.defer_abort = true; *n_regs_ = n_regs; return regs; } // the probe reads the two hits' final coordinates
 			int ret = D.align1_inv(&regs[i-1], &regs[i], &r2);
 			if (ret > 0) {
 				regs = insert_reg(&r2, i, &n_regs, regs);
@@ -894,11 +919,40 @@ mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAli
 	}
 	*n_regs_ = n_regs;
 	if (ra.incomplete) return regs;
+	if (ra.defer && !ra.fin_hits.empty()) return regs; // hl_align_apply_fin() + hl_align_finish() complete the read
+	hl_align_finish(opt, ra, n_regs_, regs);
+	return regs;
+}
+
+bool hl_align_apply_fin(ReadAlign &ra, int n_regs, mm_reg1_t *regs, const HlFinOut *fin, const uint32_t *const *cig)
+{
+	for (size_t k = 0; k < ra.fin_hits.size(); ++k) if (fin[k].status != 0) return false;
+	for (size_t k = 0; k < ra.fin_hits.size(); ++k) {
+		const HlFinHit &h = ra.fin_hits[k];
+		const HlFinOut &o = fin[k];
+		mm_reg1_t *r = nullptr;
+		for (int i = 0; i < n_regs; ++i) if (regs[i].p == h.p) { r = &regs[i]; break; }
+		assert(r);
+		const uint32_t capacity = roundup32((uint32_t)o.n_cigar + sizeof(mm_extra_t) / 4);
+		mm_extra_t *p = (mm_extra_t*)realloc(r->p, (size_t)capacity * 4);
+		p->capacity = capacity, p->n_cigar = (uint32_t)o.n_cigar;
+		if (o.n_cigar > 0) memcpy(p->cigar, cig[k], (size_t)o.n_cigar * 4);
+		r->p = p;
+		if (o.qshift) { if (r->rev) r->qe -= o.qshift; else r->qs += o.qshift; } // mm_fix_cigar's leading I/D (align.c:172-180)
+		r->rs += o.tshift;
+		r->blen = o.blen, r->mlen = o.mlen, r->is_spliced = o.is_spliced;
+		p->n_ambi += (uint32_t)o.n_ambi;
+		p->dp_max = p->dp_max0 = o.dp_max;
+	}
+	return true;
+}
+
+void hl_align_finish(const mm_mapopt_t *opt, ReadAlign &ra, int *n_regs_, mm_reg1_t *regs)
+{
 	hl_filter_regs(opt, ra.qlen, n_regs_, regs);
 	if (!(opt->flag & (MM_F_SR | MM_F_SR_RNA | MM_F_ALL_CHAINS)) && !opt->split_prefix && ra.qlen >= opt->rank_min_len) {
 		hl_update_dp_max(ra.qlen, *n_regs_, regs, opt->rank_frac, opt->a, opt->b);
 		hl_filter_regs(opt, ra.qlen, n_regs_, regs);
 	}
 	hl_hit_sort(n_regs_, regs, opt->alt_drop);
-	return regs;
 }

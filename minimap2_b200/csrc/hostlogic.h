@@ -51,7 +51,16 @@ struct KswKeyHash {
 struct KswDone {            // a finished job: ksw_extz_t fields + its CIGAR (points into the wave's pinned result buffer)
 	mmb_ksw_res_t r;
 	const uint32_t *cig;
+	const uint32_t *dcig = nullptr; // the same CIGAR in the device arena of its wave (kept until the batch ends; input of K4)
 };
+struct HlFinJob { const uint32_t *dcig; uint32_t n; };   // one piece of a hit's CIGAR (device address, operations)
+struct HlFinHit {            // a hit whose CIGAR assembly / mm_fix_cigar / mm_update_extra is left to the device tail (finalize.cu)
+	mm_extra_t *p;           // identifies the hit in the read's mm_reg1_t array (allocated once in this mode: header only)
+	int32_t rev, qs, rid, rs, qspan, tspan; // strand the query piece is read on, its start there, target sequence and start, bases consumed
+	int32_t job_first, n_jobs;
+	uint32_t n_cig_max;      // sum of the pieces' operation counts (upper bound of the final count)
+};
+struct HlFinOut { int32_t n_cigar, blen, mlen, n_ambi, dp_max, qshift, tshift, status, is_spliced, pad[3]; }; // = FinOut (pipeline.h)
 
 struct ReadAlign {          // per-read alignment working set (lives across waves; pooled across batches, so the vectors keep their capacity)
 	int qlen = 0;
@@ -63,8 +72,12 @@ struct ReadAlign {          // per-read alignment working set (lives across wave
 	std::vector<mmb_ksw_job_t> want; // jobs requested by the current replay
 	std::vector<int> want_slot;      // their slots in keys[]
 	bool incomplete = false;
+	bool defer = false;              // in: finished hits go to the device tail instead of the host's append / fix_cigar / update_extra
+	bool defer_abort = false;        // out: the replay reached a step that needs a hit's final coordinates (inversion probe): redo it with defer off
+	std::vector<HlFinHit> fin_hits;  // out (defer): the hits to finalize, in driver order, and their pieces
+	std::vector<HlFinJob> fin_jobs;
 	mutable size_t hint = 0;         // a replay asks for its jobs in the order the previous one did: search from the last hit on
-	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); incomplete = false; hint = 0; }
+	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); fin_hits.clear(); fin_jobs.clear(); incomplete = defer = defer_abort = false; hint = 0; }
 	int find(const KswKey &k) const { // keys are unique (a key is added only after a miss)
 		const size_t n = keys.size();
 		for (size_t c = 0, i = hint < n? hint : 0; c < n; ++c, i = i + 1 == n? 0 : i + 1)
@@ -77,6 +90,12 @@ struct ReadAlign {          // per-read alignment working set (lives across wave
 // to ra.want and ra.incomplete is set. When complete, *n_regs_/regs hold the aligned hits (regs may be realloc'd).
 // a[] must have its IGNORE/LONG_JOIN marks cleared by the caller before every replay.
 mm_reg1_t *hl_align_skeleton(const mm_mapopt_t *opt, const mm_idx_t *mi, ReadAlign &ra, int *n_regs_, mm_reg1_t *regs, int n_a, m128 *a);
+// With ra.defer set, a complete replay that produced ra.fin_hits stops before the hit-level tail of mm_align_skeleton (align.c:1103-1118);
+// once the device has finalized the hits, hl_align_apply_fin() stores the results (fin[i] / CIGAR at out + off[i] for ra.fin_hits[i]; returns
+// false if a hit must be redone on the host) and hl_align_finish() runs that tail.
+bool hl_align_apply_fin(ReadAlign &ra, int n_regs, mm_reg1_t *regs, const HlFinOut *fin, const uint32_t *const *cig);
+void hl_align_finish(const mm_mapopt_t *opt, ReadAlign &ra, int *n_regs_, mm_reg1_t *regs);
+inline bool hl_defer_supported(const mm_mapopt_t *opt) { return !(opt->flag & (MM_F_SPLICE | MM_F_EQX | MM_F_QSTRAND | MM_F_SR | MM_F_SR_RNA)); }
 
 // ---- host section profiler (MM_B200_TIMING only): cycles per section, summed over threads ----
 enum { HP_SKEL, HP_TSEQ, HP_ZDROP, HP_EXTRA, HP_FETCH, HP_APPEND, HP_PRE, HP_POST, HP_HITS, HP_N };

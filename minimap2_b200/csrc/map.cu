@@ -237,12 +237,16 @@ struct ReadState {
 	int n_regs = 0;
 	mm_reg1_t *regs = nullptr;             // final
 	bool done = false;
+	bool fin_pending = false;              // the replay is complete; its hits wait for the device tail (K4)
 };
 
 struct BatchBufs { // device arenas reused across batches (per context)
 	DevBuf a2, seq, off, mz, mz_off, n_mz, qlen, s_n, s_off, k_idx, k_aoff, flt, mini_pos, n_keep, rep_len, n_a, a_off, a, stk;
 	DevBuf n_u, n_v, u, a_out, ch1, ch2, t1, t2, doff, dense_u, dense_a, dense_mp;
 	DevBuf jobs, res, cig;
+	std::vector<std::unique_ptr<DevBuf>> cig_keep; // one CIGAR arena per (wave, chunk), alive until the batch ends: K4 reads the pieces in place
+	DevBuf fin_in, fin_out;                // K4: hit / piece descriptors; results + assembled CIGARs
+	PinBuf h_fin_in, h_fin_out;
 	DevBuf qlo, qhi, k_cnt;                // skip_seed inputs (ava / strand-restricted modes only)
 	DevBuf dreg, dreg_off;                 // masked intervals of the reads (-T / SDUST only)
 	PinBuf h_seq, h_misc, h_jobs, h_res;
@@ -302,7 +306,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	std::vector<int> live; // reads that go through the pipeline (non-empty, within max_qlen)
 	for (int i = 0; i < n_reads; ++i) {
 		rs[i].qlen = qlens[i], rs[i].seq = seqs[i], rs[i].name = names? names[i] : nullptr;
-		rs[i].ra = nullptr, rs[i].regs0 = nullptr, rs[i].regs = nullptr, rs[i].n_regs = rs[i].n_regs0 = 0, rs[i].done = false;
+		rs[i].ra = nullptr, rs[i].regs0 = nullptr, rs[i].regs = nullptr, rs[i].n_regs = rs[i].n_regs0 = 0, rs[i].done = false, rs[i].fin_pending = false;
 		n_regs_out[i] = 0, regs_out[i] = nullptr;
 		if (rep_len_out) rep_len_out[i] = 0;
 		bool ok = qlens[i] > 0 && !(opt->max_qlen > 0 && qlens[i] > opt->max_qlen); // map.c:243-244
@@ -553,6 +557,39 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		}
 		std::vector<int> active;
 		for (int j = 0; j < n; ++j) if (!rs[live[j]].done) active.push_back(live[j]);
+		// The hit-level tail of the driver (CIGAR assembly, mm_fix_cigar, mm_update_extra) runs on the device for finished reads (K4,
+		// finalize.cu) unless the mode needs it on the host (spliced / =X CIGARs / query-strand) or MM_B200_NO_DEV_FIN is set.
+		static const bool no_dev_fin = getenv("MM_B200_NO_DEV_FIN") != nullptr;
+		const bool use_fin = !no_dev_fin && hl_defer_supported(opt);
+		FinPar fpar;
+		for (int i = 0; i < 25; ++i) fpar.mat[i] = sc.mat[i];
+		fpar.q = (int8_t)opt->q, fpar.e = (int8_t)opt->e, fpar.log_gap = 1;
+		auto post_align = [&](ReadState &r, int n_regs, mm_reg1_t *regs) { // align_regs (map.c:215-225)
+			HpScope hp_(HP_POST);
+			if (!(opt->flag & MM_F_ALL_CHAINS)) {
+				hl_set_parent(opt->mask_level, opt->mask_len, n_regs, regs, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
+				hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 0, (int)(opt->max_gap * 0.8), &n_regs, regs);
+				hl_set_sam_pri(n_regs, regs);
+			}
+			r.n_regs = n_regs, r.regs = regs, r.done = true, r.fin_pending = false;
+		};
+		auto replay = [&](ReadState &r, bool defer, int *n_regs_out_) -> mm_reg1_t* { // one pass of the driver over the read's pristine chains
+			ReadAlign &ra = *r.ra;
+			int n_regs = r.n_regs0;
+			mm_reg1_t *regs;
+			{
+				HpScope hp_(HP_PRE);
+				r.a.assign(r.a_src, r.a_src + r.n_a); // pristine anchors (IGNORE/LONG_JOIN marks cleared)
+				regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
+				memcpy(regs, r.regs0, sizeof(mm_reg1_t) * n_regs);
+			}
+			ra.defer = defer;
+			regs = hl_align_skeleton(opt, mi, ra, &n_regs, regs, r.n_a, r.a.data());
+			*n_regs_out_ = n_regs;
+			return regs;
+		};
+		auto drop_regs = [](int n_regs, mm_reg1_t *regs) { for (int i = 0; i < n_regs; ++i) free(regs[i].p); free(regs); };
+		size_t keep_used = 0;
 		int wave = 0;
 		while (!active.empty()) {
 			// replay every active read; collect the jobs they miss
@@ -561,29 +598,86 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				ReadState &r = rs[active[t]];
 				ReadAlign &ra = *r.ra;
 				ra.want.clear(); ra.want_slot.clear();
-				int n_regs = r.n_regs0;
-				mm_reg1_t *regs;
-				{
-					HpScope hp_(HP_PRE);
-					r.a.assign(r.a_src, r.a_src + r.n_a); // pristine anchors (IGNORE/LONG_JOIN marks cleared)
-					regs = (mm_reg1_t*)malloc(sizeof(mm_reg1_t) * (n_regs > 0? n_regs : 1));
-					memcpy(regs, r.regs0, sizeof(mm_reg1_t) * n_regs);
+				int n_regs;
+				mm_reg1_t *regs = replay(r, use_fin, &n_regs);
+				if (ra.defer_abort) { // an inversion probe needs final hit coordinates: this read keeps the whole driver on the host
+					drop_regs(n_regs, regs);
+					regs = replay(r, false, &n_regs); // jobs the aborted pass asked for stay queued (the full pass asks for a superset)
 				}
-				regs = hl_align_skeleton(opt, mi, ra, &n_regs, regs, r.n_a, r.a.data());
-				if (ra.incomplete) {
-					for (int i = 0; i < n_regs; ++i) free(regs[i].p);
-					free(regs);
-				} else {
-					HpScope hp_(HP_POST);
-					if (!(opt->flag & MM_F_ALL_CHAINS)) { // align_regs (map.c:215-225)
-						hl_set_parent(opt->mask_level, opt->mask_len, n_regs, regs, opt->a * 2 + opt->b, opt->flag & MM_F_HARD_MLEVEL, opt->alt_drop);
-						hl_select_sub(opt->pri_ratio, mi->k * 2, opt->best_n, 0, (int)(opt->max_gap * 0.8), &n_regs, regs);
-						hl_set_sam_pri(n_regs, regs);
-					}
-					r.n_regs = n_regs, r.regs = regs, r.done = true;
-				}
+				if (ra.incomplete) drop_regs(n_regs, regs);
+				else if (ra.defer && !ra.fin_hits.empty()) r.n_regs = n_regs, r.regs = regs, r.fin_pending = true;
+				else post_align(r, n_regs, regs);
 			});
 			lap("  wave replay");
+			// ---- K4: device tail for the reads whose replay is complete ----
+			{
+				std::vector<int> fr;
+				for (size_t t = 0; t < active.size(); ++t) if (rs[active[t]].fin_pending) fr.push_back(active[t]);
+				if (!fr.empty()) {
+					const size_t nf = fr.size();
+					std::vector<int64_t> hoff(nf + 1, 0), joff2(nf + 1, 0);
+					for (size_t t = 0; t < nf; ++t) {
+						const ReadAlign &ra = *rs[fr[t]].ra;
+						hoff[t + 1] = hoff[t] + (int64_t)ra.fin_hits.size(), joff2[t + 1] = joff2[t] + (int64_t)ra.fin_jobs.size();
+					}
+					const int64_t n_hits = hoff[nf], n_pieces = joff2[nf];
+					std::vector<int64_t> coff((size_t)n_hits + 1, 0); // output CIGAR offsets (room for the sum of the pieces)
+					for (size_t t = 0; t < nf; ++t) {
+						const ReadAlign &ra = *rs[fr[t]].ra;
+						for (size_t k = 0; k < ra.fin_hits.size(); ++k) coff[hoff[t] + k + 1] = ra.fin_hits[k].n_cig_max;
+					}
+					for (int64_t i = 0; i < n_hits; ++i) coff[i + 1] += coff[i];
+					const int64_t tot_cig = coff[n_hits];
+					const size_t in_bytes = sizeof(FinReg) * (size_t)n_hits + sizeof(FinJobRef) * (size_t)n_pieces;
+					uint8_t *h_in = bb.h_fin_in.as<uint8_t>(in_bytes + 64);
+					FinReg *h_regs = (FinReg*)h_in;
+					FinJobRef *h_pieces = (FinJobRef*)(h_regs + n_hits);
+					parallel_for((int64_t)nf, n_threads, [&](int64_t t, int) {
+						const ReadState &r = rs[fr[t]];
+						const ReadAlign &ra = *r.ra;
+						for (size_t k = 0; k < ra.fin_jobs.size(); ++k) { FinJobRef &j = h_pieces[joff2[t] + k]; j.cig = ra.fin_jobs[k].dcig, j.n = ra.fin_jobs[k].n, j.pad = 0; }
+						for (size_t k = 0; k < ra.fin_hits.size(); ++k) {
+							const HlFinHit &h = ra.fin_hits[k];
+							FinReg &f = h_regs[hoff[t] + k];
+							f.q0 = ra.q_dev_off, f.t0 = (int64_t)mi->seq[h.rid].offset + h.rs, f.out_off = coff[hoff[t] + k];
+							f.qlen = r.qlen, f.qs = h.qs, f.rev = h.rev, f.qspan = h.qspan, f.tspan = h.tspan;
+							f.job_first = (int32_t)(joff2[t] + h.job_first), f.n_jobs = h.n_jobs, f.pad = 0;
+						}
+					});
+					uint8_t *d_in = bb.fin_in.as<uint8_t>(in_bytes + 64);
+					const size_t out_bytes = sizeof(FinOut) * (size_t)n_hits + 4 * (size_t)tot_cig;
+					uint8_t *d_out = bb.fin_out.as<uint8_t>(out_bytes + 64);
+					uint8_t *h_out = bb.h_fin_out.as<uint8_t>(out_bytes + 64);
+					MMB_CUDA_CHECK(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+					mmb_finalize_device(ctx, (const FinReg*)d_in, (const FinJobRef*)(d_in + sizeof(FinReg) * (size_t)n_hits), (int)n_hits, d_seq, (const uint32_t*)B->d_S,
+										(uint32_t*)(d_out + sizeof(FinOut) * (size_t)n_hits), (FinOut*)d_out, fpar);
+					MMB_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+					MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+					ctx->last_h2d_bytes += in_bytes, ctx->last_d2h_bytes += out_bytes;
+					lap("  device tail");
+					const HlFinOut *h_fin = (const HlFinOut*)h_out;
+					const uint32_t *h_fcig = (const uint32_t*)(h_out + sizeof(FinOut) * (size_t)n_hits);
+					parallel_for((int64_t)nf, n_threads, [&](int64_t t, int) {
+						hl_hp_flush();
+						ReadState &r = rs[fr[t]];
+						ReadAlign &ra = *r.ra;
+						std::vector<const uint32_t*> cp(ra.fin_hits.size());
+						for (size_t k = 0; k < cp.size(); ++k) cp[k] = h_fcig + coff[hoff[t] + k];
+						int n_regs = r.n_regs;
+						mm_reg1_t *regs = r.regs;
+						bool ok;
+						{ HpScope hp_(HP_EXTRA); ok = hl_align_apply_fin(ra, n_regs, regs, h_fin + hoff[t], cp.data()); }
+						if (ok) hl_align_finish(opt, ra, &n_regs, regs);
+						else { // a gap penalty outside the fixed-point range (never with sane scoring): the host driver redoes the read
+							drop_regs(n_regs, regs);
+							regs = replay(r, false, &n_regs);
+							if (ra.incomplete) { fprintf(stderr, "[ERROR] minimap2_b200: host redo of a finished read is incomplete\n"); abort(); }
+						}
+						post_align(r, n_regs, regs);
+					});
+					lap("  tail apply");
+				}
+			}
 			// gather jobs
 			std::vector<int> still;
 			std::vector<int64_t> joff(active.size() + 1, 0);
@@ -604,7 +698,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				});
 				// run in chunks to bound the device result buffers; results land in pinned host memory that stays alive until
 				// the end of the batch, so per-read caches just point into it
-				const int64_t CH = 1 << 20;
+				const int64_t CH = 1 << 22;
 				mmb_ksw_res_t *res = bb.h_res.as<mmb_ksw_res_t>((size_t)n_jobs);
 				// CIGAR arena estimate per job: (qlen+tlen)/2 + 8 operations covers every realistic alignment, the true bound is qlen+tlen
 				// (alternating 1I1D); an overflow is recovered below by rerunning the chunk with the exact size the kernels reported
@@ -618,6 +712,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				GateHold gatew(G.gated, 1);
 				lap("  gate wait w");
 				std::vector<int64_t> chunk_base; // offset of each chunk's CIGAR block inside h_cig
+				std::vector<const uint32_t*> chunk_dev; // and the block's address in its device arena
 				int64_t cig_fill = 0;
 				for (int64_t b = 0; b < n_jobs; b += CH) {
 					const int64_t m = std::min(CH, n_jobs - b);
@@ -626,7 +721,8 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 					for (;;) {
 						mmb_ksw_job_t *d_jobs = bb.jobs.as<mmb_ksw_job_t>((size_t)m);
 						mmb_ksw_res_t *d_res = bb.res.as<mmb_ksw_res_t>((size_t)m);
-						uint32_t *d_cig = bb.cig.as<uint32_t>((size_t)cap + 4);
+						while (bb.cig_keep.size() <= keep_used) bb.cig_keep.emplace_back(new DevBuf);
+						uint32_t *d_cig = bb.cig_keep[keep_used]->as<uint32_t>((size_t)cap + 4); // stays alive until the batch ends (K4 reads the pieces in place)
 						unsigned long long *d_used = (unsigned long long*)d_cig;
 						MMB_CUDA_CHECK(cudaMemcpyAsync(d_jobs, &jobs[b], sizeof(mmb_ksw_job_t) * m, cudaMemcpyHostToDevice, ctx->stream));
 						MMB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, 8, ctx->stream));
@@ -651,6 +747,8 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 						ctx->last_h2d_bytes += sizeof(mmb_ksw_job_t) * (uint64_t)m;
 						if (ctx->profiling) ctx->prof_bytes[MMB_PROF_KSW] += 4ull * used;
 						chunk_base.push_back(cig_fill);
+						chunk_dev.push_back(d_cig + 2);
+						++keep_used;
 						if (used) MMB_CUDA_CHECK(cudaMemcpyAsync(h_cig + cig_fill, d_cig + 2, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
 						cig_fill += (int64_t)used;
 						MMB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -666,7 +764,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 					ReadAlign &ra = *r.ra;
 					for (size_t i = 0; i < ra.want.size(); ++i) {
 						const int64_t jid = joff[t] + (int64_t)i;
-						KswDone d; d.r = res[jid], d.cig = h_cig + chunk_base[jid / CH] + res[jid].cigar_off;
+						KswDone d; d.r = res[jid], d.cig = h_cig + chunk_base[jid / CH] + res[jid].cigar_off, d.dcig = chunk_dev[jid / CH] + res[jid].cigar_off;
 						ra.done_idx[ra.want_slot[i]] = (int)ra.done.size();
 						ra.done.push_back(d);
 					}

@@ -47,3 +47,19 @@ void mmb_chain_rmq_primary_device(mmb_ctx_t *ctx, const mmb_chain_par_t *par, in
 								  int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf);
 void mmb_chain_rescue_device(mmb_ctx_t *ctx, const RescuePar *rp, int n_reads, const int64_t *d_a_off, int64_t n_tot,
 							 int32_t *d_n_u, int32_t *d_n_v, uint64_t *d_u, m128 *d_a_out, DevBuf &scratch, DevBuf &scratch2, DevBuf &treebuf, int64_t tot_v);
+
+// ---- K4 (finalize.cu): CIGAR assembly + mm_fix_cigar + mm_update_extra of finished hits on the device (align.c:105-181,254-334) ----
+struct FinJobRef { const uint32_t *cig; uint32_t n, pad; }; // one ksw2 result: its CIGAR in the device arena of the wave that ran it
+struct FinReg {
+	int64_t q0;               // offset of the read's first base in the device query array (nt4)
+	int64_t t0;               // offset (in bases) of target position rs in the packed reference
+	int64_t out_off;          // where the hit's CIGAR goes in the output arena (room for the sum of its pieces)
+	int32_t qlen, qs, rev;    // read length; start of the aligned piece on the strand it is read on; 1: reverse complement
+	int32_t qspan, tspan;     // query / target bases the CIGAR must consume (consistency check)
+	int32_t job_first, n_jobs;
+	int32_t pad;
+};
+struct FinOut { int32_t n_cigar, blen, mlen, n_ambi, dp_max, qshift, tshift, status, is_spliced, pad[3]; }; // status 0: done; else the host driver redoes the read
+struct FinPar { int8_t mat[25]; int8_t q, e, log_gap; };
+void mmb_finalize_device(mmb_ctx_t *ctx, const FinReg *d_regs, const FinJobRef *d_jobs, int n_regs, const uint8_t *d_query, const uint32_t *d_S,
+						 uint32_t *d_out, FinOut *d_res, const FinPar &par);

@@ -84,7 +84,7 @@ def build(name, files, extra=("emu_stubs.cc",)):
     return lib
 
 
-ALL = ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu", "sketch.cu", "scan.cu", "seed.cu", "chain.cu", "index.cu", "map.cu", "synth.cu",
+ALL = ["mmb_ctx.cu", "ksw_fast.cu", "ksw_extd2.cu", "sketch.cu", "scan.cu", "seed.cu", "chain.cu", "index.cu", "map.cu", "synth.cu", "finalize.cu",
        "align.cc", "hits.cc", "format.cc", "options.cc", "fastx.cc"]
 
 if __name__ == "__main__":

@@ -88,3 +88,14 @@ def test_oracle_exts2_matches_golden(V):
         for k, e in zip(KEYS, V["sp%d_res" % i]):
             assert r[k] == int(e), (i, k, r[k], int(e), hex(flag))
         assert r["cigar"] == [int(x) for x in V["sp%d_cig" % i]], i
+
+
+def test_hit_tail_vectors():
+    """oracle/mm2o_extra.c against the recorded outputs of the reference's per-hit tail (tests/golden/vectors_tail.npz)"""
+    import tail_cases as T
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vectors_tail.npz"))
+    rng = np.random.default_rng(int(z["seed"]))
+    cases = [T.make_case(rng) for _ in range(int(z["n"]))]
+    exp = T.unpack_results(z["stats"], z["cigars"])
+    for i, c in enumerate(cases):
+        assert T.same(T.run_oracle(c), exp[i]), i

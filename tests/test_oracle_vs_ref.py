@@ -231,3 +231,20 @@ def test_exts2_splice(seed):
         x = O.oracle_exts2(q, t, mat, go, ge, go2, noncan, zd, eb, jb, jp, fl, junc)
         y = O.ref_exts2(q, t, mat, go, ge, go2, noncan, zd, eb, jb, jp, fl, junc)
         assert x == y, (it, hex(fl), len(q), len(t), {k: (x[k], y[k]) for k in x if x[k] != y[k] and k != "cigar"}, x["cigar"][:8], y["cigar"][:8])
+
+
+def test_hit_tail_oracle_vs_reference():
+    """mm_append_cigar + mm_fix_cigar + mm_update_extra (align.c:105-334): oracle/mm2o_extra.c against the reference's own static functions
+    (oracle/_ref/libminimap2_refalign.so = the reference with align.c compiled into a unit that exports them)."""
+    import os
+    import tail_cases as T
+    if not os.path.exists(T.REFALIGN_SO):
+        pytest.skip("oracle/_ref/libminimap2_refalign.so not built")
+    rng = np.random.default_rng(5)
+    for i in range(3000):
+        c = T.make_case(rng)
+        assert T.same(T.run_oracle(c), T.run_reference(c)), i
+    for q, e in ((6, 2), (5, 4), (16, 1)):
+        for i in range(300):
+            c = T.make_case(rng)
+            assert T.same(T.run_oracle(c, q, e), T.run_reference(c, q, e)), (q, e, i)

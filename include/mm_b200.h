@@ -87,6 +87,9 @@ typedef struct {      /* scoring: what align.c:655 ksw_gen_ts_mat + mm_mapopt_t 
 	int8_t mat[25];
 	int8_t q, e, q2, e2;
 	int8_t noncan, junc_bonus, junc_pen; /* spliced alignment only (MMB_JOB_SPLICE): mm_mapopt_t noncan / junc_bonus / junc_pen */
+	int16_t zd_skip; /* MMB_JOB_ZDROP jobs: if > 0, the kernel may skip the mm_test_zdrop scan (and report max drop 0) when the alignment's total
+	                  * penalty under that function's scoring provably cannot exceed this value; the caller passes the smallest threshold it compares the
+	                  * drop with (min(zdrop, zdrop_inv), align.c:92-102). 0: always scan */
 } mmb_ksw_score_t;
 
 /* Kernel-level entry with HOST buffers (used by the parity tests and for single calls):

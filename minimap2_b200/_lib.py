@@ -25,7 +25,7 @@ class KswRes(C.Structure):  # mmb_ksw_res_t
 
 class KswScore(C.Structure):  # mmb_ksw_score_t
     _fields_ = [("mat", C.c_int8 * 25), ("q", C.c_int8), ("e", C.c_int8), ("q2", C.c_int8), ("e2", C.c_int8),
-                ("noncan", C.c_int8), ("junc_bonus", C.c_int8), ("junc_pen", C.c_int8)]
+                ("noncan", C.c_int8), ("junc_bonus", C.c_int8), ("junc_pen", C.c_int8), ("zd_skip", C.c_int16)]
 
 
 class ChainPar(C.Structure):  # mmb_chain_par_t

@@ -756,6 +756,16 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		while (k < n_tiers && m > tiers[k].maxlen) ++k;
 		tj[(spl? n_tiers + 1 : 0) + k].push_back(i);
 	}
+	static const bool ksw_stats = getenv("MM_B200_KSW_STATS") != nullptr; // development aid: shapes of the jobs the universal tiers get
+	if (ksw_stats) {
+		for (int k = 0; k < n_tiers; ++k) {
+			uint64_t c = 0, sq = 0, st = 0; int ext = 0, right = 0;
+			for (int i : tj[k]) c += (uint64_t)h_jobs[i].qlen * h_jobs[i].tlen, sq += h_jobs[i].qlen, st += h_jobs[i].tlen, ext += !!(h_jobs[i].flag & MMB_KSW_EXTZ_ONLY), right += !!(h_jobs[i].flag & MMB_KSW_RIGHT);
+			if (!tj[k].empty()) fprintf(stderr, "[ksw] tier %d: %zu jobs (ext-only %d, right-aligned %d), mean qlen %.1f tlen %.1f, cells %.3g\n", k, tj[k].size(), ext, right, (double)sq / tj[k].size(), (double)st / tj[k].size(), (double)c);
+		}
+		uint64_t c = 0; for (int i : fastj) c += (uint64_t)h_jobs[i].qlen * h_jobs[i].tlen;
+		fprintf(stderr, "[ksw] packed path: %zu jobs, cells %.3g; ll %zu\n", fastj.size(), (double)c, llj.size());
+	}
 	if (!tj[n_tiers].empty() || !tj[2 * n_tiers + 1].empty()) {
 		fprintf(stderr, "[ERROR] ksw job longer than %d not supported by this build\n", tiers[n_tiers - 1].maxlen);
 		abort();

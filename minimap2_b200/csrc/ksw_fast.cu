@@ -43,6 +43,7 @@ struct FastArgs {
 	int8_t mch, mis, scn;
 	int8_t q, e, q2, e2;
 	int8_t zd_q, zd_e;                    // gap open/extension as mm_test_zdrop uses them (opt->q, opt->e: not reordered)
+	int zd_skip;                          // > 0: skip that scan when the path's total penalty cannot exceed it (mmb_ksw_score_t::zd_skip)
 	int long_thres, long_diff;
 	int8_t mat[25];
 	uint32_t one, neg1;                   // 1 and 0xffffffff, passed at run time so that ptxas keeps the IMAD form of PK_FADD/PK_FSUB
@@ -291,7 +292,10 @@ __device__ __forceinline__ uint32_t pk_mad(uint32_t a, uint32_t b, uint32_t c)
 #endif
 
 template<int H, int LN>
-__global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
+#ifndef PK_MINB
+#define PK_MINB (H <= 8? 4 : 3) // CTAs per SM the register allocation must leave room for (128 / 168 registers)
+#endif
+__global__ void __launch_bounds__(128, PK_MINB) ksw_pk_kernel(FastArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem[];
 	constexpr int C = 2 * H;
@@ -373,9 +377,12 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 		if (NJ == 2) n_steps = max(n_steps, __shfl_xor_sync(full, n_steps, 16));
 		uint8_t *pa = p + sub * CP - (ptrdiff_t)(2 * sub) * W; // traceback row jA of this lane's block A
 		const bool lane_on = t0 < tlen;
+		uint32_t oh_nx = sub == 0? qs[0] : 0x80u; // the query base of the coming step, fetched one step ahead (keeps the shared-memory latency off the step's critical path)
 		#pragma unroll 1
 		for (int s = 0; s < n_steps; ++s, pa += W) {
 			const int jA = s - 2 * sub; // block A row; block B is at jA - 1
+			const uint32_t oh = oh_nx;
+			{ const int jn = jA + 1; oh_nx = jn >= 0 && jn <= qlen? qs[jn] : 0x80u; }
 			const uint32_t sv = __shfl_up_sync(full, vl_end, 1, LN), sx = __shfl_up_sync(full, xl_end, 1, LN), sx2 = __shfl_up_sync(full, x2l_end, 1, LN);
 			if (jA >= 0 && jA <= qlen && lane_on) {
 				// left inputs: lo <- right edge of the previous lane's block B (same row), hi <- this lane's block A, previous row;
@@ -390,7 +397,6 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 				// v travels through the column loop without its bias (vl = enc(v) - BB2, a 32-bit difference whose half-borrows cancel in
 				// every sum it enters): x + v and z - v are then two-input operations
 				uint32_t vl = PK_FADD(vlE, NBB2);
-				const uint32_t oh = qs[jA];
 				const uint32_t ohx = oh | oh_prev << 16;
 				const uint32_t qbm = ohx & 0x000f000fu;
 				const uint32_t mN = (ohx >> 7 & 0x00010001u) * 0xffffu;
@@ -480,8 +486,11 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			uint32_t *cig = A.cigws + A.cigws_stride * (size_t)(worker0 + g);
 			int n = 0, i = g_tlen - 1, jj = g_qlen - 1, state = 0;
 			uint32_t run_op = 0, run_len = 0; // pending CIGAR run (lane 0 writes it when the operator changes)
+			int n_m = 0, gap_dp = 0, gap_zd = 0; // aligned bases; gap costs as the DP charges them and as mm_test_zdrop does (for the scan-skip bound)
+			#define PK_CLOSE() do { if (run_len) { if (run_op == 0) n_m += (int)run_len; else { const int l__c = (int)run_len; \
+				gap_dp += min(q + e * l__c, q2 + e2 * l__c), gap_zd += A.zd_q + A.zd_e * l__c; } } } while (0)
 			#define PK_EMIT(op_, len_) do { const uint32_t o__ = (op_), l__ = (len_); if (l__) { if (run_len && o__ == run_op) run_len += l__; \
-				else { if (run_len && lane == 0) cig[n] = run_len << 4 | run_op; n += run_len? 1 : 0; run_op = o__, run_len = l__; } } } while (0)
+				else { PK_CLOSE(); if (run_len && lane == 0) cig[n] = run_len << 4 | run_op; n += run_len? 1 : 0; run_op = o__, run_len = l__; } } } while (0)
 			// The traceback bytes live in HBM/L2; reading them cell by cell along the path is a chain of dependent global loads (the
 			// long-scoreboard stall that kept half of the warps waiting in round 1). The warp stages a tile instead -- the 32 rows up from
 			// the current cell x the 80 physical bytes that cover the 32 columns left of it, five independent 16-byte loads per lane --
@@ -530,14 +539,21 @@ __global__ void __launch_bounds__(128) ksw_pk_kernel(FastArgs A)
 			}
 			if (i >= 0) PK_EMIT(2u, (uint32_t)(i + 1));
 			if (jj >= 0) PK_EMIT(1u, (uint32_t)(jj + 1));
+			PK_CLOSE();
 			if (run_len) { if (lane == 0) cig[n] = run_len << 4 | run_op; ++n; }
 			#undef PK_EMIT
+			#undef PK_CLOSE
 			__syncwarp();
 			// ---- mm_test_zdrop's scan (align.c:61-89) over the path just traced, 32 bases per step: prefix sums give the score at
 			// every base, an exclusive prefix maximum the running maximum it is compared with, a max-scan of the updating
 			// lanes the position of that maximum, and the first lane holding the largest drop wins (strict '>' in the reference).
 			int zd_max = -1, zd_t0 = -1, zd_t1 = -1, zd_q0 = -1, zd_q1 = -1;
-			if (g_flag & MMB_JOB_ZDROP) {
+			// Every drop the scan could find is at most the total of the path's negative steps under mm_test_zdrop's scoring (align.c:61-89):
+			// its gap costs, plus what the non-matching aligned bases cost -- bounded by mch * aligned bases - DP gap costs - DP score, which
+			// charges each of them mch more than the scan does. Below the caller's thresholds the answer is "no drop" whatever the exact value.
+			const bool zd_skip = A.zd_skip > 0 && A.mch * n_m - gap_dp - g_score + gap_zd <= A.zd_skip;
+			if ((g_flag & MMB_JOB_ZDROP) && zd_skip) zd_max = 0;
+			else if (g_flag & MMB_JOB_ZDROP) {
 				const uint8_t *gq = smem + (size_t)(wk * NJ + g) * A.qmax;
 				const uint8_t *gt = smem + (size_t)nwk * NJ * A.qmax + (size_t)(wk * NJ + g) * TSM;
 				const int zq = A.zd_q, ze = A.zd_e, mch = A.mch, mis = A.mis, scn = A.scn;
@@ -662,7 +678,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 	int8_t q = sc->q, e = sc->e, q2 = sc->q2, e2 = sc->e2;
 	if (q2 + e2 < q + e) std::swap(q, q2), std::swap(e, e2);
 	A.q = q, A.e = e, A.q2 = q2, A.e2 = e2;
-	A.zd_q = sc->q, A.zd_e = sc->e;
+	A.zd_q = sc->q, A.zd_e = sc->e, A.zd_skip = sc->zd_skip;
 	A.one = 1u, A.neg1 = 0xffffffffu;
 	A.mch = sc->mat[0], A.mis = sc->mat[1], A.scn = sc->mat[24] == 0? (int8_t)(-e2) : sc->mat[24];
 	for (int i = 0; i < 25; ++i) A.mat[i] = sc->mat[i];

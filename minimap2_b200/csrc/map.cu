@@ -554,6 +554,13 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 			}
 			sc.q = (int8_t)opt->q, sc.e = (int8_t)opt->e, sc.q2 = (int8_t)opt->q2, sc.e2 = (int8_t)opt->e2;
 			sc.noncan = (int8_t)opt->noncan, sc.junc_bonus = (int8_t)opt->junc_bonus, sc.junc_pen = (int8_t)opt->junc_pen;
+			// mm_test_zdrop only compares the largest drop with zdrop and (unless the inversion probe is off, align.c:92) zdrop_inv: a
+			// path whose total penalty stays below both needs no scan
+			{
+				const bool inv_off = (opt->flag & (MM_F_SPLICE | MM_F_SR | MM_F_FOR_ONLY | MM_F_REV_ONLY)) != 0;
+				const int th = inv_off? opt->zdrop : std::min(opt->zdrop, opt->zdrop_inv);
+				sc.zd_skip = (int16_t)std::max(0, std::min(th, 30000));
+			}
 		}
 		std::vector<int> active;
 		for (int j = 0; j < n; ++j) if (!rs[live[j]].done) active.push_back(live[j]);

@@ -4,12 +4,13 @@ import numpy as np
 from ._lib import lib, KswJob, KswRes, KswScore, ChainPar
 
 
-def make_score(mat, q, e, q2, e2, noncan=0, junc_bonus=0, junc_pen=0):
+def make_score(mat, q, e, q2, e2, noncan=0, junc_bonus=0, junc_pen=0, zd_skip=0):
     sc = KswScore()
     for i in range(25):
         sc.mat[i] = int(mat[i])
     sc.q, sc.e, sc.q2, sc.e2 = q, e, q2, e2
     sc.noncan, sc.junc_bonus, sc.junc_pen = noncan, junc_bonus, junc_pen
+    sc.zd_skip = zd_skip
     return sc
 
 

@@ -32,7 +32,7 @@ def emu():
     return load_emu()
 
 
-def run_jobs(emu, mat, q, e, q2, e2, pairs, params):
+def run_jobs(emu, mat, q, e, q2, e2, pairs, params, zd_skip=0):
     L, ctx, KswJob, KswRes, KswScore = emu
     n = len(pairs)
     qcat = np.concatenate([np.asarray(p[0], dtype=np.uint8) for p in pairs]); tcat = np.concatenate([np.asarray(p[1], dtype=np.uint8) for p in pairs])
@@ -46,6 +46,7 @@ def run_jobs(emu, mat, q, e, q2, e2, pairs, params):
     for i in range(25):
         sc.mat[i] = int(mat[i])
     sc.q, sc.e, sc.q2, sc.e2 = q, e, q2, e2
+    sc.zd_skip = zd_skip
     res = (KswRes * n)(); cig = np.zeros(tot, dtype=np.uint32)
     used = L.mmb_ksw_batch_host(ctx, C.byref(sc), n, jobs, qcat.ctypes.data, len(qcat), tcat.ctypes.data, len(tcat), res, cig.ctypes.data, len(cig))
     assert used >= 0
@@ -284,3 +285,35 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "hbm-tier":
         if not (ex.args and isinstance(ex.args[0], int)):  # too few jobs for the "annotation changed something" count: not a failure
             raise
     print("HBM_TIER_OK")
+
+
+def check_zdrop_scan_skip(run, mat):
+    """mmb_ksw_score_t::zd_skip: the kernel may answer "no drop" (0) without scanning, but only when the true largest drop is within the
+    threshold; every other job still carries the exact scan. Shared by the emulated and the device test."""
+    rng = np.random.default_rng(99)
+    pairs, params = [], []
+    for it in range(120):
+        t = rng.integers(0, 4, int(rng.integers(40, 380))).astype(np.uint8)
+        q = O.mutate(t, rng, err=float(rng.choice([0.02, 0.08, 0.15, 0.3])))
+        if it % 7 == 0 and len(q) > 30:  # a junk stretch: a large drop
+            a = int(rng.integers(5, len(q) - 20)); q[a:a + 15] = rng.integers(0, 4, 15)
+        if len(q) == 0:
+            q = np.array([0], dtype=np.uint8)
+        pairs.append((q, t)); params.append(dict(w=30001, zdrop=400, end_bonus=-1, flag=APPROX | JOB_ZDROP))
+    n_skip = n_scan = 0
+    for thr in (60, 200):
+        got = run(mat, 4, 2, 24, 1, pairs, params, thr)
+        for (qq, tt), (g, zd) in zip(pairs, got):
+            exp = O.oracle_extd2(qq, tt, mat, 4, 2, 24, 1, 30001, 400, -1, APPROX)
+            assert g == exp
+            true = zdrop_scan(qq, tt, mat, exp["cigar"], 4, 2)
+            if zd == true:
+                n_scan += 1
+            else:  # skipped: reported as "no drop", and the true drop really is within the threshold
+                assert zd[0] == 0 and true[0] <= thr, (zd, true, thr)
+                n_skip += 1
+    assert n_skip >= 40 and n_scan >= 40, (n_skip, n_scan)
+
+
+def test_emulated_zdrop_scan_skip(emu):
+    check_zdrop_scan_skip(lambda *a: run_jobs(emu, *a), O.simple_mat(2, 4, 1))

@@ -101,3 +101,24 @@ def test_extd2_edge_cases(ctx):
              (np.full(40, 4, dtype=np.uint8), np.full(33, 4, dtype=np.uint8))]
     params = [dict(w=-1, zdrop=400, end_bonus=-1, flag=f) for f in (0, EXT, APPROX, 0)]
     compare(ctx, pairs, params)
+
+
+def test_zdrop_scan_and_skip(ctx):
+    """the packed kernel's in-kernel mm_test_zdrop scan (align.c:61-89) on the device: exact against a plain restatement, and the
+    scan-skip bound (mmb_ksw_score_t::zd_skip) only ever answers "no drop" when the true drop is within the threshold"""
+    import minimap2_b200 as mb
+    from minimap2_b200._lib import KswJob, KswRes, KswScore
+    import test_emu_ksw as E
+    dev = (mb.lib(), ctx.h, KswJob, KswRes, KswScore)
+    mat = O.simple_mat(2, 4, 1)
+    E.check_zdrop_scan_skip(lambda *a: E.run_jobs(dev, *a), mat)
+    rng = np.random.default_rng(3)
+    pairs = []
+    for it in range(200):
+        t = rng.integers(0, 4, int(rng.integers(30, 500))).astype(np.uint8)
+        pairs.append((O.mutate(t, rng, err=float(rng.choice([0.05, 0.15, 0.3]))), t))
+    pairs = [(q if len(q) else np.array([0], dtype=np.uint8), t) for q, t in pairs]
+    params = [dict(w=30001, zdrop=400, end_bonus=-1, flag=E.APPROX | E.JOB_ZDROP)] * len(pairs)
+    for (qq, tt), (g, zd) in zip(pairs, E.run_jobs(dev, mat, 4, 2, 24, 1, pairs, params)):
+        exp = O.oracle_extd2(qq, tt, mat, 4, 2, 24, 1, 30001, 400, -1, E.APPROX)
+        assert g == exp and zd == E.zdrop_scan(qq, tt, mat, exp["cigar"], 4, 2)

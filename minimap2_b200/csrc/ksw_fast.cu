@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128, PK_MINB) ksw_pk_kernel(FastArgs A)
 		const int n_lanes = (tlen + C - 1) / C;
 		int n_steps = act? qlen + 2 * (n_lanes - 1) + 1 : 0;
 		if (NJ == 2) n_steps = max(n_steps, __shfl_xor_sync(full, n_steps, 16));
-		uint8_t *pa = p + sub * CP - (ptrdiff_t)(2 * sub) * W; // traceback row jA of this lane's block A
+		uint8_t *pa = p + sub * CP; // traceback bytes of step s: the rows are indexed by STEP (row j of lane l's block A lives in step-row j + 2l, of its block B in j + 2l + 1), so the lanes of a step store one contiguous line
 		const bool lane_on = t0 < tlen;
 		uint32_t oh_nx = sub == 0? qs[0] : 0x80u; // the query base of the coming step, fetched one step ahead (keeps the shared-memory latency off the step's critical path)
 		#pragma unroll 1
@@ -449,20 +449,27 @@ __global__ void __launch_bounds__(128, PK_MINB) ksw_pk_kernel(FastArgs A)
 					const uint32_t r01 = __byte_perm(wd[4 * k], wd[4 * k + 1], 0x6240), r23 = __byte_perm(wd[4 * k + 2], wd[4 * k + 3], 0x6240);
 					lo[k] = __byte_perm(r01, r23, 0x5410), hi[k] = __byte_perm(r01, r23, 0x7632);
 				}
-				if (jA < qlen) {
-					if constexpr (CPH == 1) *pa = (uint8_t)lo[0];
-					else if constexpr (CPH == 2) *(uint16_t*)pa = (uint16_t)lo[0];
-					else if constexpr (CPH == 4) *(uint32_t*)pa = lo[0];
-					else if constexpr (CPH == 8) *(uint2*)pa = make_uint2(lo[0], lo[NW - 1]);
-					else *(uint4*)pa = make_uint4(lo[0], lo[1], lo[2], lo[NW - 1]);
-				}
-				if (jA >= 1) {
-					uint8_t *pb = pa - W + CPH;
-					if constexpr (CPH == 1) *pb = (uint8_t)hi[0];
-					else if constexpr (CPH == 2) *(uint16_t*)pb = (uint16_t)hi[0];
-					else if constexpr (CPH == 4) *(uint32_t*)pb = hi[0];
-					else if constexpr (CPH == 8) *(uint2*)pb = make_uint2(hi[0], hi[NW - 1]);
-					else *(uint4*)pb = make_uint4(hi[0], hi[1], hi[2], hi[NW - 1]);
+				if (jA >= 1 && jA < qlen && CPH <= 8) { // both blocks are inside the matrix (all but the first and last row of a lane): one store for the pair
+					if constexpr (CPH == 1) *(uint16_t*)pa = (uint16_t)((lo[0] & 0xffu) | hi[0] << 8);
+					else if constexpr (CPH == 2) *(uint32_t*)pa = (lo[0] & 0xffffu) | hi[0] << 16;
+					else if constexpr (CPH == 4) *(uint2*)pa = make_uint2(lo[0], hi[0]);
+					else if constexpr (CPH == 8) *(uint4*)pa = make_uint4(lo[0], lo[NW - 1], hi[0], hi[NW - 1]);
+				} else {
+					if (jA < qlen) {
+						if constexpr (CPH == 1) *pa = (uint8_t)lo[0];
+						else if constexpr (CPH == 2) *(uint16_t*)pa = (uint16_t)lo[0];
+						else if constexpr (CPH == 4) *(uint32_t*)pa = lo[0];
+						else if constexpr (CPH == 8) *(uint2*)pa = make_uint2(lo[0], lo[NW - 1]);
+						else *(uint4*)pa = make_uint4(lo[0], lo[1], lo[2], lo[NW - 1]);
+					}
+					if (jA >= 1) {
+						uint8_t *pb = pa + CPH;
+						if constexpr (CPH == 1) *pb = (uint8_t)hi[0];
+						else if constexpr (CPH == 2) *(uint16_t*)pb = (uint16_t)hi[0];
+						else if constexpr (CPH == 4) *(uint32_t*)pb = hi[0];
+						else if constexpr (CPH == 8) *(uint2*)pb = make_uint2(hi[0], hi[NW - 1]);
+						else *(uint4*)pb = make_uint4(hi[0], hi[1], hi[2], hi[NW - 1]);
+					}
 				}
 			}
 		}
@@ -501,12 +508,12 @@ __global__ void __launch_bounds__(128, PK_MINB) ksw_pk_kernel(FastArgs A)
 				const int di = (state == 0 || state == 1 || state == 3)? 1 : 0, dj = (state == 0 || state == 2 || state == 4)? 1 : 0;
 				const int ci = i - lane * di, cj = jj - lane * dj;
 				const bool inr = ci >= 0 && cj >= 0;
-				int ph = 0;
-				if (inr) { const int wi = ci % C; ph = (ci / C) * CP + (wi < H? wi : CPH + wi - H); }
-				const bool intile = have && inr && cj <= tj && cj > tj - 32 && ph >= tpb && ph < tpb + TW;
+				int ph = 0, sr = 0; // physical byte and step-row of the cell
+				if (inr) { const int wi = ci % C, sb = ci / C; ph = sb * CP + (wi < H? wi : CPH + wi - H); sr = cj + 2 * sb + (wi < H? 0 : 1); }
+				const bool intile = have && inr && sr <= tj && sr > tj - 32 && ph >= tpb && ph < tpb + TW;
 				if (!__shfl_sync(full, (int)intile, 0)) { // the current cell is not staged: stage the tile that has it in its bottom right corner
 					const int c0 = i > 31? i - 31 : 0, w0 = c0 % C;
-					tj = jj, tpb = ((c0 / C) * CP + (w0 < H? w0 : CPH + w0 - H)) & ~15;
+					tj = __shfl_sync(full, sr, 0), tpb = ((c0 / C) * CP + (w0 < H? w0 : CPH + w0 - H)) & ~15; // every step of the walk lowers the step-row
 					__syncwarp();
 					const int rr = tj - lane;
 					if (rr >= 0) {
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(128, PK_MINB) ksw_pk_kernel(FastArgs A)
 					continue;
 				}
 				uint32_t tmp = 0;
-				if (intile) tmp = tile[(tj - cj) * TW + (ph - tpb)] ^ 0x7fu;
+				if (intile) tmp = tile[(tj - sr) * TW + (ph - tpb)] ^ 0x7fu;
 				const bool cont = intile && (state == 0? (tmp & 7) == 0 : (tmp >> (state + 2) & 1) != 0);
 				const unsigned stop = __ballot_sync(full, !cont);
 				const int r = stop? __ffs(stop) - 1 : 32;
@@ -734,7 +741,7 @@ void mmb_ksw_fast_plan(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, const std::vec
 		if (cta_per_sm < 1) { fprintf(stderr, "[ERROR] ksw_fast: no occupancy\n"); abort(); }
 		int grid = ctx->n_sm * cta_per_sm;
 		grid = std::max(1, std::min(grid, ((int)v[k].size() + nwk * NJ - 1) / (nwk * NJ)));
-		A.pws_stride = ((size_t)maxq * W + 255) & ~(size_t)255;
+		A.pws_stride = ((size_t)(maxq + 2 * LNW[k] + 2) * W + 255) & ~(size_t)255; // one row per step of the lane-skewed sweep
 		A.cigws_stride = (size_t)maxsum + 8;
 		int *d_order = d_order_all + order_off; order_off += v[k].size() + 1;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v[k].data(), v[k].size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -536,13 +536,17 @@ def main():
                                    "gb_per_s": (prof[nm]["bytes"] / 1e9) / (prof[nm]["ms"] / 1e3) if prof[nm]["ms"] > 0 else 0.0,
                                    "frac_of_hbm_peak": ((prof[nm]["bytes"] / 1e9) / (prof[nm]["ms"] / 1e3) / peak) if prof[nm]["ms"] > 0 and peak else 0.0}
                               for nm in ("sketch", "seed", "sort", "chain", "ksw")}
+        roofline["stages"]["tail"] = {"ms_per_step": prof["other"]["ms"] / n_prof, "what": "K4 finalize_kernel (per-hit CIGAR assembly, mm_fix_cigar, mm_update_extra on the device) + ksw_ll probes"}
     except Exception:
         pass
     tp = os.path.join(ROOT, "profiles", "ksw_traffic.json")
     if dom == "ksw" and a.workload == "map-ont" and os.path.exists(tp):
         try:  # dram__bytes of the K3 launches from the committed `ncu --set full` capture of this command (profiles/README.md says which run)
+            # the capture covers ONE alignment wave (all K3 kernels of one scheduler group); its DRAM bytes per algorithmic byte, times this
+            # run's algorithmic bytes per launch set, is the per-launch figure (a launch set = one wave of one group, like `achieved`)
             tj = json.load(open(tp))
-            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            roofline["traffic"] = tj["dram_bytes_wave"] / tj["algorithmic_bytes_wave"] * roofline["algorithmic_bytes_per_launch"]
+            roofline["traffic_over_algorithmic"] = tj["dram_bytes_wave"] / tj["algorithmic_bytes_wave"]
             roofline["traffic_source"] = tj.get("source", "profiles/ksw_traffic.json")
         except Exception:
             pass

@@ -322,8 +322,6 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	uint8_t *h_seq = bb.h_seq.as<uint8_t>((size_t)total_bases + 16);
 	parallel_for(n, n_threads, [&](int64_t j, int) { memcpy(h_seq + off[j], rs[live[j]].seq, rs[live[j]].qlen); });
 	lap("host concat");
-	GateHold gate1(G.gated, 0);
-	lap("gate wait 1");
 	uint8_t *d_seq = bb.seq.as<uint8_t>((size_t)total_bases + 16);
 	int64_t *d_off = bb.off.as<int64_t>((size_t)n + 1);
 	int32_t *d_qlen = bb.qlen.as<int32_t>((size_t)n);
@@ -342,6 +340,10 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 		++ctx->n_launch;
 	}
 	G.res_n = n, G.res_bases = total_bases, G.res_first = rs[live[0]].seq;
+	// the reads are on their way before the group queues for a device slot: every group's upload starts when the batch starts and
+	// overlaps the kernels of the groups ahead of it
+	GateHold gate1(G.gated, 0);
+	lap("gate wait 1");
 	int64_t *d_mz_off = bb.mz_off.as<int64_t>((size_t)n + 1);
 	const int64_t total_mz = mmb_sketch_device(ctx, d_seq, nullptr, d_off, n, nullptr, 0, mi->w, mi->k, mi->flag & MM_I_HPC, total_bases,
 											   bb.mz, d_mz_off, bb.t1, bb.t2, 1 /* rid = segment index 0 for every read (map.c:65) */);

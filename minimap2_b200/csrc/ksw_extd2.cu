@@ -182,7 +182,10 @@ __device__ int backtrack_tiled(const uint8_t *p, int n_col, int qlen, int tlen, 
 // SP = true is ksw_exts2_sse (ksw2_exts2_sse.c:26-465): the second gap state is an intron (open q2, free extension, A.e2 == 0 here)
 // whose closing / opening is scored with the acceptor / donor signal of the target position; no band; y2[] holds the donor array.
 template<int G, bool SP>
-__global__ void __launch_bounds__(256) ksw_extd2_kernel(KswArgs A)
+#ifndef KE_MINB
+#define KE_MINB 3 // CTAs per SM the register allocation leaves room for: the small-job tiers are latency-bound, residency is their throughput
+#endif
+__global__ void __launch_bounds__(256, KE_MINB) ksw_extd2_kernel(KswArgs A)
 {
 	extern __shared__ __align__(16) uint8_t smem_raw[];
 	__shared__ int s_job[8];

@@ -730,8 +730,11 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 					for (;;) {
 						mmb_ksw_job_t *d_jobs = bb.jobs.as<mmb_ksw_job_t>((size_t)m);
 						mmb_ksw_res_t *d_res = bb.res.as<mmb_ksw_res_t>((size_t)m);
-						while (bb.cig_keep.size() <= keep_used) bb.cig_keep.emplace_back(new DevBuf);
-						uint32_t *d_cig = bb.cig_keep[keep_used]->as<uint32_t>((size_t)cap + 4); // stays alive until the batch ends (K4 reads the pieces in place)
+						// with the device tail on, every (wave, chunk) keeps its arena until the batch ends (K4 reads the pieces in place);
+						// otherwise one arena is reused, as the host has its copy (spliced jobs reserve room for intron-sized CIGAR estimates)
+						const size_t ki = use_fin? keep_used : 0;
+						while (bb.cig_keep.size() <= ki) bb.cig_keep.emplace_back(new DevBuf);
+						uint32_t *d_cig = bb.cig_keep[ki]->as<uint32_t>((size_t)cap + 4);
 						unsigned long long *d_used = (unsigned long long*)d_cig;
 						MMB_CUDA_CHECK(cudaMemcpyAsync(d_jobs, &jobs[b], sizeof(mmb_ksw_job_t) * m, cudaMemcpyHostToDevice, ctx->stream));
 						MMB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, 8, ctx->stream));

@@ -26,13 +26,15 @@ t4 = lut[t_all]; q4 = lut[q_all]
 jobs = (KswJob * n_jobs)()
 ratio = len(q4) / len(t4)
 cells = 0
-tls = rng.integers(200, 270, n_jobs)
+tl_lo, tl_hi = (int(x) for x in os.environ.get('KSW_TLEN', '200,270').split(','))
+qfrac = float(os.environ.get('KSW_QFRAC', '1.0'))  # extension-shaped jobs: KSW_TLEN=60,110 KSW_QFRAC=0.5 with flag 0x40
+tls = rng.integers(tl_lo, tl_hi, n_jobs)
 for i in range(n_jobs):
     tl = int(tls[i]); ts = i * 240
-    qs = int(ts * ratio); ql = int(tl * ratio)
+    qs = int(ts * ratio); ql = max(1, int(tl * ratio * qfrac))
     j = jobs[i]
     j.q_start, j.t_start, j.q_step, j.t_step, j.qlen, j.tlen = qs, ts, 1, 1, ql, tl
-    j.w, j.zdrop, j.end_bonus, j.flag = 30001, 400, -1, flag
+    j.w, j.zdrop, j.end_bonus, j.flag = (751, 400, 10, flag) if flag & 0x40 else (30001, 400, -1, flag)
     cells += ql * tl
 res = (KswRes * n_jobs)()
 cig = np.zeros(n_jobs * 300, dtype=np.uint32)

@@ -450,6 +450,11 @@ def main():
 
     log("warm-up x%d" % a.warmup)
     run_steps(max(a.warmup, 3), True)
+    try:
+        free_b, tot_b = torch.cuda.mem_get_info()
+        log("device memory after warm-up: %.1f of %.1f GB in use" % ((tot_b - free_b) / 1e9, tot_b / 1e9))
+    except Exception:
+        pass
     L.mmb_launch_count_all(1)
     sampler = ClockSampler(local_rank)
     sampler.start()

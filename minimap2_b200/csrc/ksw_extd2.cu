@@ -846,8 +846,8 @@ void mmb_ksw_launch(mmb_ctx_t *ctx, const mmb_ksw_score_t *sc, int n_jobs, const
 		grid = std::max(1, std::min(grid, need));
 		maxp = (maxp + 255) & ~(size_t)255;
 		const size_t gws_stride = gstate? (state_bytes + 255) & ~(size_t)255 : 0;
-		// bound the workspace (8 GB): fewer resident workers for very large matrices
-		while ((size_t)grid * nw * (maxp + gws_stride) > ((size_t)8 << 30) && grid > 1) grid = (grid + 1) / 2;
+		// bound the workspace (2 GB per launch; every scheduler group keeps its own): fewer resident workers for very large matrices
+		while ((size_t)grid * nw * (maxp + gws_stride) > ((size_t)2 << 30) && grid > 1) grid = (grid + 1) / 2;
 		A.pws_stride = maxp, A.cigws_stride = (size_t)maxsum + 8;
 		int *d_order = d_queues + g_off; g_off += v.size() + 1;
 		MMB_CUDA_CHECK(cudaMemcpyAsync(d_order + 1, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));

@@ -707,13 +707,18 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				});
 				// run in chunks to bound the device result buffers; results land in pinned host memory that stays alive until
 				// the end of the batch, so per-read caches just point into it
-				const int64_t CH = 1 << 22;
+				const int64_t CH = 1 << 20;
 				mmb_ksw_res_t *res = bb.h_res.as<mmb_ksw_res_t>((size_t)n_jobs);
 				// CIGAR arena estimate per job: (qlen+tlen)/2 + 8 operations covers every realistic alignment, the true bound is qlen+tlen
 				// (alternating 1I1D); an overflow is recovered below by rerunning the chunk with the exact size the kernels reported
 				// and growing the host staging buffer. MM_B200_CIG_SHIFT (test hook) shrinks the estimate to force that path.
 				static const int cig_shift = getenv("MM_B200_CIG_SHIFT")? atoi(getenv("MM_B200_CIG_SHIFT")) : 0;
-				auto cig_est = [&](const mmb_ksw_job_t &jb) -> int64_t { return (jb.flag & MMB_JOB_LL)? 0 : (((int64_t)(jb.qlen + jb.tlen) / 2 + 8) >> cig_shift) + 1; };
+				// (a spliced job's target spans its introns, each a single N operation: only a query-sized part of the target can turn into operations)
+				auto cig_est = [&](const mmb_ksw_job_t &jb) -> int64_t {
+					if (jb.flag & MMB_JOB_LL) return 0;
+					const int64_t t_eff = (jb.flag & MMB_JOB_SPLICE)? std::min<int64_t>(jb.tlen, 2 * (int64_t)jb.qlen + 64) : jb.tlen;
+					return (((int64_t)jb.qlen + t_eff) / 2 + 8 >> cig_shift) + 1;
+				};
 				int64_t cap_tot = 0;
 				for (int64_t i = 0; i < n_jobs; ++i) cap_tot += cig_est(jobs[i]);
 				while (bb.h_cig.size() <= (size_t)wave) bb.h_cig.emplace_back(new PinBuf);
@@ -916,7 +921,13 @@ static int map_batch_pass(const mm_idx_t *mi, int n_reads, const int *qlens, con
 		// equal shares, except that the last three groups shrink (3/4, 1/2, 1/4 of a share): the end of the batch is then
 		// the short serial chain of a small group instead of a full-size one
 		std::vector<double> wsum(NG + 1, 0.0);
-		for (int g2 = 0; g2 < NG; ++g2) wsum[g2 + 1] = wsum[g2] + (NG >= 8 && g2 >= NG - 3? 0.25 * (NG - g2) : 1.0);
+		// MM_B200_TAPER (development): comma-separated shares of the last groups, e.g. "0.7,0.45,0.25,0.12"
+		static const std::vector<double> taper = []() { std::vector<double> t; const char *e = getenv("MM_B200_TAPER"); if (e) { for (const char *p = e; *p;) { char *q; t.push_back(strtod(p, &q)); p = *q == ','? q + 1 : q; if (q == p && *q != ',') break; } } return t; }();
+		for (int g2 = 0; g2 < NG; ++g2) {
+			double wgt = NG >= 8 && g2 >= NG - 3? 0.25 * (NG - g2) : 1.0;
+			if (!taper.empty() && NG >= 8) wgt = g2 >= NG - (int)taper.size()? taper[g2 - (NG - (int)taper.size())] : 1.0;
+			wsum[g2 + 1] = wsum[g2] + wgt;
+		}
 		int64_t acc = 0; int g = 1;
 		for (int i = 0; i < n_reads && g < NG; ++i) {
 			acc += qlens[i] > 0? qlens[i] : 0;

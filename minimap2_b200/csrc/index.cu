@@ -420,7 +420,7 @@ extern "C" mm_idx_t *mm_idx_str(int w, int k, int is_hpc, int bucket_bits, int n
 
 struct mm_bseq_file_s { FastxReader *rd; FastxRecord pending; bool has_pending; };
 
-static mm_idx_t *idx_gen(mm_bseq_file_s *fp, int w, int k, int b, int flag, uint64_t batch_size) // index.c:389-408
+static mm_idx_t *idx_gen(mm_bseq_file_s *fp, int w, int k, int b, int flag, int64_t mini_batch_size, uint64_t batch_size) // index.c:389-408
 {
 	if (fp == 0 || fp->rd->eof()) return 0;
 	mm_idx_t *mi = idx_init(w, k, b, flag);
@@ -428,12 +428,16 @@ static mm_idx_t *idx_gen(mm_bseq_file_s *fp, int w, int k, int b, int flag, uint
 	std::vector<uint32_t> S;
 	uint64_t sum_len = 0;
 	FastxRecord r;
-	// the reference reads mini-batches until the running total exceeds batch_size (index.c:322,326): whole mini-batches of
-	// mini_batch_size bases are consumed, so a part ends at the first mini-batch boundary past the limit. With the default
-	// 8G limit a 3 Gbp reference is one part; multi-part indexes (-I) are out of scope here.
-	while (sum_len <= batch_size) {
+	// the reference reads whole mini-batches (mm_bseq_read stops at the first record that brings the mini-batch to mini_batch_size bases,
+	// bseq.c:80-119) and tests the running total only between them (index.c:322,326): a part ends at the first mini-batch boundary
+	// past batch_size
+	const uint64_t mbs = (uint64_t)mini_batch_size < batch_size? (uint64_t)mini_batch_size : batch_size;
+	uint64_t in_mb = 0;
+	for (;;) {
+		if (in_mb >= mbs) { in_mb = 0; if (sum_len > batch_size) break; }
 		int ret = fp->rd->next(r, false, false);
 		if (ret <= 0) break;
+		in_mb += r.seq.size();
 		mm_idx_seq_t s;
 		s.name = (flag & MM_I_NO_NAME)? 0 : strdup(r.name.c_str());
 		s.len = (uint32_t)r.seq.size(), s.offset = sum_len, s.is_alt = 0;
@@ -461,7 +465,7 @@ extern "C" mm_idx_t *mm_idx_build(const char *fn, int w, int k, int flag, int n_
 	mm_bseq_file_s fp;
 	fp.rd = new FastxReader(fn); fp.has_pending = false;
 	if (!fp.rd->ok()) { delete fp.rd; return 0; }
-	mm_idx_t *mi = idx_gen(&fp, w, k, 14, flag, UINT64_MAX);
+	mm_idx_t *mi = idx_gen(&fp, w, k, 14, flag, 1 << 18, UINT64_MAX); // index.c:417
 	delete fp.rd;
 	return mi;
 }
@@ -632,7 +636,7 @@ extern "C" mm_idx_t *mm_idx_reader_read(mm_idx_reader_t *r, int n_threads) // in
 		mi = mm_idx_load(r->fp.idx);
 		if (mi && mm_verbose >= 2 && (mi->k != r->opt.k || mi->w != r->opt.w || (mi->flag&MM_I_HPC) != (r->opt.flag&MM_I_HPC)))
 			fprintf(stderr, "[WARNING]\033[1;31m Indexing parameters (-k, -w or -H) overridden by parameters used in the prebuilt index.\033[0m\n");
-	} else mi = idx_gen(r->fp.seq, r->opt.w, r->opt.k, r->opt.bucket_bits, r->opt.flag, r->opt.batch_size);
+	} else mi = idx_gen(r->fp.seq, r->opt.w, r->opt.k, r->opt.bucket_bits, r->opt.flag, r->opt.mini_batch_size, r->opt.batch_size);
 	if (mi) {
 		if (r->fp_out) mm_idx_dump(r->fp_out, mi);
 		mi->index = r->n_parts++;

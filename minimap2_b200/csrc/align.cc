@@ -140,7 +140,7 @@ struct Driver {
 		return true;
 	}
 
-	const uint8_t *qptr(int rev, int qs) const { return ra.qseq[rev] + qs; }
+	const uint8_t *qptr(int rev, int qs) const { ra.ensure_qseq(); return ra.qseq[rev] + qs; }
 	void get_tseq(uint32_t rid, int st, int en, std::vector<uint8_t> &buf, int t_rc = 0) const { // mm_idx_getseq2 (index.c:192-196)
 		HpScope hp_(HP_TSEQ);
 		buf.resize((en > st? en - st : 0) + 16); // 16 bytes of slack: update_extra compares 16-byte blocks
@@ -476,6 +476,7 @@ struct Driver {
 	}
 	void adjust_minier(const m128 *a, int32_t *r, int32_t *q) const { // align.c:418-433
 		if (mi->flag & MM_I_HPC) {
+			ra.ensure_qseq();
 			const uint8_t *qs = ra.qseq[a->x >> 63];
 			int i, c;
 			*q = (int32_t)a->y;
@@ -736,8 +737,8 @@ struct Driver {
 				Seg s; s.rev = qrev, s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0, s.t_rc = trc;
 				bool ok = align_pair(s, bw1, -1, opt->zdrop, sflag | MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez); // first pass
 				if (ok) { // results that are available are consumed even if an earlier call is pending: this surfaces second-pass jobs one wave earlier
-					const uint8_t *qseq = qptr(qrev, qs);
 					const bool have_zd = ez.zd_max >= 0 && !ez.zdropped;
+					const uint8_t *qseq = have_zd? nullptr : qptr(qrev, qs); // the host only scans the bases itself when the kernel did not
 					if (!have_zd) get_tseq(rid, rs, re, tseq, trc);
 					zdrop_code = test_zdrop(s, qseq, tseq.data(), ez.n_cigar, ez.cigar, have_zd? &ez : nullptr);
 					if (zdrop_code > 0) ok = align_pair(s, bw1, -1, zdrop_code == 2? opt->zdrop_inv : opt->zdrop, sflag, &ez); // second pass

@@ -66,6 +66,15 @@ struct ReadAlign {          // per-read alignment working set (lives across wave
 	int qlen = 0;
 	int64_t q_dev_off = 0;  // offset of this read's first base in the device query array
 	const uint8_t *qseq[2] = {nullptr, nullptr}; // nt4 forward / reverse complement (align.c:1056-1061), slices of a pooled buffer
+	// The two copies are made on first use: with the device tail on, only rare host paths read query bases (z-drop scan of a job the
+	// packed kernel did not take, inversion probes, HPC seed adjustment), so most reads never pay for them.
+	const char *raw_seq = nullptr; uint8_t *qbuf = nullptr; mutable bool qseq_ready = false;
+	void ensure_qseq() const {
+		if (qseq_ready || !qbuf) return;
+		uint8_t *q0 = qbuf, *q1 = qbuf + qlen;
+		for (int i = 0; i < qlen; ++i) { const uint8_t c = mmx_nt4((uint8_t)raw_seq[i]); q0[i] = c, q1[qlen - 1 - i] = c < 4? 3 - c : 4; }
+		qseq_ready = true;
+	}
 	std::vector<KswKey> keys;      // job cache: keys[i] -> done_idx[i] (-1: requested, not delivered yet); ~50-100 entries, linear probe
 	std::vector<int> done_idx;
 	std::vector<KswDone> done;

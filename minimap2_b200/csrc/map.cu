@@ -525,20 +525,14 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 	});
 
 	lap("stage2 host hits");
-	if (with_cigar) { // nt4 forward / reverse-complement copies of the reads that will be aligned (align.c:1056-1061)
-		static uint8_t lut[256]; static bool lut_ok = false;
-		if (!lut_ok) { for (int i = 0; i < 256; ++i) lut[i] = mmx_nt4((uint8_t)i); lut_ok = true; }
-		parallel_for(n, n_threads, [&](int64_t j, int) {
+	if (with_cigar) { // nt4 forward / reverse-complement copies of the reads (align.c:1056-1061): room is set aside, the copies are made on first use
+		for (int j = 0; j < n; ++j) {
 			ReadState &r = rs[live[j]];
-			if (!r.ra) return;
-			uint8_t *q0 = bb.qseq_pool.data() + 2 * off[j], *q1 = q0 + r.qlen;
-			const uint8_t *sq = (const uint8_t*)r.seq;
-			for (int i = 0; i < r.qlen; ++i) {
-				const uint8_t c = lut[sq[i]];
-				q0[i] = c, q1[r.qlen - 1 - i] = c < 4? 3 - c : 4;
-			}
-			r.ra->qseq[0] = q0, r.ra->qseq[1] = q1;
-		});
+			if (!r.ra) continue;
+			uint8_t *q0 = bb.qseq_pool.data() + 2 * off[j];
+			r.ra->raw_seq = r.seq, r.ra->qbuf = q0, r.ra->qseq_ready = false;
+			r.ra->qseq[0] = q0, r.ra->qseq[1] = q0 + r.qlen;
+		}
 	}
 	lap("stage2 qseq encode");
 	// ---------------- stage 3: alignment waves ----------------

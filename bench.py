@@ -323,7 +323,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     # host worker pool per rank: half of this rank's share of the logical CPUs (the group threads that feed the GPU need idle cores)
-    os.environ.setdefault("MM_B200_HOST_THREADS", str(max(8, n_threads_all // (2 * max(1, world)))))
+    # host worker pool per rank: half of the logical CPUs for one rank (the scheduler's group threads must never wait for a core), three
+    # quarters of the rank's share when several ranks divide the box (the host work per rank does not shrink with the rank count)
+    os.environ.setdefault("MM_B200_HOST_THREADS", str(n_threads_all // 2 if world <= 1 else max(8, (3 * n_threads_all) // (4 * world))))
     import minimap2_b200 as mb  # noqa: F401
     from minimap2_b200 import api
     L = api._setup()

@@ -111,3 +111,26 @@ def test_strand_restricted(tmp_path, strand):
     synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
     synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
     compare(["-x", "map-ont", "-c", strand, rf, qf])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("cfg", [dict(opts=["-x", "map-ont", "-c"], glen=20_000_000, n=1500, rlen=8000, err=0.10, rep=0.1, chim=0.05, sam=False),
+                                 dict(opts=["-x", "map-hifi", "-a"], glen=20_000_000, n=1000, rlen=12000, err=0.005, rep=0.1, chim=0.02, sam=True),
+                                 dict(opts=["-x", "ava-ont"], glen=1_500_000, n=800, rlen=6000, err=0.08, rep=0.0, chim=0.0, sam=False)])
+def test_scheduler_scale(tmp_path, cfg):
+    """Batches large enough (>= 768 reads and >= 4 Mbases) for the scheduler to cut them into its 12 concurrent read groups -- the
+    configuration the benchmark runs in: per-group streams and arenas, the device-slot gate, the shared host pool, K4 per group.
+    Every output line must still equal the reference's, in input order."""
+    contigs = synth.random_genome(cfg["glen"], 11, n_contigs=5, repeat_frac=cfg["rep"])
+    reads = synth.make_reads(contigs, cfg["n"], cfg["rlen"], cfg["err"], 211, chimeric_frac=cfg["chim"])
+    rf, qf = str(tmp_path / "ref.fa"), str(tmp_path / "reads.fa")
+    synth.write_fasta(rf, ["chr%d" % i for i in range(len(contigs))], contigs)
+    synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
+    ava = cfg["opts"][-1] == "ava-ont"
+    ref = run(O.REF_BIN, ["-t", "32"] + cfg["opts"] + ([qf, qf] if ava else [rf, qf]))
+    got = run(MINE, ["-t", "16"] + cfg["opts"] + ([qf, qf] if ava else [rf, qf]))
+    if cfg["sam"]:
+        ref = [l for l in ref if not l.startswith("@PG")]; got = [l for l in got if not l.startswith("@PG")]
+    assert len(ref) == len(got) and len(ref) >= cfg["n"] * 0.5, (len(ref), len(got))
+    for i, (a, b) in enumerate(zip(ref, got)):
+        assert a == b, "line %d differs:\nref: %s\ngot: %s" % (i, a[:600], b[:600])

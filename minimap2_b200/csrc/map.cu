@@ -261,16 +261,16 @@ GroupCtx *g_groups[MAX_GROUPS] = {nullptr};
 std::mutex g_group_mu;
 
 
-void unsupported_check(const mm_idx_t *mi, const mm_mapopt_t *opt)
+// false (after a message) for modes this build does not implement: the API calls then return an error / no hits instead of mapping
+// with different semantics -- there is no CPU fallback, and a library must not take the caller's process down for an option
+bool supported_mode(const mm_idx_t *mi, const mm_mapopt_t *opt)
 {
 	const char *what = nullptr;
 	if (opt->flag & (MM_F_SR | MM_F_SR_RNA)) what = "short-read mode (-x sr / splice:sr)";
 	else if ((opt->flag & MM_F_QSTRAND) && (!(opt->flag & MM_F_NO_INV) || (opt->flag & (MM_F_SPLICE | MM_F_OUT_SAM)) || (mi->flag & MM_I_HPC)))
 		what = "query-strand mode without MM_F_NO_INV (main.c:252 sets both), or combined with splice / SAM / HPC (mm_check_opt rejects those)";
-	if (what) {
-		fprintf(stderr, "[ERROR] minimap2_b200: %s is not implemented in this build; refusing to run (no CPU fallback)\n", what);
-		abort();
-	}
+	if (what) fprintf(stderr, "[ERROR] minimap2_b200: %s is not implemented in this build; refusing to map (no CPU fallback)\n", what);
+	return what == nullptr;
 }
 
 } // namespace
@@ -956,7 +956,10 @@ extern "C" int mm_map_batch(const mm_idx_t *mi, int n_reads, const int *qlens, c
 	static std::mutex batch_mu; // the scheduler groups (streams, arenas) are process-wide: concurrent callers take turns
 	std::lock_guard<std::mutex> batch_lk(batch_mu);
 	g_batch_t0 = realtime();
-	unsupported_check(mi, opt);
+	if (!supported_mode(mi, opt)) { // mm_map / mm_map_frag report no hits, mm_map_file returns the error (main.c:389 exits on it)
+		for (int i = 0; i < n_reads; ++i) { n_regs_out[i] = 0, regs_out[i] = nullptr; if (rep_len_out) rep_len_out[i] = 0; }
+		return -1;
+	}
 	const bool rechain = opt->max_occ > opt->mid_occ && !(opt->flag & MM_F_RMQ); // map.c:293
 	if (!rechain) {
 		const MapPass first = { opt->mid_occ, true, nullptr };
@@ -1131,6 +1134,7 @@ void format_reads(std::string &out, FileBatch &fb, int lo, int hi, const mm_idx_
 extern "C" int mm_map_file_frag(const mm_idx_t *idx, int n_segs, const char **fn, const mm_mapopt_t *opt, int n_threads)
 {
 	if (n_segs != 1) { fprintf(stderr, "[ERROR] minimap2_b200: multi-file (paired) input is not implemented\n"); return -1; }
+	if (!supported_mode(idx, opt)) return -1;
 	FastxReader rd(fn[0]);
 	if (!rd.ok()) {
 		if (mm_verbose >= 1) fprintf(stderr, "ERROR: failed to open file '%s'\n", fn[0]);

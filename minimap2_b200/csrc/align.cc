@@ -90,11 +90,17 @@ struct Driver {
 		return k;
 	}
 
-	// cache lookup; on a miss the job is queued for the GPU and false is returned
-	bool fetch(const KswKey &k, Ez *ez) {
+	// cache lookup; on a miss the job is queued for the GPU and false is returned. slot_out (optional) receives the job's cache slot.
+	bool fetch(const KswKey &k, Ez *ez, int *slot_out = nullptr) {
 		HpScope hp_(HP_FETCH);
 		int slot = ra.find(k);
+		if (slot_out) *slot_out = slot >= 0? slot : (int)ra.keys.size();
+		return fetch_slot(slot, &k, ez);
+	}
+	// the same for a job whose slot is known (k may be null then)
+	bool fetch_slot(int slot, const KswKey *kp, Ez *ez) {
 		if (slot >= 0 && ra.done_idx[slot] >= 0) {
+			ra.hint = (size_t)slot + 1;
 			const KswDone &d = ra.done[ra.done_idx[slot]];
 			ez->max = d.r.max, ez->zdropped = d.r.zdropped, ez->max_q = d.r.max_q, ez->max_t = d.r.max_t;
 			ez->mqe = d.r.mqe, ez->mqe_t = d.r.mqe_t, ez->mte = d.r.mte, ez->mte_q = d.r.mte_q;
@@ -104,6 +110,7 @@ struct Driver {
 			return true;
 		}
 		if (slot < 0) {
+			const KswKey &k = *kp;
 			ra.keys.push_back(k); ra.done_idx.push_back(-1);
 			mmb_ksw_job_t j;
 			j.q_start = k.q_start, j.t_start = k.t_start, j.q_step = k.q_step, j.t_step = k.t_step;
@@ -119,7 +126,8 @@ struct Driver {
 	// mm_align_pair (align.c:336-368). Single-affine scoring (q == q2, e == e2: ksw_extz2_sse, align.c:360-361) runs the same
 	// dual-affine kernels with both gap terms equal: on every flag combination align.c uses, ksw_extz2_sse(q,e) and
 	// ksw_extd2_sse(q,e,q,e) return identical ksw_extz_t and CIGARs (tests/test_oracle_vs_ref.py::test_extz2_is_extd2_with_equal_gaps).
-	bool align_pair(const Seg &s, int w, int end_bonus, int zdrop, int ksw_flag, Ez *ez) {
+	bool align_pair(const Seg &s, int w, int end_bonus, int zdrop, int ksw_flag, Ez *ez, int *slot = nullptr) {
+		if (slot && *slot >= 0) { HpScope hp_(HP_FETCH); return fetch_slot(*slot, nullptr, ez); } // planned job, requested by an earlier replay
 		if (opt->transition != 0 && opt->b != opt->transition) ksw_flag |= MMB_KSW_GENERIC_SC;
 		if (opt->flag & MM_F_SPLICE) { // ksw_exts2 (align.c:352-355): the splice-model bits travel in the job flag
 			ksw_flag |= MMB_JOB_SPLICE;
@@ -130,7 +138,7 @@ struct Driver {
 			ez->zdropped = 1;
 			return true;
 		}
-		return fetch(make_key(s, w, zdrop, end_bonus, ksw_flag), ez);
+		return fetch(make_key(s, w, zdrop, end_bonus, ksw_flag), ez, slot);
 	}
 
 	bool ll_i16(const Seg &s, int *score, int *q_off, int *t_off) { // ksw_ll_qinit + ksw_ll_i16
@@ -635,18 +643,30 @@ struct Driver {
 		if (bw_long < bw) bw_long = bw;
 		const bool is_splice = (opt->flag & MM_F_SPLICE) != 0;
 		int sflag = 0; // KSW_EZ_SPLICE_* for every ksw call of this region
-		if (!(opt->flag & MM_F_NO_END_FLT)) {
-			if (is_splice) { if (!fix_bad_ends_splice(r, a, &as1, &cnt1)) return false; } // the probe is pending: nothing below can be planned yet
-			else fix_bad_ends(r, a, opt->bw, opt->min_chain_score * 2, &as1, &cnt1);
-		} else as1 = r->as, cnt1 = r->cnt;
 		if (is_splice) {
 			if (splice_flag & MM_F_SPLICE_FOR) sflag |= rev? MMB_KSW_SPLICE_REV : MMB_KSW_SPLICE_FOR;
 			if (splice_flag & MM_F_SPLICE_REV) sflag |= rev? MMB_KSW_SPLICE_FOR : MMB_KSW_SPLICE_REV;
 			if (opt->flag & MM_F_SPLICE_FLANK) sflag |= MMB_KSW_SPLICE_FLANK;
 			if (mi->spsc) sflag |= MMB_KSW_SPLICE_SCORE; // align.c:688: junc[] carries splice scores (mm_idx_spsc_get)
 		}
+		// What follows up to the gap-fill list depends on the anchors only (spliced reads: and on the end probes, which are awaited first):
+		// it is computed by the first replay that gets this far and kept in the read's plan list; later replays start at the extensions.
+		static const bool no_plan = getenv("MM_B200_NO_PLAN_CACHE") != nullptr; // development switch: plan every hit in every replay
+		const int32_t key_as = r->as, key_cnt = r->cnt;
+		HlHitPlan *P = nullptr;
+		if (!no_plan) for (HlHitPlan &hp : ra.plans) if (hp.as == key_as && hp.cnt == key_cnt && hp.splice_flag == (splice_flag << 1 | (r->split_inv? 1 : 0))) { P = &hp; break; }
+		HlHitPlan fresh; // used when the hit has no stored plan yet
+		if (P) {
+			as1 = P->as1, cnt1 = P->cnt1, rs = P->rs, qs = P->qs, re = P->re, qe = P->qe, rs0 = P->rs0, qs0 = P->qs0, re0 = P->re0, qe0 = P->qe0;
+			for (const auto &m : P->marks) a[m.first].y |= m.second;
+		} else {
+		if (!(opt->flag & MM_F_NO_END_FLT)) {
+			if (is_splice) { if (!fix_bad_ends_splice(r, a, &as1, &cnt1)) return false; } // the probe is pending: nothing below can be planned yet
+			else fix_bad_ends(r, a, opt->bw, opt->min_chain_score * 2, &as1, &cnt1);
+		} else as1 = r->as, cnt1 = r->cnt;
 		filter_bad_seeds(as1, cnt1, a, 10, 40, opt->max_gap >> 1, 10);
 		filter_bad_seeds_alt(as1, cnt1, a, 30, opt->max_gap >> 1);
+		for (i = 0; i < cnt1; ++i) if (a[as1 + i].y & (MMX_SEED_IGNORE | MMX_SEED_LONG_JOIN)) fresh.marks.emplace_back(as1 + i, a[as1 + i].y & (MMX_SEED_IGNORE | MMX_SEED_LONG_JOIN));
 		adjust_minier(&a[as1], &rs, &qs);
 		adjust_minier(&a[as1 + cnt1 - 1], &re, &qe);
 		assert(cnt1 > 0);
@@ -712,11 +732,30 @@ struct Driver {
 			if (qe0 - r->qe > max_ext) qe0 = r->qe + max_ext;
 		}
 		assert(re0 > rs0);
+			// the gap fills (align.c:803-813): anchor pairs far enough apart, long joins, the last anchor
+			fresh.as = key_as, fresh.cnt = key_cnt, fresh.splice_flag = splice_flag << 1 | (r->split_inv? 1 : 0);
+			fresh.as1 = as1, fresh.cnt1 = cnt1, fresh.rs = rs, fresh.qs = qs, fresh.re = re, fresh.qe = qe, fresh.rs0 = rs0, fresh.qs0 = qs0, fresh.re0 = re0, fresh.qe0 = qe0;
+			{
+				int32_t prs = rs, pqs = qs, pre = re, pqe = qe;
+				for (i = 1; i < cnt1; ++i) {
+					if ((a[as1 + i].y & (MMX_SEED_IGNORE | MMX_SEED_TANDEM)) && i != cnt1 - 1) continue;
+					adjust_minier(&a[as1 + i], &pre, &pqe);
+					if (i == cnt1 - 1 || (a[as1 + i].y & MMX_SEED_LONG_JOIN) || (pqe - pqs >= opt->min_ksw_len && pre - prs >= opt->min_ksw_len)) {
+						HlFill f;
+						f.i = i, f.qs = pqs, f.qe = pqe, f.rs = prs, f.re = pre, f.slot = -1;
+						f.bw1 = (a[as1 + i].y & MMX_SEED_LONG_JOIN)? (pqe - pqs > pre - prs? pqe - pqs : pre - prs) : bw_long;
+						fresh.fills.push_back(f);
+						prs = pre, pqs = pqe;
+					}
+				}
+			}
+			if (!no_plan) { ra.plans.push_back(std::move(fresh)); P = &ra.plans.back(); } else P = &fresh;
+		} // planning
 
 		// left extension (align.c:779-799)
 		if (qs > 0 && rs > 0) {
 			Seg s; s.rev = qrev, s.qs = qs0, s.qlen = qs - qs0, s.q_reversed = 1, s.rid = rid, s.rs = rs0, s.tlen = rs - rs0, s.t_reversed = 1, s.t_rc = trc;
-			bool ok = align_pair(s, bw, opt->end_bonus, r->split_inv? opt->zdrop_inv : opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY | MMB_KSW_RIGHT | MMB_KSW_REV_CIGAR, &ez);
+			bool ok = align_pair(s, bw, opt->end_bonus, r->split_inv? opt->zdrop_inv : opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY | MMB_KSW_RIGHT | MMB_KSW_REV_CIGAR, &ez, &P->slot_left);
 			if (ok) {
 				if (ez.n_cigar > 0) { add_cigar(r, ez); r->p->dp_score += ez.max; }
 				rs1 = rs - (ez.reach_end? ez.mqe_t + 1 : ez.max_t + 1);
@@ -727,15 +766,15 @@ struct Driver {
 		if (!pending) assert(qs1 >= 0 && rs1 >= 0);
 
 		// gap filling (align.c:803-872)
-		for (i = 1; i < cnt1; ++i) {
-			if ((a[as1 + i].y & (MMX_SEED_IGNORE | MMX_SEED_TANDEM)) && i != cnt1 - 1) continue;
-			adjust_minier(&a[as1 + i], &re, &qe);
+		for (size_t fk = 0; fk < P->fills.size(); ++fk) {
+			HlFill &F = P->fills[fk];
+			i = F.i, qs = F.qs, qe = F.qe, rs = F.rs, re = F.re;
 			re1 = re, qe1 = qe;
-			if (i == cnt1 - 1 || (a[as1 + i].y & MMX_SEED_LONG_JOIN) || (qe - qs >= opt->min_ksw_len && re - rs >= opt->min_ksw_len)) {
-				int j, bw1 = bw_long, zdrop_code;
-				if (a[as1 + i].y & MMX_SEED_LONG_JOIN) bw1 = qe - qs > re - rs? qe - qs : re - rs;
+			{
+				int j, zdrop_code;
+				const int bw1 = F.bw1;
 				Seg s; s.rev = qrev, s.qs = qs, s.qlen = qe - qs, s.q_reversed = 0, s.rid = rid, s.rs = rs, s.tlen = re - rs, s.t_reversed = 0, s.t_rc = trc;
-				bool ok = align_pair(s, bw1, -1, opt->zdrop, sflag | MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez); // first pass
+				bool ok = align_pair(s, bw1, -1, opt->zdrop, sflag | MMB_KSW_APPROX_MAX | MMB_JOB_ZDROP, &ez, &F.slot); // first pass
 				if (ok) { // results that are available are consumed even if an earlier call is pending: this surfaces second-pass jobs one wave earlier
 					const bool have_zd = ez.zd_max >= 0 && !ez.zdropped;
 					const uint8_t *qseq = have_zd? nullptr : qptr(qrev, qs); // the host only scans the bases itself when the kernel did not
@@ -772,7 +811,7 @@ struct Driver {
 		// right extension (align.c:874-890)
 		if (!dropped && qe < qe0 && re < re0) {
 			Seg s; s.rev = qrev, s.qs = qe, s.qlen = qe0 - qe, s.q_reversed = 0, s.rid = rid, s.rs = re, s.tlen = re0 - re, s.t_reversed = 0, s.t_rc = trc;
-			bool ok = align_pair(s, bw, opt->end_bonus, opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY, &ez);
+			bool ok = align_pair(s, bw, opt->end_bonus, opt->zdrop, sflag | MMB_KSW_EXTZ_ONLY, &ez, &P->slot_right);
 			if (ok) {
 				if (ez.n_cigar > 0) { add_cigar(r, ez); r->p->dp_score += ez.max; }
 				re1 = re + (ez.reach_end? ez.mqe_t + 1 : ez.max_t + 1);

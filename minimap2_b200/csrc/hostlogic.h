@@ -60,6 +60,18 @@ struct HlFinHit {            // a hit whose CIGAR assembly / mm_fix_cigar / mm_u
 	int32_t job_first, n_jobs;
 	uint32_t n_cig_max;      // sum of the pieces' operation counts (upper bound of the final count)
 };
+// What mm_align1 decides from the anchors alone (align.c:693-813: end filters, seed filters, the DP window, which anchor pairs get a
+// gap fill), kept per hit across the replays of a read: a later replay goes straight to consuming results. slot = the job's index in
+// the read's job cache once it has been requested (-1: not yet).
+struct HlFill { int32_t i, qs, qe, rs, re, bw1, slot; };
+struct HlHitPlan {
+	int32_t as, cnt; int64_t splice_flag;                       // identity of the hit (anchor range after mm_squeeze_a) and the transcript-strand round
+	int32_t as1, cnt1, rs, qs, re, qe, rs0, qs0, re0, qe0;
+	int32_t slot_left = -1, slot_right = -1;
+	std::vector<HlFill> fills;
+	std::vector<std::pair<int32_t, uint64_t>> marks; // IGNORE / LONG_JOIN bits the seed filters put on the hit's anchors: put back when the plan is
+	                                                  // reused, because a hit split off this one later is planned from the marked anchors (align.c:454-525)
+};
 struct HlFinOut { int32_t n_cigar, blen, mlen, n_ambi, dp_max, qshift, tshift, status, is_spliced, pad[3]; }; // = FinOut (pipeline.h)
 
 struct ReadAlign {          // per-read alignment working set (lives across waves; pooled across batches, so the vectors keep their capacity)
@@ -85,8 +97,9 @@ struct ReadAlign {          // per-read alignment working set (lives across wave
 	bool defer_abort = false;        // out: the replay reached a step that needs a hit's final coordinates (inversion probe): redo it with defer off
 	std::vector<HlFinHit> fin_hits;  // out (defer): the hits to finalize, in driver order, and their pieces
 	std::vector<HlFinJob> fin_jobs;
+	std::vector<HlHitPlan> plans;    // per-hit plans of this read (see HlHitPlan); cleared with the job cache
 	mutable size_t hint = 0;         // a replay asks for its jobs in the order the previous one did: search from the last hit on
-	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); fin_hits.clear(); fin_jobs.clear(); incomplete = defer = defer_abort = false; hint = 0; }
+	void reset() { keys.clear(); done_idx.clear(); done.clear(); want.clear(); want_slot.clear(); fin_hits.clear(); fin_jobs.clear(); plans.clear(); incomplete = defer = defer_abort = false; hint = 0; }
 	int find(const KswKey &k) const { // keys are unique (a key is added only after a miss)
 		const size_t n = keys.size();
 		for (size_t c = 0, i = hint < n? hint : 0; c < n; ++c, i = i + 1 == n? 0 : i + 1)

@@ -322,7 +322,6 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    # host worker pool per rank: half of this rank's share of the logical CPUs (the group threads that feed the GPU need idle cores)
     # host worker pool per rank: half of the logical CPUs for one rank (the scheduler's group threads must never wait for a core), three
     # quarters of the rank's share when several ranks divide the box (the host work per rank does not shrink with the rank count)
     os.environ.setdefault("MM_B200_HOST_THREADS", str(n_threads_all // 2 if world <= 1 else max(8, (3 * n_threads_all) // (4 * world))))

@@ -23,6 +23,11 @@ def test_emulated_tail_matches_oracle():
     ctx = _Ctx(C.c_void_p(L.mmb_ctx_create(0)))
     rng = np.random.default_rng(11)
     cases = [T.make_case(rng) for _ in range(300)]
+    for _ in range(12):  # hits spanning several 32-operation chunks and more than 32 pieces: the chunk carries of every stage
+        parts = [T.make_case(rng, low_complexity=bool(rng.integers(0, 2))) for _ in range(int(rng.integers(3, 14)))]
+        q = np.concatenate([p["qseq"] for p in parts]); t = np.concatenate([p["tseq"] for p in parts])
+        pieces = [x for p in parts for x in p["pieces"]]
+        cases.append(dict(read=q, rev=0, qs=0, qseq=q, tseq=t, target=np.concatenate([t, np.zeros(16, np.uint8)]), t0=0, pieces=pieces, qspan=len(q), tspan=len(t)))
     got = T.run_device(ctx, L, cases)
     bad = [i for i, c in enumerate(cases) if not T.same(got[i], T.run_oracle(c))]
     assert not bad, bad[:10]

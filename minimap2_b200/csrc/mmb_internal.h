@@ -26,7 +26,7 @@ struct DevBuf {
 	void *reserve(size_t bytes) {
 		if (bytes > cap) {
 			if (p) MMB_CUDA_CHECK(cudaFree(p));
-			size_t ncap = bytes + (bytes >> 2) + 256;
+			size_t ncap = bytes + (bytes > ((size_t)64 << 20)? bytes >> 3 : bytes >> 2) + 256; // growth headroom: 1/8 for the large arenas (twelve groups own a set each), 1/4 below 64 MB
 			MMB_CUDA_CHECK(cudaMalloc(&p, ncap));
 			cap = ncap;
 		}

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256, KE_MINB) ksw_extd2_kernel(KswArgs A)
 		}
 		const bool with_cigar = !(flag & MMB_KSW_SCORE_ONLY), approx_max = (flag & MMB_KSW_APPROX_MAX) != 0;
 		const bool right = (flag & MMB_KSW_RIGHT) != 0, generic = (flag & MMB_KSW_GENERIC_SC) != 0;
-		if (w < 0) w = tlen > qlen? tlen : qlen;
+		if (SP || w < 0) w = tlen > qlen? tlen : qlen; // ksw_exts2_sse takes no band (ksw2_exts2_sse.c:26-31): the driver's bandwidth is not part of a spliced call
 		const int tlen16 = (tlen + 15) / 16 * 16;
 		int n_col = qlen < tlen? qlen : tlen;
 		n_col = (((n_col < w + 1? n_col : w + 1) + 15) / 16 + 1) * 16;

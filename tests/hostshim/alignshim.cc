@@ -41,6 +41,15 @@ static KswDone run_job(const mm_mapopt_t *opt, const mm_idx_t *mi, const int8_t 
 		if ((j.flag & MMB_JOB_T_COMP) && c < 4) c = 3 - c;
 		t[i] = c;
 	}
+	if (const char *dump = getenv("HS_DUMP_JOBS")) { // debugging aid: the jobs with their sequences, one text record each
+		FILE *fp = fopen(dump, "a");
+		fprintf(fp, "J %d %d %d %d %d %d\n", j.qlen, j.tlen, j.w, j.zdrop, j.end_bonus, j.flag);
+		for (int i = 0; i < j.qlen; ++i) fputc('0' + q[i], fp);
+		fputc('\n', fp);
+		for (int i = 0; i < j.tlen; ++i) fputc('0' + t[i], fp);
+		fputc('\n', fp);
+		fclose(fp);
+	}
 	KswDone d;
 	memset(&d, 0, sizeof(d));
 	d.r.zd_max = -1; // the scan of mm_test_zdrop is left to the driver (host path)

@@ -420,3 +420,17 @@ def test_mmi_files_are_interchangeable(emu_cli, tmp_path):
     assert out == exp
     out = subprocess.run([emu_cli, "-t", "2", "-c", theirs, os.path.join(data, "MT-orang.fa")], check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=1200).stdout.decode().splitlines()
     assert out == exp
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="oracle/_ref not built")
+def test_emulated_spliced_extension_ignores_the_band(emu_cli):
+    """ksw_exts2_sse takes no band (ksw2_exts2_sse.c:26-31). With -G 500 the driver's bandwidth (751) is smaller than the window of a right
+    extension that runs on through a 766-bp intron; the spliced kernel used to clip the DP to that band and end the hit early (found by
+    tests/cuda_emu/fuzz_cli.py --splice, seed 6009)."""
+    data = os.path.join(GOLD, "data")
+    args = ["-t", "3", "-x", "splice", "-c", "--MD", "-C", "5", "-G", "500", os.path.join(data, "splice_G500_ref.fa"), os.path.join(data, "splice_G500_q.fa")]
+    got = subprocess.run([emu_cli] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, MM_B200_GROUPS="1"), timeout=1200)
+    ref = subprocess.run([O.REF_BIN] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert got.returncode == 0, got.stderr.decode()[-1000:]
+    assert got.stdout.decode().splitlines() == ref.stdout.decode().splitlines()
+    assert any("766N" in l for l in ref.stdout.decode().splitlines())

@@ -152,7 +152,7 @@ def check_splice_jobs(emu, rng, models, n_jobs, max_exons, with_junc=False, with
             if rng.random() < 0.1:
                 q[rng.integers(0, len(q))] = 4
             base = int(rng.choice([0, APPROX, EXT, EXT | RIGHT | REVC, RIGHT]))
-            pairs.append((q, t)); params.append(dict(w=-1, zdrop=int(rng.choice([-1, 200])), end_bonus=int(rng.choice([-1, 10])), flag=base | int(rng.choice([SPF, SPR])) | model | JOB_SPLICE))
+            pairs.append((q, t)); params.append(dict(w=[-1, 17, 300][it % 3], zdrop=int(rng.choice([-1, 200])), end_bonus=int(rng.choice([-1, 10])), flag=base | int(rng.choice([SPF, SPR])) | model | JOB_SPLICE))  # w: ksw_exts2 has no band, whatever bandwidth the driver passes along
         n = len(pairs)
         qcat = np.concatenate([p[0] for p in pairs]); tcat = np.concatenate([p[1] for p in pairs])
         jobs = (KswJob * n)(); qo = to = tot = 0

@@ -701,7 +701,7 @@ static int map_group(GroupCtx &G, const mm_idx_t *mi, int n_reads, const int *ql
 				});
 				// run in chunks to bound the device result buffers; results land in pinned host memory that stays alive until
 				// the end of the batch, so per-read caches just point into it
-				const int64_t CH = 1 << 20;
+				static const int64_t CH = getenv("MM_B200_JOB_CHUNK")? std::max(1, atoi(getenv("MM_B200_JOB_CHUNK"))) : 1 << 20; // test hook: tiny chunks exercise the multi-chunk bookkeeping
 				mmb_ksw_res_t *res = bb.h_res.as<mmb_ksw_res_t>((size_t)n_jobs);
 				// CIGAR arena estimate per job: (qlen+tlen)/2 + 8 operations covers every realistic alignment, the true bound is qlen+tlen
 				// (alternating 1I1D); an overflow is recovered below by rerunning the chunk with the exact size the kernels reported

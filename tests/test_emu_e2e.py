@@ -245,6 +245,7 @@ def emu_runs(emu_cli, tmp_path_factory):
     for name in GOLDEN:
         jobs[name] = (cases()[name], data, None)
     jobs["cig_overflow"] = (cases()["x3s_paf_cigar"], data, None, {"MM_B200_CIG_SHIFT": "6"})
+    jobs["job_chunks"] = (cases()["x3s_paf_cigar"], data, None, {"MM_B200_JOB_CHUNK": "7"})
     if HAVE_REF:
         jobs["splice"] = (_splice_inputs(d), d, True)
         jobs["splice_junc"] = (_splice_inputs(d, junc=True), d, True)
@@ -287,6 +288,15 @@ def test_emulated_cigar_arena_overflow_is_recovered(emu_runs):
     """the CIGAR arena estimate (qlen+tlen)/2+8 per job is a heuristic; MM_B200_CIG_SHIFT shrinks it 64-fold so that every wave overflows:
     the chunk is rerun with the size the kernels reported and the host staging buffer grows (it used to abort: ADVICE round 1)"""
     r = emu_runs["cig_overflow"]
+    assert r["rc"] == 0, r["err"]
+    exp = open(os.path.join(GOLD, "expected", "x3s_paf_cigar.txt")).read().splitlines()
+    assert r["out"] == exp
+
+
+def test_emulated_many_job_chunks(emu_runs):
+    """an alignment wave larger than the device result buffers runs in chunks (2^20 jobs); MM_B200_JOB_CHUNK=7 forces dozens of chunks per
+    wave: per-chunk CIGAR arenas, their device addresses in the job cache, and K4 stitching pieces that live in different arenas"""
+    r = emu_runs["job_chunks"]
     assert r["rc"] == 0, r["err"]
     exp = open(os.path.join(GOLD, "expected", "x3s_paf_cigar.txt")).read().splitlines()
     assert r["out"] == exp

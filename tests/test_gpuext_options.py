@@ -161,3 +161,12 @@ def test_sdust_masking(tmp_path):
     synth.write_fasta(qf, ["read%d" % i for i in range(len(reads))], reads)
     assert compare(["-c", "-T", "20", rf, qf]) >= 280
     compare(["-x", "map-ont", "-T", "12", rf, qf])
+
+
+@pytest.mark.skipif(not os.path.exists(O.REF_BIN), reason="oracle/_ref not built")
+def test_spliced_extension_ignores_the_band():
+    """-x splice -G 500: the driver's bandwidth (751) is narrower than the window of a right extension that runs on through a 766-bp intron;
+    ksw_exts2_sse takes no band (ksw2_exts2_sse.c:26-31). Device counterpart of tests/test_emu_e2e.py::test_emulated_spliced_extension_ignores_the_band
+    (added after the round's last device session: first device run pending)."""
+    n = compare(["-x", "splice", "-c", "--MD", "-C", "5", "-G", "500", os.path.join(DATA, "splice_G500_ref.fa"), os.path.join(DATA, "splice_G500_q.fa")])
+    assert n == 3
